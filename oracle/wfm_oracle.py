@@ -1,0 +1,579 @@
+"""CPU oracle for the microTiPi widefield PSF path  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy restatement of the *live* ("para") branches of the
+reference's ``WideFieldModel`` (WFM = src/microTiPi/epifluorescence/
+WideFieldModel.java) and of ``Zernike.java``.  It is the checker for the CUDA
+path; nothing in the product (``microtipi_b200/``) may import it.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs use it.
+
+PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures and
+cannot be compiled here (no JDK; its arithmetic lives in the un-vendored,
+un-pinned dependencies JTransforms 3.x ``org.jtransforms.fft.DoubleFFT_2D`` and
+TiPi ``mitiv.*``).  The oracle is therefore pinned only by known-answer tests
+derived from the reference's own formulas (tests/test_oracle.py): Parseval
+energy, focal-plane identity, symmetry, conjugate storage, finite-difference
+gradient checks, linearity, z-shard invariance and an extended-precision direct
+DFT adjudicator.
+
+FFT stand-in: ``DoubleFFT_2D(Nx,Ny).complexForward`` is the in-place,
+unnormalised, e^{-2 pi i jk/N} transform on both axes == ``scipy.fft.fft2``.
+
+Array layout (TiPi arrays are first-index-fastest):  pixel ``in = ix + Nx*iy``
+(WFM:385,468,594).  numpy arrays here are C-ordered with shapes
+``psf[Nz, Ny, Nx]`` and ``cpx[Nz, Ny, Nx, 2]`` so that ``.ravel()`` reproduces
+the reference flat order ``ix + Nx*(iy + Ny*iz)`` and ``c + 2*(ix + ...)``.
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+import scipy.fft as sfft
+
+DEUXPI = 2.0 * math.pi  # MicroscopeModel.java:44
+
+DEFOCUS, PHASE, MODULUS = 0, 1, 2  # WFM:113-121
+
+# ----------------------------------------------------------------------------
+# Quirk policy
+# ----------------------------------------------------------------------------
+MODULUS_INTENDED = "intended"              # sum over z (dead sequential branch WFM:710-726)
+MODULUS_REFERENCE_LAST_PLANE = "last_plane"  # live fp64 para behaviour WFM:662-675 (Q1)
+
+
+# ----------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------
+def kappa(n: int) -> np.ndarray:
+    """FFT wrap-around integer frequency: idx > N/2 -> idx-N (strict '>').
+
+    WFM:1460-1481 (computeDefocus), 1040-1061 (apply_J_defocus rx/ry).
+    ``N/2`` is Java integer division."""
+    idx = np.arange(n, dtype=np.int64)
+    return np.where(idx > n // 2, idx - n, idx)
+
+
+def defoc_scale(iz, Nz: int, dz: float):
+    """2*pi*dz*z with z in wrap-around order, strict '>' (WFM:302-309).
+
+    Java evaluates ``DEUXPI*(iz1 - Nz)*dz`` left to right: (DEUXPI*int)*dz."""
+    iz = np.asarray(iz, dtype=np.int64)
+    zi = np.where(iz > Nz // 2, iz - Nz, iz).astype(np.float64)
+    return (DEUXPI * zi) * dz
+
+
+def defoc_depth(iz, Nz: int, dz: float):
+    """``defoc`` of apply_J_defocus: (iz - Nz)*dz or iz*dz (WFM:1220-1229)."""
+    iz = np.asarray(iz, dtype=np.int64)
+    zi = np.where(iz > Nz // 2, iz - Nz, iz).astype(np.float64)
+    return zi * dz
+
+
+def splitmix64_uniform(seed: int, start: int, count: int) -> np.ndarray:
+    """Counter-based uniform(-1,1) doubles: element i depends only on
+    (seed, start+i).  Implemented identically in the CUDA fill kernel
+    (SURVEY.md 8d2), so z-slab shards are reproducible from the global index."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(start, start + count, dtype=np.uint64)
+        z = idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)  # [0,1)
+    return 2.0 * u - 1.0
+
+
+# ----------------------------------------------------------------------------
+# pupil construction  
+# ----------------------------------------------------------------------------
+def compute_mask_pupil(Nx: int, Ny: int, dxy: float, NA: float, lam: float):
+    """WFM:1374-1406.  Returns (mask bool[Ny,Nx], pupil_area)."""
+    radius = NA / lam                                   # WFM:165
+    scale_y = (1.0 / dxy / Ny) ** 2                      # Math.pow(1/dxy/Ny, 2)
+    scale_x = (1.0 / dxy / Nx) ** 2
+    radius2 = radius * radius
+    ny = np.arange(Ny)
+    nx = np.arange(Nx)
+    iy = np.minimum(ny, Ny - ny).astype(np.float64)
+    ix = np.minimum(nx, Nx - nx).astype(np.float64)
+    ry = iy * iy * scale_y
+    rx = ix * ix * scale_x
+    mask = (rx[None, :] + ry[:, None]) < radius2
+    return mask, math.sqrt(float(mask.sum()))
+
+
+def compute_defocus(Nx, Ny, dxy, lambda_ni, deltaX, deltaY, mapPupil, psi_prev=None, mask_prev=None):
+    """WFM:1452-1499.  Only pixels of ``mapPupil`` are touched; elsewhere psi and
+    maskPupil keep their previous value (psi starts at 0, WFM:168)."""
+    lambda_ni2 = lambda_ni * lambda_ni
+    scale_x = 1.0 / (Nx * dxy)
+    scale_y = 1.0 / (Ny * dxy)
+    ry = (scale_y * kappa(Ny).astype(np.float64) - deltaY) ** 2
+    rx = (scale_x * kappa(Nx).astype(np.float64) - deltaX) ** 2
+    q = (lambda_ni2 - rx[None, :]) - ry[:, None]
+    psi = np.zeros((Ny, Nx)) if psi_prev is None else np.array(psi_prev, dtype=np.float64).reshape(Ny, Nx).copy()
+    mask = mapPupil.copy() if mask_prev is None else np.array(mask_prev, dtype=bool).reshape(Ny, Nx).copy()
+    neg = q < 0.0
+    with np.errstate(invalid="ignore"):
+        root = np.sqrt(np.where(neg, 0.0, q))
+    psi[mapPupil] = np.where(neg, 0.0, root)[mapPupil]
+    mask[mapPupil] = (~neg)[mapPupil]
+    return psi, mask
+
+
+def phase_offset(radial: bool) -> int:
+    """Phase coefficient n uses Zernike mode n+3 (n+1 if radial): WFM:1640-1644."""
+    return 1 if radial else 3
+
+
+def set_phase(alpha, Z, mask, radial=False):
+    """WFM:1625-1649: phi = sum_n alpha_n Z_{n+off} on maskPupil, 0 elsewhere.
+    Sequential mul-then-add in n order (Java has no FMA contraction)."""
+    Ny, Nx = mask.shape
+    Npix = Nx * Ny
+    off = phase_offset(radial)
+    phi = np.zeros(Npix)
+    Zf = np.asarray(Z).reshape(-1, Npix)
+    for n, a in enumerate(np.asarray(alpha, dtype=np.float64)):
+        phi = phi + Zf[n + off] * a
+    phi[~mask.ravel()] = 0.0
+    return phi.reshape(Ny, Nx)
+
+
+def set_modulus(beta, Z, mask):
+    """WFM:1588-1610: rho = sum_n Z_n*beta_n*(1/||beta||) on maskPupil."""
+    Ny, Nx = mask.shape
+    Npix = Nx * Ny
+    beta = np.asarray(beta, dtype=np.float64)
+    betaNorm = 1.0 / math.sqrt(float(np.sum(beta * beta)))
+    rho = np.zeros(Npix)
+    Zf = np.asarray(Z).reshape(-1, Npix)
+    for n, b in enumerate(beta):
+        rho = rho + (Zf[n] * b) * betaNorm
+    rho[~mask.ravel()] = 0.0
+    return rho.reshape(Ny, Nx)
+
+
+# ----------------------------------------------------------------------------
+# the hot path  
+# ----------------------------------------------------------------------------
+def _fft2(a, single):
+    if single:
+        return sfft.fft2(a.astype(np.complex64))
+    return sfft.fft2(a)
+
+
+def compute_psf(rho, phi, psi, Nz, dz, single=False, z0=0, nz_local=None, workers=None):
+    """``computePsf`` fp64 para WFM:280-350 (fp32: 209-278).
+
+    Returns (cpx[nz,Ny,Nx,2], psf[nz,Ny,Nx]); ``cpx`` holds conj(FFT2(A)) and
+    ``psf = |a|^2 * 1/(Nx*Ny*Nz)`` with the GLOBAL Nz.  ``z0/nz_local`` select a
+    z-slab (the global Nz still drives PSFnorm and the wrap rule)."""
+    Ny, Nx = rho.shape
+    nzl = Nz - z0 if nz_local is None else nz_local
+    ftype = np.float32 if single else np.float64
+    PSFnorm = ftype(1.0 / (Nx * Ny * Nz))
+    cpx = np.empty((nzl, Ny, Nx, 2), dtype=ftype)
+    psf = np.empty((nzl, Ny, Nx), dtype=ftype)
+    for l in range(nzl):
+        s = float(defoc_scale(z0 + l, Nz, dz))
+        ph = phi + s * psi                                   # WFM:313
+        A = (rho * np.cos(ph)).astype(ftype) + 1j * (rho * np.sin(ph)).astype(ftype)
+        if single:
+            a = sfft.fft2(A.astype(np.complex64), workers=workers)
+        else:
+            a = sfft.fft2(A, workers=workers)
+        re = a.real.astype(ftype)
+        im = a.imag.astype(ftype)
+        cpx[l, :, :, 0] = re
+        cpx[l, :, :, 1] = -im                                 # conjugate, WFM:326
+        psf[l] = (re * re + im * im) * PSFnorm                # WFM:327
+    return cpx, psf
+
+
+def _adjoint_fft(cpx_plane, q_plane, single, workers=None):
+    """B = FFT2(conj(a) * q)  (WFM:907-918).  Forward transform, never inverse."""
+    if single:
+        aq = (cpx_plane[..., 0] * q_plane).astype(np.float32) + 1j * (cpx_plane[..., 1] * q_plane).astype(np.float32)
+        return sfft.fft2(aq.astype(np.complex64), workers=workers)
+    aq = cpx_plane[..., 0] * q_plane + 1j * (cpx_plane[..., 1] * q_plane)
+    return sfft.fft2(aq, workers=workers)
+
+
+def _plane_trig(phi, psi, s):
+    ph = phi + s * psi
+    return np.sin(ph), np.cos(ph)
+
+
+def apply_J_phase(q, cpx, rho, phi, psi, mask, Z, nPhase, Nz, dz, radial=False,
+                  single=False, z0=0, workers=None):
+    """``apply_J_phase`` fp64 para WFM:883-965 (fp32: 746-830).
+
+    g[k] = - sum_z sum_{in in mask} 2*PSFnorm*jin*Z[(k+off)*Npix+in],
+    jin = rho*(B_re sin ph + B_im cos ph).  Post-FFT math is double in both
+    precisions (WFM:791-802)."""
+    Ny, Nx = rho.shape
+    Npix = Nx * Ny
+    nzl = cpx.shape[0]
+    PSFnorm = 1.0 / (Nx * Ny * Nz)
+    off = phase_offset(radial)
+    Zf = np.asarray(Z).reshape(-1, Npix)[off:off + nPhase]
+    m = mask.ravel()
+    g = np.zeros(nPhase)
+    for l in range(nzl):
+        s = float(defoc_scale(z0 + l, Nz, dz))
+        B = _adjoint_fft(cpx[l], q[l], single, workers)
+        sn, cs = _plane_trig(phi, psi, s)
+        jin = rho * (B.real.astype(np.float64) * sn + B.imag.astype(np.float64) * cs)
+        jm = jin.ravel()[m]
+        g -= (2.0 * PSFnorm) * (Zf[:, m] @ jm)
+    return g
+
+
+def apply_J_defocus(q, cpx, rho, phi, psi, mask, Nz, dz, dxy, lambda_ni, deltaX, deltaY,
+                    single=False, z0=0, workers=None, ndefocus=3):
+    """``apply_J_defocus`` fp64 para: prologue WFM:1031-1061, tasks 1201-1288,
+    epilogue 1352-1367.  Reproduces the live result including the missing
+    factor 2 (Q3): d0 = S t*lni*defoc/psi, d1 = +S t*rx*defoc/psi, d2 likewise,
+    t = -2pi*rho*(B_re sin + B_im cos)*PSFnorm."""
+    if ndefocus == 2:
+        raise ValueError("defocus vectors of length 2 hit AIOOBE in the reference (Q4)")
+    Ny, Nx = rho.shape
+    nzl = cpx.shape[0]
+    PSFnorm = 1.0 / (Nx * Ny * Nz)
+    scale_x = 1.0 / (Nx * dxy)
+    scale_y = 1.0 / (Ny * dxy)
+    rx = kappa(Nx).astype(np.float64) * scale_x - deltaX
+    ry = kappa(Ny).astype(np.float64) * scale_y - deltaY
+    d0 = d1 = d2 = 0.0
+    idef_raw = np.zeros_like(psi)                      # idef = 1/psi on maskPupil (WFM:1251)
+    with np.errstate(divide="ignore"):
+        np.divide(1.0, psi, out=idef_raw, where=mask)
+    for l in range(nzl):
+        s = float(defoc_scale(z0 + l, Nz, dz))
+        defoc = float(defoc_depth(z0 + l, Nz, dz))
+        B = _adjoint_fft(cpx[l], q[l], single, workers)
+        sn, cs = _plane_trig(phi, psi, s)
+        t = -DEUXPI * rho * (B.real.astype(np.float64) * sn + B.imag.astype(np.float64) * cs) * PSFnorm
+        t = np.where(mask, t, 0.0)
+        w = defoc * idef_raw
+        o0 = np.sum(t * (idef_raw * lambda_ni * defoc))
+        o1 = -np.sum(t * (rx[None, :] * w))
+        o2 = -np.sum(t * (ry[:, None] * w))
+        d0 += o0
+        d1 -= o1
+        d2 -= o2
+    if ndefocus == 1:
+        return np.array([d0])
+    return np.array([d0, d1, d2])
+
+
+def apply_J_modulus(q, cpx, rho, phi, psi, mask, Z, beta, Nz, dz, single=False, z0=0,
+                    mode=MODULUS_INTENDED, workers=None):
+    """``apply_J_modulus`` fp64 para WFM:566-683.
+
+    Per plane J_z = B_re cos ph - B_im sin ph over ALL pixels (WFM:607-611).
+    mode "intended": JRho[k] = 2*PSFnorm*(sum_z J_z . Z_k)*(1-(beta_k/||beta||)^2)/||beta||
+    (dead sequential branch WFM:710-726; also what fp32 mode follows, Q2).
+    mode "last_plane": live fp64 behaviour -- the ``set`` at WFM:674 overwrites per
+    plane, so only iz = Nz-1 survives (Q1)."""
+    Ny, Nx = rho.shape
+    Npix = Nx * Ny
+    nzl = cpx.shape[0]
+    beta = np.asarray(beta, dtype=np.float64)
+    nM = beta.size
+    PSFnorm = 1.0 / (Nx * Ny * Nz)
+    NBeta = 1.0 / math.sqrt(float(np.sum(beta * beta)))
+    Zf = np.asarray(Z).reshape(-1, Npix)[:nM]
+    J = np.zeros(Npix)
+    for l in range(nzl):
+        iz = z0 + l
+        if mode == MODULUS_REFERENCE_LAST_PLANE and iz != Nz - 1:
+            continue
+        s = float(defoc_scale(iz, Nz, dz))
+        B = _adjoint_fft(cpx[l], q[l], single, workers)
+        sn, cs = _plane_trig(phi, psi, s)
+        J += (B.real.astype(np.float64) * cs - B.imag.astype(np.float64) * sn).ravel()
+    tmp = Zf @ J
+    return 2.0 * PSFnorm * tmp * (1.0 - (beta * NBeta) ** 2) * NBeta
+
+
+# ----------------------------------------------------------------------------
+# Zernike basis  (Zernike.java; TiPi helpers are ASSUMPTIONS, see below)
+# ----------------------------------------------------------------------------
+def zernumero_noll(J: int):
+    """Zernike.java:37-52, Noll index J -> (n, m)."""
+    n1 = (math.sqrt(1 + 8 * J) - 1) / 2
+    n = int(math.floor(n1))
+    if n1 == n:
+        n = n - 1
+    k = (n + 1) * (n + 2) // 2
+    m = int(n - 2 * math.floor((k - J) / 2))
+    return n, m
+
+
+def coeff_radial(n: int, m: int) -> np.ndarray:
+    """Zernike.java:70-90: (-1)^s (n-s)!/(s!(p-s)!(q-s)!) via log-factorial cumsum."""
+    p = (n - m) // 2
+    qq = (n + m) // 2
+    lfact = np.zeros(n + 1)
+    for i in range(1, n + 1):
+        lfact[i] = math.log(i)
+    lfact = np.cumsum(lfact)
+    R = np.zeros(p + 1)
+    for s in range(p + 1):
+        R[s] = math.exp(lfact[n - s] - lfact[s] - lfact[p - s] - lfact[qq - s])
+        if s % 2:
+            R[s] = -R[s]
+    return R
+
+
+def fft_dist(W: int, H: int) -> np.ndarray:
+    """ASSUMPTION (TiPi MathUtils.fftDist1D source unavailable): r[i+j*W] =
+    sqrt(kappa(i)^2 + kappa(j)^2), consistent with WFM:1385-1390."""
+    kx = kappa(W).astype(np.float64)
+    ky = kappa(H).astype(np.float64)
+    return np.sqrt(kx[None, :] ** 2 + ky[:, None] ** 2).ravel()
+
+
+def fft_angle(W: int, H: int) -> np.ndarray:
+    """ASSUMPTION (TiPi MathUtils.fftAngle1D source unavailable): atan2(kappa(j), kappa(i))."""
+    kx = kappa(W).astype(np.float64)
+    ky = kappa(H).astype(np.float64)
+    return np.arctan2(ky[:, None] + 0 * kx[None, :], kx[None, :] + 0 * ky[:, None]).ravel()
+
+
+def zernike_array(nb: int, W: int, H: int, radius: float, normalize=True, radial=False) -> np.ndarray:
+    """Zernike.java:119-288.  Returns Z[nb, H*W]."""
+    WH = W * H
+    r = fft_dist(W, H)
+    theta = fft_angle(W, H)
+    inside = r < radius                                   # strict, Zernike.java:146
+    Z = np.zeros((nb, WH))
+    if radial:
+        nmax = nb + 1
+    else:
+        nmax, _ = zernumero_noll(nb + 1)
+    rP = np.zeros((nmax + 1, WH))
+    rP[0, inside] = 1.0
+    Z[0, inside] = 1.0
+    if nmax >= 1:
+        rP[1, inside] = r[inside] / radius
+    if normalize:
+        Z[0] *= 1.0 / math.sqrt(float(np.sum(Z[0] * Z[0])))
+    kmax = nb if radial else nmax
+    for k in range(2, kmax + 1):
+        if k <= nmax:
+            rP[k] = rP[k - 1] * rP[1]
+    for nz in range(1, nb):
+        if radial:
+            n, m = nz, 0
+        else:
+            n, m = zernumero_noll(nz + 1)
+        R = coeff_radial(n, m)
+        zr = np.zeros(WH)
+        for s in range((n - m) // 2, -1, -1):
+            zr = zr + R[s] * rP[n - 2 * s]
+        if m == 0:
+            Z[nz] = math.sqrt(n + 1) * zr
+        elif (nz + 1) % 2 == 0:
+            Z[nz] = math.sqrt(2 * (n + 1)) * zr * np.cos(m * theta)
+        else:
+            Z[nz] = math.sqrt(2 * (n + 1)) * zr * np.sin(m * theta)
+        if normalize:
+            Z[nz] *= 1.0 / math.sqrt(float(np.sum(Z[nz] * Z[nz])))
+    return Z
+
+
+def gram_schmidt(Z: np.ndarray) -> np.ndarray:
+    """ASSUMPTION (TiPi MathUtils.gram_schmidt_orthonormalization source
+    unavailable; call site WFM:196): in-order modified Gram-Schmidt of the
+    sampled modes under the plain pixel dot product."""
+    Zo = np.array(Z, dtype=np.float64, copy=True)
+    for k in range(Zo.shape[0]):
+        for j in range(k):
+            Zo[k] -= np.dot(Zo[j], Zo[k]) * Zo[j]
+        Zo[k] *= 1.0 / math.sqrt(float(np.dot(Zo[k], Zo[k])))
+    return Zo
+
+
+def compute_zernike(Nzern, Nx, Ny, NA, lam, dxy, radial=False):
+    """WFM:194-197."""
+    radius = NA / lam
+    Z = zernike_array(Nzern, Nx, Ny, radius * dxy * Nx, True, radial)
+    return gram_schmidt(Z)
+
+
+# ----------------------------------------------------------------------------
+# model object: constructor sequencing WFM:154-188 and the PState protocol
+# ----------------------------------------------------------------------------
+class WideFieldModelOracle:
+    """Mirror of the reference class for tests.  Same method names, argument
+    meaning and error behaviour (IllegalArgumentException -> ValueError)."""
+
+    def __init__(self, shape, nPhase, nModulus, NA, lam, ni, dxy, dz, radial=False, single=False,
+                 modulus_mode=MODULUS_INTENDED):
+        Nx, Ny, Nz = shape
+        if Nx != Ny:
+            raise ValueError("Nx should equal Ny")                      # WFM:158-160
+        self.Nx, self.Ny, self.Nz = Nx, Ny, Nz
+        self.dxy, self.dz = dxy, dz
+        self.NA, self.lam, self.ni = NA, lam, ni
+        self.radial, self.single = radial, single
+        self.modulus_mode = modulus_mode
+        self.lambda_ni = ni / lam
+        self.deltaX = self.deltaY = 0.0
+        self.phi = np.zeros((Ny, Nx))
+        self.psi = np.zeros((Ny, Nx))
+        self.PState = 0
+        self.cpx = self.psf = None
+        self.mapPupil, self.pupil_area = compute_mask_pupil(Nx, Ny, dxy, NA, lam)   # WFM:174
+        self.maskPupil = self.mapPupil.copy()
+        self.nModulus = max(1, nModulus)
+        self.nPhase = nPhase
+        self.alpha = None
+        self._setNModulus()                                             # WFM:185
+        self._setNPhase()                                               # WFM:186
+        self.setDefocus([ni / lam, 0.0, 0.0])                           # WFM:187,1562-1564
+
+    # -- sizes ---------------------------------------------------------------
+    def _setNModulus(self):                                             # WFM:1939-1961
+        if self.alpha is None:
+            self.Nzern = self.nModulus
+        else:
+            self.Nzern = max(len(self.alpha) + phase_offset(self.radial), self.nModulus)
+        self.Z = compute_zernike(self.Nzern, self.Nx, self.Ny, self.NA, self.lam, self.dxy, self.radial)
+        beta = np.zeros(self.nModulus)
+        beta[0] = 1.0
+        self.setModulus(beta)
+
+    def _setNPhase(self):                                               # WFM:1899-1914
+        if self.nPhase > 0:
+            self.Nzern = max(self.nPhase + phase_offset(self.radial), self.nModulus)
+            self.Z = compute_zernike(self.Nzern, self.Nx, self.Ny, self.NA, self.lam, self.dxy, self.radial)
+            self.setPhase(np.zeros(self.nPhase))
+        else:
+            self.alpha = None
+
+    # -- setters (each ends in freeMem) ---------------------------------------
+    def setDefocus(self, defoc):                                        # WFM:1510-1534
+        defoc = list(defoc)
+        if len(defoc) == 3:
+            self.deltaX, self.deltaY = defoc[1], defoc[2]
+            self.lambda_ni = defoc[0]
+            self.ni = self.lambda_ni * self.lam
+        elif len(defoc) == 1:
+            self.lambda_ni = defoc[0]
+            self.ni = self.lambda_ni * self.lam
+        else:
+            raise ValueError("bad defocus  parameters")                 # length 2 -> AIOOBE (Q4)
+        self.psi, self.maskPupil = compute_defocus(self.Nx, self.Ny, self.dxy, self.lambda_ni,
+                                                   self.deltaX, self.deltaY, self.mapPupil,
+                                                   self.psi, self.maskPupil)
+        self.freeMem()
+
+    def setPhase(self, alpha):                                          # WFM:1625-1649
+        alpha = np.asarray(alpha, dtype=np.float64)
+        if alpha.size != self.nPhase:
+            raise ValueError("phase parameter does not belong to the right space  ")
+        self.alpha = alpha.copy()
+        self.phi = set_phase(alpha, self.Z, self.maskPupil, self.radial)
+        self.freeMem()
+
+    def setModulus(self, beta):                                         # WFM:1588-1610
+        beta = np.asarray(beta, dtype=np.float64)
+        if beta.size != self.nModulus:
+            raise ValueError("DoubleShapedVector beta does not belong to the modulus space")
+        self.beta = beta.copy()
+        self.rho = set_modulus(beta, self.Z, self.maskPupil)
+        self.freeMem()
+
+    def freeMem(self):                                                  # WFM:1970-1974
+        self.PState = 0
+        self.cpx = self.psf = None
+
+    # -- hot path --------------------------------------------------------------
+    def computePsf(self):                                               # WFM:206-396
+        if self.PState > 0:
+            return
+        self.cpx, self.psf = compute_psf(self.rho, self.phi, self.psi, self.Nz, self.dz, self.single)
+        self.PState = 1
+
+    def getPsf(self):                                                   # WFM:1798-1804
+        if self.PState < 1:
+            self.computePsf()
+        return self.psf
+
+    def get_cpxPsf(self):                                               # WFM:1856-1861
+        if self.PState < 1:
+            self.computePsf()
+        return self.cpx
+
+    def _need_psf(self):
+        # Q5: the reference would NPE on a dirty model; superset behaviour: recompute.
+        if self.PState < 1:
+            self.computePsf()
+
+    def apply_J_phase(self, q):
+        self._need_psf()
+        return apply_J_phase(q, self.cpx, self.rho, self.phi, self.psi, self.maskPupil, self.Z,
+                             self.nPhase, self.Nz, self.dz, self.radial, self.single)
+
+    def apply_J_defocus(self, q):
+        self._need_psf()
+        return apply_J_defocus(q, self.cpx, self.rho, self.phi, self.psi, self.maskPupil, self.Nz,
+                               self.dz, self.dxy, self.lambda_ni, self.deltaX, self.deltaY, self.single)
+
+    def apply_J_modulus(self, q):
+        self._need_psf()
+        return apply_J_modulus(q, self.cpx, self.rho, self.phi, self.psi, self.maskPupil, self.Z,
+                               self.beta, self.Nz, self.dz, self.single, mode=self.modulus_mode)
+
+    def apply_Jacobian(self, q, flag):                                  # WFM:399-409
+        if flag == DEFOCUS:
+            return self.apply_J_defocus(q)
+        if flag == PHASE:
+            return self.apply_J_phase(q)
+        if flag == MODULUS:
+            return self.apply_J_modulus(q)
+        raise ValueError("DoubleShapedVector grad does not belong to any space")
+
+
+# ----------------------------------------------------------------------------
+# extended-precision adjudicator (small N only)
+# ----------------------------------------------------------------------------
+def dft2_longdouble(A: np.ndarray) -> np.ndarray:
+    """Direct O(N^3) 2-D DFT in numpy.longdouble (80-bit on x86): bounds both
+    the GPU and the numpy FFT error for N <= 64."""
+    Ny, Nx = A.shape
+    A = A.astype(np.clongdouble)
+    two_pi = np.longdouble("6.283185307179586476925286766559005768")
+    def dftmat(n):
+        jk = (np.arange(n)[:, None] * np.arange(n)[None, :]) % n
+        ang = -(two_pi * jk.astype(np.longdouble)) / np.longdouble(n)
+        return np.cos(ang) + 1j * np.sin(ang)
+    return dftmat(Ny) @ A @ dftmat(Nx).T
+
+
+def rel_l2(a, b) -> float:
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    d = np.linalg.norm(a - b)
+    n = np.linalg.norm(b)
+    return float(d / n) if n > 0 else float(d)
+
+
+# ----------------------------------------------------------------------------
+# SURVEY 8d2 synthetic inputs
+# ----------------------------------------------------------------------------
+DEFAULTS = dict(NA=1.4, lam=542e-9, ni=1.518, dxy=64.5e-9, dz=160e-9)
+
+
+def synthetic_alpha(nPhase=10, seed=1234, sigma=0.3):
+    return np.random.default_rng(seed).normal(0.0, sigma, nPhase)
+
+
+def synthetic_q(Nx, Ny, Nz, seed=42, z0=0, nz_local=None, single=False):
+    nzl = Nz - z0 if nz_local is None else nz_local
+    q = splitmix64_uniform(seed, z0 * Nx * Ny, nzl * Nx * Ny).reshape(nzl, Ny, Nx)
+    return q.astype(np.float32) if single else q
