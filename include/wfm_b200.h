@@ -1,0 +1,199 @@
+/*
+ * wfm_b200.h -- C ABI of the B200-native widefield PSF model + Jacobians.
+ *
+ * This is the drop-in boundary for ONE path of jplumail/microTiPi: the pupil ->
+ * per-z defocus -> 2-D FFT -> |.|^2 pipeline of WideFieldModel.computePsf and its
+ * adjoint pipeline apply_J_phase / apply_J_defocus / apply_J_modulus.  The
+ * reference has no FFI seam of its own (it is pure Java); every entry point below
+ * names the Java member it replaces so that a `WideFieldModel`-compatible Java
+ * class can bind it through Panama FFM or JNI.
+ *
+ *   WFM = /root/reference/src/microTiPi/epifluorescence/WideFieldModel.java
+ *   MM  = /root/reference/src/microTiPi/microscopy/MicroscopeModel.java
+ *
+ * Conventions
+ *   - Plain C types only.  The caller owns every host pointer; the library copies
+ *     in/out before returning.  Device memory is owned by the handle.
+ *   - Every function returns an int status: WFM_OK (0) or a negative wfm_status.
+ *     Nothing aborts or throws across the ABI.  wfm_last_error() gives the text.
+ *     WFM_ERR_INVALID_ARG corresponds to the reference's IllegalArgumentException
+ *     sites (WFM:159,407,420,1514,1530,1592,1629).
+ *   - A handle is NOT thread-safe (the reference's callers are single threaded,
+ *     PSF_Estimation.java:200-251); distinct handles may be used concurrently.
+ *   - Layout is TiPi's first-index-fastest: pixel in = ix + Nx*iy (WFM:385);
+ *     psf  flat index ix + Nx*(iy + Ny*izl)               (MM:73-76)
+ *     cpx  flat index c + 2*(ix + Nx*(iy + Ny*izl)), c=0 re, c=1 im   (WFM:170,341)
+ *     Z    flat index in + k*Npix, k < nzern                          (WFM:1605)
+ *     where izl is the plane index inside the handle's z-slab [z0, z0+nz_local).
+ *   - precision F64: psf/cpx/q are double.  precision F32 (`single=true`): psf/cpx/q
+ *     are float, pupil trig and all Jacobian reductions stay double (WFM:243-245,
+ *     791-802).  Gradient outputs are always double.
+ *   - There is no CPU fallback: every compute entry point runs CUDA kernels on the
+ *     handle's device and fails with WFM_ERR_CUDA if it cannot.
+ */
+#ifndef WFM_B200_H
+#define WFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define WFM_API __declspec(dllexport)
+#else
+#define WFM_API __attribute__((visibility("default")))
+#endif
+
+typedef struct wfm_model wfm_model; /* opaque */
+
+typedef enum wfm_status {
+    WFM_OK = 0,
+    WFM_ERR_INVALID_ARG = -1, /* IllegalArgumentException in the reference */
+    WFM_ERR_UNSUPPORTED = -2, /* e.g. Nx not a supported power of two */
+    WFM_ERR_STATE = -3,       /* a required setter has not been called yet */
+    WFM_ERR_CUDA = -4,
+    WFM_ERR_NOMEM = -5,
+    WFM_ERR_INTERNAL = -6
+} wfm_status;
+
+typedef enum wfm_precision { WFM_F64 = 0, WFM_F32 = 1 } wfm_precision;
+
+/* WFM:113-123  DEFOCUS=0, PHASE=1, MODULUS=2 */
+typedef enum wfm_param { WFM_DEFOCUS = 0, WFM_PHASE = 1, WFM_MODULUS = 2 } wfm_param;
+
+/* Jacobian selection bits for wfm_apply_jacobian_dev / wfm_apply_j_all */
+#define WFM_J_DEFOCUS 1u
+#define WFM_J_PHASE 2u
+#define WFM_J_MODULUS 4u
+
+/* Quirk Q1: the live fp64 apply_J_modulus keeps only the last plane
+ * (WFM:662-675); the intended behaviour sums over z (WFM:710-726). */
+typedef enum wfm_modulus_mode {
+    WFM_MODULUS_INTENDED = 0,
+    WFM_MODULUS_REFERENCE_LAST_PLANE = 1
+} wfm_modulus_mode;
+
+/* ---- life cycle -------------------------------------------------------------------- */
+
+/* new WideFieldModel(shape, ...) state holder: WFM:154-172 + MM:62-78.
+ * Whole stack on one device.  Fails with WFM_ERR_INVALID_ARG if nx != ny (WFM:158). */
+WFM_API int wfm_create(wfm_model** out, int nx, int ny, int nz, double dxy, double dz,
+                       int precision, int device);
+
+/* z-slab shard of a global stack: planes [z0, z0+nz_local) of nz_global.
+ * PSFnorm = 1/(Nx*Ny*nz_global) and the iz > Nz/2 wrap use the GLOBAL Nz (WFM:284,302). */
+WFM_API int wfm_create_slab(wfm_model** out, int nx, int ny, int nz_global, int z0, int nz_local,
+                            double dxy, double dz, int precision, int device);
+
+WFM_API int wfm_destroy(wfm_model* h);
+
+/* Text of the last error on this handle (or of the last failed wfm_create* when h == NULL). */
+WFM_API const char* wfm_last_error(const wfm_model* h);
+
+/* Run the handle's work on a caller-owned CUDA stream (cudaStream_t passed as void*);
+ * NULL restores the handle's own stream. */
+WFM_API int wfm_set_stream(wfm_model* h, void* cuda_stream);
+WFM_API int wfm_synchronize(wfm_model* h);
+
+/* ---- pupil construction ------------------------------------------------------------- */
+
+/* NA, lambda, ni of the constructor (WFM:161-166) followed by computeMaskPupil()
+ * (WFM:1374-1406): sets mapPupil = maskPupil = disk of radius NA/lambda.  Marks the PSF dirty. */
+WFM_API int wfm_set_optics(wfm_model* h, double NA, double lambda, double ni);
+
+/* The (Gram-Schmidt orthonormalised) Zernike basis Z of computeZernike() (WFM:194-197):
+ * nzern planes of Npix doubles.  `radial` selects the phase-mode offset (n+1 vs n+3,
+ * WFM:1640-1644).  The library copies Z to the device. */
+WFM_API int wfm_set_basis(wfm_model* h, const double* Z, int nzern, int radial);
+
+/* Build the basis on the device instead: Zernike.zernikeArray (Zernike.java:119-288) +
+ * in-order Gram-Schmidt (call site WFM:196), radius_px = NA/lambda*dxy*Nx (WFM:195). */
+WFM_API int wfm_build_basis(wfm_model* h, int nzern, int radial);
+WFM_API int wfm_get_basis(wfm_model* h, double* Z_out, int nzern);
+
+/* setPhase(DoubleShapedVector) WFM:1625-1649.  n + offset must be <= nzern. */
+WFM_API int wfm_set_phase(wfm_model* h, const double* alpha, int n);
+/* setModulus(DoubleShapedVector) WFM:1588-1610. */
+WFM_API int wfm_set_modulus(wfm_model* h, const double* beta, int n);
+/* setDefocus(DoubleShapedVector) WFM:1510-1534 + computeDefocus() 1452-1499.
+ * n == 3: {ni/lambda, deltaX, deltaY}; n == 1: {ni/lambda}; n == 2 is rejected
+ * (it indexes element 2 of a length-2 vector in the reference, quirk Q4). */
+WFM_API int wfm_set_defocus(wfm_model* h, const double* defoc, int n);
+
+/* Escape hatch for "identical synthetic pupils": load rho, phi, psi (Npix doubles each) and
+ * maskPupil (Npix bytes) verbatim.  Any pointer may be NULL to keep the current array. */
+WFM_API int wfm_set_pupil_arrays(wfm_model* h, const double* rho, const double* phi,
+                                 const double* psi, const uint8_t* mask);
+
+WFM_API int wfm_set_modulus_mode(wfm_model* h, int mode);
+
+/* getRho/getPhi/getPsi/getMaskPupil WFM:1673,1713,1723,1784 (host copies). */
+WFM_API int wfm_get_rho(wfm_model* h, double* out);
+WFM_API int wfm_get_phi(wfm_model* h, double* out);
+WFM_API int wfm_get_psi(wfm_model* h, double* out);
+WFM_API int wfm_get_mask(wfm_model* h, uint8_t* out);
+
+/* ---- the hot path ------------------------------------------------------------------- */
+
+/* computePsf() WFM:206-396: no-op when the PSF is valid (PState > 0, WFM:207). */
+WFM_API int wfm_compute_psf(wfm_model* h);
+/* freeMem() WFM:1970-1974: PState = 0 (device buffers are kept for reuse). */
+WFM_API int wfm_invalidate(wfm_model* h);
+/* 1 when psf/cpxPsf are valid (PState), 0 when dirty. */
+WFM_API int wfm_psf_state(const wfm_model* h);
+
+/* getPsf() WFM:1798-1804 / get_cpxPsf() WFM:1856-1861: compute if dirty, then copy the
+ * slab to host memory (double or float according to the handle's precision). */
+WFM_API int wfm_get_psf(wfm_model* h, void* out_host);
+WFM_API int wfm_get_cpx_psf(wfm_model* h, void* out_host);
+/* Device-resident views of the same arrays (valid until the next setter / destroy). */
+WFM_API int wfm_device_psf(wfm_model* h, void** dev_ptr);
+WFM_API int wfm_device_cpx_psf(wfm_model* h, void** dev_ptr);
+
+/* apply_J_phase WFM:738-1021, apply_J_defocus WFM:1029-1369, apply_J_modulus WFM:429-730.
+ * q_host: gradient w.r.t. the PSF voxels of this slab, same shape/precision as psf.
+ * out: n doubles; n must equal nPhase / 1 or 3 / nModulus.  If the PSF is dirty it is
+ * recomputed first (quirk Q5: the reference would dereference a null cpxPsf). */
+WFM_API int wfm_apply_j_phase(wfm_model* h, const void* q_host, double* out, int n);
+WFM_API int wfm_apply_j_defocus(wfm_model* h, const void* q_host, double* out, int n);
+WFM_API int wfm_apply_j_modulus(wfm_model* h, const void* q_host, double* out, int n);
+/* apply_Jacobian(grad, xspace) WFM:399-409 with the space identified by its flag. */
+WFM_API int wfm_apply_jacobian(wfm_model* h, int param, const void* q_host, double* out, int n);
+/* One FFT pass for all three (they differ only after the FFT: WFM:928 vs 1253 vs 610). */
+WFM_API int wfm_apply_j_all(wfm_model* h, const void* q_host, double* out_defocus3,
+                            double* out_phase, double* out_modulus);
+
+/* Device-resident variant: q_dev and grad_dev are device pointers.  grad_dev receives
+ * 3 + nPhase + nModulus doubles laid out [defocus(3) | phase | modulus]; entries of kinds not
+ * selected are zero.  For a z-slab handle the values are this slab's PARTIAL sums, ready for
+ * one sum-allreduce across ranks.  Asynchronous on the handle's stream. */
+WFM_API int wfm_apply_jacobian_dev(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev);
+WFM_API int wfm_grad_length(const wfm_model* h);
+
+/* ---- utilities ---------------------------------------------------------------------- */
+
+/* Counter-based splitmix64 uniform(-1,1) fill of a device array: element i
+ * gets u(seed, first_index + i), written as double or float. */
+WFM_API int wfm_fill_uniform(wfm_model* h, void* dev_ptr, int precision, uint64_t seed,
+                             uint64_t first_index, uint64_t count);
+
+/* Pinned host memory for the host<->device copies of the entry points above. */
+WFM_API int wfm_host_alloc(void** out, size_t bytes);
+WFM_API int wfm_host_free(void* p);
+
+/* Introspection used by the benchmark and the tests. */
+WFM_API int wfm_get_info(const wfm_model* h, int* nx, int* ny, int* nz_global, int* z0, int* nz_local,
+                         int* precision, int* nzern, int* nphase, int* nmodulus);
+/* Number of active pupil rows / columns the pruned FFT passes visit. */
+WFM_API int wfm_active_extent(const wfm_model* h, int* n_active_x, int* n_active_y);
+/* Total kernel launches issued by this library since load (all handles). */
+WFM_API uint64_t wfm_launch_count(void);
+WFM_API const char* wfm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFM_B200_H */

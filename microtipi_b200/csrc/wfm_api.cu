@@ -1,0 +1,787 @@
+// wfm_api.cu -- implementation of the C ABI in include/wfm_b200.h.
+//
+// Host-side state machine of the reference class (PState / freeMem protocol, setter order,
+// IllegalArgumentException sites) plus the kernel launches.  WFM = WideFieldModel.java.
+#include "../../include/wfm_b200.h"
+#include "wfm_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace wfm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need ? need : 1);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+}  // namespace
+
+struct wfm_model {
+    // geometry (MicroscopeModel.java:62-78, WFM:154-172)
+    int N = 0, nz_global = 0, z0 = 0, nzl = 0;
+    double dxy = 0, dz = 0;
+    int precision = WFM_F64;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // optics (WFM:161-166)
+    bool have_optics = false;
+    double NA = 0, lambda = 0, ni = 0, lambda_ni = 0, radius = 0, deltaX = 0, deltaY = 0;
+    int ndefocus = 3;
+    // basis
+    int nzern = 0, radial = 0;
+    DevBuf Z;
+    // coefficients (parameterCoefs[], MicroscopeModel.java:54)
+    int nphase = 0, nmod = 0;
+    Coefs alpha{}, beta{};
+    bool have_rho = false;
+    // pupil arrays
+    DevBuf rho, phi, psi, mask, map, support;
+    std::vector<uint8_t> h_map, h_zsup, h_esc;
+    bool activity_dirty = true;
+    int nax = 0, nay = 0, pitch = 0;
+    DevBuf act_x, inv_x, act_y, inv_y;
+    // FFT twiddles
+    DevBuf tw;
+    // outputs + PState (MicroscopeModel.java:42)
+    DevBuf cpx, psf;
+    int pstate = 0;
+    // scratch
+    DevBuf scratch, Gp, block_part, grad, qdev;
+    int modulus_mode = WFM_MODULUS_INTENDED;
+    std::string err;
+
+    int npix() const { return N * N; }
+    size_t esz() const { return precision == WFM_F64 ? 8 : 4; }
+    int glen() const { return 3 + nphase + nmod; }
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define WFM_CK(h, call)                                                                         \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return (h)->fail(e__ == cudaErrorMemoryAllocation ? WFM_ERR_NOMEM : WFM_ERR_CUDA,   \
+                             "%s failed: %s", #call, cudaGetErrorString(e__));                  \
+    } while (0)
+
+#define WFM_CK_LAUNCH(h, what)                                                                  \
+    do {                                                                                        \
+        cudaError_t e__ = cudaGetLastError();                                                   \
+        if (e__ != cudaSuccess)                                                                 \
+            return (h)->fail(WFM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e__)); \
+    } while (0)
+
+namespace {
+
+bool supported_n(int n) { return n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048; }
+
+Geom geom_of(const wfm_model* h) {
+    Geom g;
+    g.N = h->N; g.nz_global = h->nz_global; g.z0 = h->z0; g.nzl = h->nzl; g.dz = h->dz;
+    g.psf_norm = 1.0 / ((double)h->N * (double)h->N * (double)h->nz_global);   // WFM:284
+    return g;
+}
+
+template <typename T> int col_tile(int N) {
+    switch (N) {
+        case 32: return ColCfg<T, 32>::C;
+        case 64: return ColCfg<T, 64>::C;
+        case 128: return ColCfg<T, 128>::C;
+        case 256: return ColCfg<T, 256>::C;
+        case 512: return ColCfg<T, 512>::C;
+        case 1024: return ColCfg<T, 1024>::C;
+        default: return ColCfg<T, 2048>::C;
+    }
+}
+
+int upload_twiddles(wfm_model* h) {
+    const int N = h->N;
+    if (h->precision == WFM_F64) {
+        std::vector<double2> t(N);
+        for (int m = 0; m < N; ++m) {
+            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)N;
+            t[m].x = (double)cosl(a); t[m].y = (double)(-sinl(a));
+        }
+        WFM_CK(h, h->tw.ensure(sizeof(double2) * N));
+        WFM_CK(h, cudaMemcpy(h->tw.p, t.data(), sizeof(double2) * N, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float2> t(N);
+        for (int m = 0; m < N; ++m) {
+            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)N;
+            t[m].x = (float)cosl(a); t[m].y = (float)(-sinl(a));
+        }
+        WFM_CK(h, h->tw.ensure(sizeof(float2) * N));
+        WFM_CK(h, cudaMemcpy(h->tw.p, t.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+    }
+    return WFM_OK;
+}
+
+// Rows / columns of the pupil plane that can hold a non-zero value: union of mapPupil, the
+// support of the basis and anything loaded through the escape hatch.
+int rebuild_activity(wfm_model* h) {
+    if (!h->activity_dirty) return WFM_OK;
+    const int N = h->N, npix = h->npix();
+    std::vector<uint8_t> sup(npix, 0);
+    for (int i = 0; i < npix; ++i)
+        sup[i] = (uint8_t)((h->h_map.empty() ? 0 : h->h_map[i]) | (h->h_zsup.empty() ? 0 : h->h_zsup[i]) |
+                           (h->h_esc.empty() ? 0 : h->h_esc[i]));
+    std::vector<int> ax, ay, ix(N, -1), iy(N, -1);
+    std::vector<uint8_t> cx_any(N, 0), cy_any(N, 0);
+    for (int y = 0; y < N; ++y)
+        for (int x = 0; x < N; ++x)
+            if (sup[x + N * y]) { cx_any[x] = 1; cy_any[y] = 1; }
+    for (int x = 0; x < N; ++x) if (cx_any[x]) { ix[x] = (int)ax.size(); ax.push_back(x); }
+    for (int y = 0; y < N; ++y) if (cy_any[y]) { iy[y] = (int)ay.size(); ay.push_back(y); }
+    if (ax.empty()) { ix[0] = 0; ax.push_back(0); }
+    if (ay.empty()) { iy[0] = 0; ay.push_back(0); }
+    h->nax = (int)ax.size(); h->nay = (int)ay.size();
+    const int C = h->precision == WFM_F64 ? col_tile<double>(N) : col_tile<float>(N);
+    h->pitch = (h->nax + C - 1) / C * C;
+    WFM_CK(h, h->act_x.ensure(sizeof(int) * ax.size()));
+    WFM_CK(h, h->act_y.ensure(sizeof(int) * ay.size()));
+    WFM_CK(h, h->inv_x.ensure(sizeof(int) * N));
+    WFM_CK(h, h->inv_y.ensure(sizeof(int) * N));
+    WFM_CK(h, h->support.ensure(npix));
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    WFM_CK(h, cudaMemcpy(h->act_x.p, ax.data(), sizeof(int) * ax.size(), cudaMemcpyHostToDevice));
+    WFM_CK(h, cudaMemcpy(h->act_y.p, ay.data(), sizeof(int) * ay.size(), cudaMemcpyHostToDevice));
+    WFM_CK(h, cudaMemcpy(h->inv_x.p, ix.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+    WFM_CK(h, cudaMemcpy(h->inv_y.p, iy.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+    WFM_CK(h, cudaMemcpy(h->support.p, sup.data(), npix, cudaMemcpyHostToDevice));
+    h->activity_dirty = false;
+    return WFM_OK;
+}
+
+template <class K> int set_smem(wfm_model* h, K kfn, size_t bytes) {
+    if (bytes > 48 * 1024) WFM_CK(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return WFM_OK;
+}
+
+// ---- computePsf ---------------------------------------------------------------------------------
+template <typename T, int N> int launch_psf(wfm_model* h) {
+    PsfArgs<T> a;
+    a.g = geom_of(h);
+    a.rho = (const double*)h->rho.p; a.phi = (const double*)h->phi.p; a.psi = (const double*)h->psi.p;
+    a.act_y = (const int*)h->act_y.p; a.inv_y = (const int*)h->inv_y.p; a.nay = h->nay;
+    a.tw = (const cx<T>*)h->tw.p;
+    a.T1 = (cx<T>*)h->scratch.p; a.cpx = (cx<T>*)h->cpx.p; a.psf = (T*)h->psf.p;
+    a.plane0 = 0;
+    {
+        auto kfn = &k_psf_rows<T, N>;
+        const size_t smem = sizeof(cx<T>) * RowLayout<T, N>::LEN * RowCfg<N>::RB;
+        int rc = set_smem(h, kfn, smem); if (rc) return rc;
+        dim3 grid((h->nay + RowCfg<N>::RB - 1) / RowCfg<N>::RB, h->nzl);
+        WFM_LAUNCH(kfn, grid, dim3(RowCfg<N>::THREADS), smem, h->stream, a);
+        WFM_CK_LAUNCH(h, "k_psf_rows");
+    }
+    {
+        auto kfn = &k_psf_cols<T, N>;
+        const size_t smem = ColCfg<T, N>::SMEM;
+        int rc = set_smem(h, kfn, smem); if (rc) return rc;
+        dim3 grid(N / ColCfg<T, N>::C, h->nzl);
+        WFM_LAUNCH(kfn, grid, dim3(ColCfg<T, N>::THREADS), smem, h->stream, a);
+        WFM_CK_LAUNCH(h, "k_psf_cols");
+    }
+    return WFM_OK;
+}
+
+// ---- apply_J_* ------------------------------------------------------------------------------------
+template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev) {
+    JacArgs<T> a;
+    a.g = geom_of(h);
+    a.cpx = (const cx<T>*)h->cpx.p; a.q = (const T*)q_dev;
+    a.rho = (const double*)h->rho.p; a.phi = (const double*)h->phi.p; a.psi = (const double*)h->psi.p;
+    a.mask = (const uint8_t*)h->mask.p; a.support = (const uint8_t*)h->support.p;
+    a.act_x = (const int*)h->act_x.p; a.inv_x = (const int*)h->inv_x.p; a.nax = h->nax; a.pitch = h->pitch;
+    a.tw = (const cx<T>*)h->tw.p;
+    a.T2 = (cx<T>*)h->scratch.p;
+    a.nsub = (h->nzl + WFM_JAC_BS - 1) / WFM_JAC_BS;
+    a.last_plane_only = (h->modulus_mode == WFM_MODULUS_REFERENCE_LAST_PLANE) ? 1 : 0;
+    a.plane0 = 0;
+    const size_t img = (size_t)N * h->pitch;
+    WFM_CK(h, h->Gp.ensure(sizeof(double) * 3 * a.nsub * img));
+    a.Gp = (double*)h->Gp.p;
+    {
+        auto kfn = &k_jac_rows<T, N>;
+        const size_t smem = sizeof(cx<T>) * RowLayout<T, N>::LEN * RowCfg<N>::RB;
+        int rc = set_smem(h, kfn, smem); if (rc) return rc;
+        dim3 grid((N + RowCfg<N>::RB - 1) / RowCfg<N>::RB, h->nzl);
+        WFM_LAUNCH(kfn, grid, dim3(RowCfg<N>::THREADS), smem, h->stream, a);
+        WFM_CK_LAUNCH(h, "k_jac_rows");
+    }
+    {
+        const size_t smem = ColCfg<T, N>::SMEM;
+        dim3 grid(h->pitch / ColCfg<T, N>::C, a.nsub);
+        if (kinds & WFM_J_MODULUS) {
+            auto kfn = &k_jac_cols<T, N, true>;
+            int rc = set_smem(h, kfn, smem); if (rc) return rc;
+            WFM_LAUNCH(kfn, grid, dim3(ColCfg<T, N>::THREADS), smem, h->stream, a);
+        } else {
+            auto kfn = &k_jac_cols<T, N, false>;
+            int rc = set_smem(h, kfn, smem); if (rc) return rc;
+            WFM_LAUNCH(kfn, grid, dim3(ColCfg<T, N>::THREADS), smem, h->stream, a);
+        }
+        WFM_CK_LAUNCH(h, "k_jac_cols");
+    }
+    {
+        ReduceArgs r;
+        r.g = a.g; r.Gp = a.Gp; r.nsub = a.nsub; r.pitch = h->pitch; r.nax = h->nax;
+        r.act_x = a.act_x; r.Z = (const double*)h->Z.p; r.psi = a.psi; r.mask = a.mask;
+        r.nphase = h->nphase; r.nmod = h->nmod; r.phase_off = h->radial ? 1 : 3;
+        r.kinds = kinds; r.dxy = h->dxy; r.lambda_ni = h->lambda_ni; r.deltaX = h->deltaX; r.deltaY = h->deltaY;
+        r.glen = h->glen();
+        const int nblocks = (int)((img + WFM_RED_THREADS - 1) / WFM_RED_THREADS);
+        WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * r.glen));
+        r.block_part = (double*)h->block_part.p;
+        auto kfn = &k_jac_reduce;
+        WFM_LAUNCH(kfn, dim3(nblocks), dim3(WFM_RED_THREADS), 0, h->stream, r);
+        WFM_CK_LAUNCH(h, "k_jac_reduce");
+        double nbeta = 0.0;
+        if (h->nmod > 0) {
+            double s = 0.0;
+            for (int k = 0; k < h->nmod; ++k) s += h->beta.v[k] * h->beta.v[k];
+            nbeta = 1.0 / std::sqrt(s);                                        // WFM:435
+        }
+        auto kfin = &k_jac_final;
+        WFM_LAUNCH(kfin, dim3((r.glen + 127) / 128), dim3(128), 0, h->stream, (const double*)r.block_part, nblocks,
+                   r.glen, h->nphase, a.g.psf_norm, h->beta, nbeta, kinds, grad_dev);
+        WFM_CK_LAUNCH(h, "k_jac_final");
+    }
+    return WFM_OK;
+}
+
+#define WFM_DISPATCH_N(FN, h, ...)                                                     \
+    switch ((h)->N) {                                                                  \
+        case 32: return FN<T, 32>(h, ##__VA_ARGS__);                                   \
+        case 64: return FN<T, 64>(h, ##__VA_ARGS__);                                   \
+        case 128: return FN<T, 128>(h, ##__VA_ARGS__);                                 \
+        case 256: return FN<T, 256>(h, ##__VA_ARGS__);                                 \
+        case 512: return FN<T, 512>(h, ##__VA_ARGS__);                                 \
+        case 1024: return FN<T, 1024>(h, ##__VA_ARGS__);                               \
+        case 2048: return FN<T, 2048>(h, ##__VA_ARGS__);                               \
+        default: return (h)->fail(WFM_ERR_UNSUPPORTED, "unsupported N=%d", (h)->N);    \
+    }
+
+template <typename T> int dispatch_psf(wfm_model* h) { WFM_DISPATCH_N(launch_psf, h) }
+template <typename T> int dispatch_jac(wfm_model* h, unsigned kinds, const void* q, double* g) {
+    WFM_DISPATCH_N(launch_jac, h, kinds, q, g)
+}
+
+int ensure_scratch(wfm_model* h) {
+    const size_t c = 2 * h->esz();
+    const size_t t1 = (size_t)h->nzl * h->nay * h->N * c;
+    const size_t t2 = (size_t)h->nzl * h->N * h->pitch * c;
+    WFM_CK(h, h->scratch.ensure(t1 > t2 ? t1 : t2));
+    return WFM_OK;
+}
+
+int compute_psf_impl(wfm_model* h) {
+    if (h->pstate > 0) return WFM_OK;                                          // WFM:207
+    if (!h->have_rho) return h->fail(WFM_ERR_STATE, "pupil modulus not set: call wfm_set_modulus or wfm_set_pupil_arrays first");
+    WFM_CK(h, cudaSetDevice(h->device));
+    int rc = rebuild_activity(h); if (rc) return rc;
+    rc = ensure_scratch(h); if (rc) return rc;
+    const size_t vox = (size_t)h->npix() * h->nzl;
+    WFM_CK(h, h->cpx.ensure(vox * 2 * h->esz()));
+    WFM_CK(h, h->psf.ensure(vox * h->esz()));
+    rc = (h->precision == WFM_F64) ? dispatch_psf<double>(h) : dispatch_psf<float>(h);
+    if (rc) return rc;
+    h->pstate = 1;                                                             // WFM:395
+    return WFM_OK;
+}
+
+int invalidate(wfm_model* h) { h->pstate = 0; return WFM_OK; }                 // WFM:1970-1974
+
+int elementwise_grid(int n) { return (n + 255) / 256; }
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int wfm_create_slab(wfm_model** out, int nx, int ny, int nz_global, int z0, int nz_local, double dxy,
+                    double dz, int precision, int device) {
+    if (!out) { g_create_error = "out is NULL"; return WFM_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (nx != ny) { g_create_error = "Nx should equal Ny"; return WFM_ERR_INVALID_ARG; }      // WFM:158-160
+    if (nx <= 0 || nz_global <= 0 || nz_local <= 0 || z0 < 0 || z0 + nz_local > nz_global) {
+        g_create_error = "bad shape / slab"; return WFM_ERR_INVALID_ARG;
+    }
+    if (precision != WFM_F64 && precision != WFM_F32) { g_create_error = "bad precision"; return WFM_ERR_INVALID_ARG; }
+    if (!supported_n(nx)) {
+        g_create_error = "Nx must be a power of two in [32, 2048]"; return WFM_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        g_create_error = "no CUDA device available (this library has no CPU fallback)"; return WFM_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return WFM_ERR_INVALID_ARG; }
+    wfm_model* h = new (std::nothrow) wfm_model();
+    if (!h) { g_create_error = "out of host memory"; return WFM_ERR_NOMEM; }
+    h->N = nx; h->nz_global = nz_global; h->z0 = z0; h->nzl = nz_local; h->dxy = dxy; h->dz = dz;
+    h->precision = precision; h->device = device;
+    auto bail = [&](int code, const char* what) { g_create_error = what; wfm_destroy(h); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(WFM_ERR_CUDA, "cudaSetDevice failed");
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(WFM_ERR_CUDA, "cudaStreamCreate failed");
+    h->stream = h->own_stream;
+    const size_t npix = (size_t)nx * nx;
+    // this.phi = new double[Ny*Nx]; this.psi = new double[Ny*Nx]  (WFM:167-168); rho starts empty
+    if (h->rho.ensure(8 * npix) || h->phi.ensure(8 * npix) || h->psi.ensure(8 * npix) || h->mask.ensure(npix) ||
+        h->map.ensure(npix) || h->grad.ensure(8 * (3 + 2 * WFM_MAX_COEF)))
+        return bail(WFM_ERR_NOMEM, "device allocation failed");
+    cudaMemset(h->rho.p, 0, 8 * npix); cudaMemset(h->phi.p, 0, 8 * npix); cudaMemset(h->psi.p, 0, 8 * npix);
+    cudaMemset(h->mask.p, 0, npix); cudaMemset(h->map.p, 0, npix);
+    if (upload_twiddles(h) != WFM_OK) return bail(WFM_ERR_CUDA, "twiddle upload failed");
+    *out = h;
+    return WFM_OK;
+}
+
+int wfm_create(wfm_model** out, int nx, int ny, int nz, double dxy, double dz, int precision, int device) {
+    return wfm_create_slab(out, nx, ny, nz, 0, nz, dxy, dz, precision, device);
+}
+
+int wfm_destroy(wfm_model* h) {
+    if (!h) return WFM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->Z, &h->rho, &h->phi, &h->psi, &h->mask, &h->map, &h->support, &h->act_x, &h->inv_x,
+                      &h->act_y, &h->inv_y, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gp, &h->block_part,
+                      &h->grad, &h->qdev})
+        b->release();
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return WFM_OK;
+}
+
+const char* wfm_last_error(const wfm_model* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int wfm_set_stream(wfm_model* h, void* s) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    cudaStreamSynchronize(h->stream);
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return WFM_OK;
+}
+
+int wfm_synchronize(wfm_model* h) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    return WFM_OK;
+}
+
+int wfm_set_optics(wfm_model* h, double NA, double lambda, double ni) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!(NA > 0) || !(lambda > 0) || !(ni > 0)) return h->fail(WFM_ERR_INVALID_ARG, "NA, lambda and ni must be positive");
+    WFM_CK(h, cudaSetDevice(h->device));
+    h->NA = NA; h->lambda = lambda; h->ni = ni;
+    h->radius = NA / lambda;                                                   // WFM:165
+    h->lambda_ni = ni / lambda;                                                // WFM:166
+    h->have_optics = true;
+    auto kfn = &k_mask_pupil;
+    WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix())), dim3(256), 0, h->stream, (uint8_t*)h->map.p,
+               (uint8_t*)h->mask.p, h->N, h->dxy, h->radius);
+    WFM_CK_LAUNCH(h, "k_mask_pupil");
+    h->h_map.resize(h->npix());
+    WFM_CK(h, cudaMemcpyAsync(h->h_map.data(), h->map.p, h->npix(), cudaMemcpyDeviceToHost, h->stream));
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    h->activity_dirty = true;
+    return invalidate(h);                                                      // WFM:1405
+}
+
+int wfm_set_basis(wfm_model* h, const double* Z, int nzern, int radial) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!Z || nzern <= 0) return h->fail(WFM_ERR_INVALID_ARG, "Z is NULL or nzern <= 0");
+    WFM_CK(h, cudaSetDevice(h->device));
+    const size_t npix = h->npix();
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    WFM_CK(h, h->Z.ensure(8 * npix * nzern));
+    WFM_CK(h, cudaMemcpy(h->Z.p, Z, 8 * npix * nzern, cudaMemcpyHostToDevice));
+    h->nzern = nzern; h->radial = radial ? 1 : 0;
+    h->h_zsup.assign(npix, 0);
+    for (int k = 0; k < nzern; ++k)
+        for (size_t i = 0; i < npix; ++i)
+            if (Z[(size_t)k * npix + i] != 0.0) h->h_zsup[i] = 1;
+    h->activity_dirty = true;
+    return invalidate(h);
+}
+
+// computeZernike() WFM:194-197 on the device.
+int wfm_build_basis(wfm_model* h, int nzern, int radial) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (nzern <= 0) return h->fail(WFM_ERR_INVALID_ARG, "nzern <= 0");
+    if (!h->have_optics) return h->fail(WFM_ERR_STATE, "optics not set: call wfm_set_optics first");
+    WFM_CK(h, cudaSetDevice(h->device));
+    const int N = h->N, npix = h->npix();
+    // Noll index -> (n, m)  Zernike.java:37-52
+    auto noll = [](int J, int& n, int& m) {
+        const double n1 = (std::sqrt(1.0 + 8.0 * J) - 1.0) / 2.0;
+        n = (int)std::floor(n1);
+        if (n1 == (double)n) n -= 1;
+        const int k = (n + 1) * (n + 2) / 2;
+        m = n - 2 * (int)std::floor((k - J) / 2.0);
+    };
+    std::vector<ZernMode> modes(nzern);
+    memset(modes.data(), 0, sizeof(ZernMode) * nzern);
+    int nmax = 0;
+    for (int nz = 1; nz < nzern; ++nz) {
+        int n, m;
+        if (radial) { n = nz; m = 0; } else noll(nz + 1, n, m);
+        const int p = (n - m) / 2, q = (n + m) / 2;
+        if (p + 1 > WFM_ZERN_MAXS || n > 2 * WFM_ZERN_MAXS - 2)
+            return h->fail(WFM_ERR_UNSUPPORTED, "Zernike radial degree %d too high", n);
+        ZernMode& md = modes[nz];
+        md.n = n; md.m = m;
+        md.kind = (m == 0) ? 0 : (((nz + 1) % 2 == 0) ? 1 : 2);                 // Zernike.java:217,241
+        md.norm = (m == 0) ? std::sqrt((double)(n + 1)) : std::sqrt((double)(2 * (n + 1)));
+        std::vector<double> lfact(n + 1, 0.0);                                 // Zernike.java:75-80
+        for (int i = 1; i <= n; ++i) lfact[i] = lfact[i - 1] + std::log((double)i);
+        for (int sI = 0; sI <= p; ++sI) {
+            double r = std::exp(lfact[n - sI] - lfact[sI] - lfact[p - sI] - lfact[q - sI]);
+            md.R[sI] = (sI % 2) ? -r : r;
+        }
+        if (n > nmax) nmax = n;
+    }
+    if (nmax < 1) nmax = 1;
+    const double radius_px = h->radius * h->dxy * (double)N;                   // WFM:195
+    DevBuf dmodes, partial;
+    WFM_CK(h, dmodes.ensure(sizeof(ZernMode) * nzern));
+    const int nparts = 128;
+    WFM_CK(h, partial.ensure(8 * nparts));
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    WFM_CK(h, cudaMemcpy(dmodes.p, modes.data(), sizeof(ZernMode) * nzern, cudaMemcpyHostToDevice));
+    WFM_CK(h, h->Z.ensure(8 * (size_t)npix * nzern));
+    double* Z = (double*)h->Z.p;
+    {
+        auto kfn = &k_zernike_modes;
+        WFM_LAUNCH(kfn, dim3(elementwise_grid(npix)), dim3(256), 0, h->stream, Z, (const ZernMode*)dmodes.p,
+                   nzern, nmax, N, radius_px);
+        WFM_CK_LAUNCH(h, "k_zernike_modes");
+    }
+    auto kdot = &k_dot_partial;
+    auto kupd = &k_gs_update;
+    auto dot = [&](const double* a, const double* b) {
+        WFM_LAUNCH(kdot, dim3(nparts), dim3(WFM_DOT_THREADS), 0, h->stream, a, b, npix, (double*)partial.p);
+    };
+    auto update = [&](double* zk, const double* zj, int mode) {
+        WFM_LAUNCH(kupd, dim3(elementwise_grid(npix)), dim3(256), 0, h->stream, zk, zj,
+                   (const double*)partial.p, nparts, npix, mode);
+    };
+    for (int k = 0; k < nzern; ++k) {              // per-mode L2 normalisation, Zernike.java:156,192,231,255,277
+        double* zk = Z + (size_t)k * npix;
+        dot(zk, zk); update(zk, zk, 1);
+    }
+    for (int k = 0; k < nzern; ++k) {              // in-order modified Gram-Schmidt (ASSUMED, WFM:196)
+        double* zk = Z + (size_t)k * npix;
+        for (int j = 0; j < k; ++j) { dot(Z + (size_t)j * npix, zk); update(zk, Z + (size_t)j * npix, 0); }
+        dot(zk, zk); update(zk, zk, 1);
+    }
+    WFM_CK_LAUNCH(h, "zernike basis kernels");
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    dmodes.release(); partial.release();
+    h->nzern = nzern; h->radial = radial ? 1 : 0;
+    h->h_zsup.assign(npix, 0);
+    for (int y = 0; y < N; ++y)
+        for (int x = 0; x < N; ++x) {
+            const double kx = (double)((x > N / 2) ? x - N : x), ky = (double)((y > N / 2) ? y - N : y);
+            if (std::sqrt(kx * kx + ky * ky) < radius_px) h->h_zsup[x + N * y] = 1;
+        }
+    h->activity_dirty = true;
+    return invalidate(h);
+}
+
+int wfm_get_basis(wfm_model* h, double* out, int nzern) {
+    if (!h || !out) return WFM_ERR_INVALID_ARG;
+    if (nzern <= 0 || nzern > h->nzern) return h->fail(WFM_ERR_INVALID_ARG, "nzern out of range");
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    WFM_CK(h, cudaMemcpy(out, h->Z.p, 8 * (size_t)h->npix() * nzern, cudaMemcpyDeviceToHost));
+    return WFM_OK;
+}
+
+int wfm_set_phase(wfm_model* h, const double* alpha, int n) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (n < 0 || n > WFM_MAX_COEF || (n > 0 && !alpha)) return h->fail(WFM_ERR_INVALID_ARG, "bad phase coefficient vector");
+    const int off = h->radial ? 1 : 3;
+    if (n > 0 && (h->nzern <= 0)) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
+    if (n > 0 && n + off > h->nzern)
+        return h->fail(WFM_ERR_INVALID_ARG, "phase parameter does not belong to the right space  ");   // WFM:1629
+    WFM_CK(h, cudaSetDevice(h->device));
+    for (int k = 0; k < n; ++k) h->alpha.v[k] = alpha[k];
+    h->nphase = n;
+    auto kfn = &k_set_phase;
+    WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix())), dim3(256), 0, h->stream, (double*)h->phi.p,
+               (const double*)h->Z.p, (const uint8_t*)h->mask.p, h->alpha, n, off, h->npix());
+    WFM_CK_LAUNCH(h, "k_set_phase");
+    return invalidate(h);                                                      // WFM:1648
+}
+
+int wfm_set_modulus(wfm_model* h, const double* beta, int n) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (n <= 0 || n > WFM_MAX_COEF || !beta) return h->fail(WFM_ERR_INVALID_ARG, "bad modulus coefficient vector");
+    if (h->nzern <= 0) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
+    if (n > h->nzern)
+        return h->fail(WFM_ERR_INVALID_ARG, "DoubleShapedVector beta does not belong to the modulus space");  // WFM:1592
+    WFM_CK(h, cudaSetDevice(h->device));
+    double s = 0.0;
+    for (int k = 0; k < n; ++k) { h->beta.v[k] = beta[k]; s += beta[k] * beta[k]; }
+    h->nmod = n;
+    const double beta_norm = 1.0 / std::sqrt(s);                               // WFM:1597
+    auto kfn = &k_set_modulus;
+    WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix())), dim3(256), 0, h->stream, (double*)h->rho.p,
+               (const double*)h->Z.p, (const uint8_t*)h->mask.p, h->beta, n, beta_norm, h->npix());
+    WFM_CK_LAUNCH(h, "k_set_modulus");
+    h->have_rho = true;
+    return invalidate(h);                                                      // WFM:1609
+}
+
+int wfm_set_defocus(wfm_model* h, const double* defoc, int n) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!defoc || (n != 1 && n != 3)) return h->fail(WFM_ERR_INVALID_ARG, "bad defocus  parameters");   // WFM:1530, Q4
+    if (!h->have_optics) return h->fail(WFM_ERR_STATE, "optics not set: call wfm_set_optics first");
+    WFM_CK(h, cudaSetDevice(h->device));
+    if (n == 3) { h->deltaX = defoc[1]; h->deltaY = defoc[2]; }                // WFM:1518-1520
+    h->lambda_ni = defoc[0];                                                   // WFM:1522
+    h->ni = h->lambda_ni * h->lambda;                                          // WFM:1523
+    h->ndefocus = n;
+    auto kfn = &k_compute_defocus;
+    WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix())), dim3(256), 0, h->stream, (double*)h->psi.p,
+               (uint8_t*)h->mask.p, (const uint8_t*)h->map.p, h->N, h->dxy, h->lambda_ni, h->deltaX, h->deltaY);
+    WFM_CK_LAUNCH(h, "k_compute_defocus");
+    return invalidate(h);                                                      // WFM:1533
+}
+
+int wfm_set_pupil_arrays(wfm_model* h, const double* rho, const double* phi, const double* psi, const uint8_t* mask) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_CK(h, cudaSetDevice(h->device));
+    const size_t npix = h->npix();
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    if (h->h_esc.empty()) h->h_esc.assign(npix, 0);
+    if (rho) {
+        WFM_CK(h, cudaMemcpy(h->rho.p, rho, 8 * npix, cudaMemcpyHostToDevice));
+        for (size_t i = 0; i < npix; ++i) if (rho[i] != 0.0) h->h_esc[i] = 1;
+        h->have_rho = true;
+    }
+    if (phi) WFM_CK(h, cudaMemcpy(h->phi.p, phi, 8 * npix, cudaMemcpyHostToDevice));
+    if (psi) WFM_CK(h, cudaMemcpy(h->psi.p, psi, 8 * npix, cudaMemcpyHostToDevice));
+    if (mask) {
+        std::vector<uint8_t> m(npix);
+        for (size_t i = 0; i < npix; ++i) { m[i] = mask[i] ? 1 : 0; if (m[i]) h->h_esc[i] = 1; }
+        WFM_CK(h, cudaMemcpy(h->mask.p, m.data(), npix, cudaMemcpyHostToDevice));
+    }
+    h->activity_dirty = true;
+    return invalidate(h);
+}
+
+int wfm_set_modulus_mode(wfm_model* h, int mode) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (mode != WFM_MODULUS_INTENDED && mode != WFM_MODULUS_REFERENCE_LAST_PLANE)
+        return h->fail(WFM_ERR_INVALID_ARG, "bad modulus mode");
+    h->modulus_mode = mode;
+    return WFM_OK;
+}
+
+static int copy_out(wfm_model* h, void* out, const void* dev, size_t bytes) {
+    if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
+    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_CK(h, cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    return WFM_OK;
+}
+
+int wfm_get_rho(wfm_model* h, double* out) { return h ? copy_out(h, out, h->rho.p, 8 * (size_t)h->npix()) : WFM_ERR_INVALID_ARG; }
+int wfm_get_phi(wfm_model* h, double* out) { return h ? copy_out(h, out, h->phi.p, 8 * (size_t)h->npix()) : WFM_ERR_INVALID_ARG; }
+int wfm_get_psi(wfm_model* h, double* out) { return h ? copy_out(h, out, h->psi.p, 8 * (size_t)h->npix()) : WFM_ERR_INVALID_ARG; }
+int wfm_get_mask(wfm_model* h, uint8_t* out) { return h ? copy_out(h, out, h->mask.p, (size_t)h->npix()) : WFM_ERR_INVALID_ARG; }
+
+int wfm_compute_psf(wfm_model* h) { return h ? compute_psf_impl(h) : WFM_ERR_INVALID_ARG; }
+int wfm_invalidate(wfm_model* h) { return h ? invalidate(h) : WFM_ERR_INVALID_ARG; }
+int wfm_psf_state(const wfm_model* h) { return h ? h->pstate : 0; }
+
+int wfm_get_psf(wfm_model* h, void* out) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1800-1802
+    return copy_out(h, out, h->psf.p, (size_t)h->npix() * h->nzl * h->esz());
+}
+
+int wfm_get_cpx_psf(wfm_model* h, void* out) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1857-1859
+    return copy_out(h, out, h->cpx.p, (size_t)h->npix() * h->nzl * 2 * h->esz());
+}
+
+int wfm_device_psf(wfm_model* h, void** p) {
+    if (!h || !p) return WFM_ERR_INVALID_ARG;
+    int rc = compute_psf_impl(h); if (rc) return rc;
+    *p = h->psf.p; return WFM_OK;
+}
+int wfm_device_cpx_psf(wfm_model* h, void** p) {
+    if (!h || !p) return WFM_ERR_INVALID_ARG;
+    int rc = compute_psf_impl(h); if (rc) return rc;
+    *p = h->cpx.p; return WFM_OK;
+}
+
+int wfm_grad_length(const wfm_model* h) { return h ? h->glen() : 0; }
+
+int wfm_apply_jacobian_dev(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!q_dev || !grad_dev) return h->fail(WFM_ERR_INVALID_ARG, "q_dev / grad_dev is NULL");
+    if (!(kinds & 7u)) return h->fail(WFM_ERR_INVALID_ARG, "no Jacobian selected");
+    if ((kinds & WFM_J_PHASE) && h->nphase <= 0) return h->fail(WFM_ERR_STATE, "phase space is empty (nPhase = 0)");
+    if ((kinds & WFM_J_MODULUS) && h->nmod <= 0) return h->fail(WFM_ERR_STATE, "modulus coefficients not set");
+    if ((kinds & (WFM_J_PHASE | WFM_J_MODULUS)) && h->nzern <= 0) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
+    int rc = compute_psf_impl(h); if (rc) return rc;                           // quirk Q5: recompute if dirty
+    return (h->precision == WFM_F64) ? dispatch_jac<double>(h, kinds, q_dev, grad_dev)
+                                     : dispatch_jac<float>(h, kinds, q_dev, grad_dev);
+}
+
+static int apply_host(wfm_model* h, unsigned kinds, const void* q_host, std::vector<double>& g) {
+    if (!q_host) return h->fail(WFM_ERR_INVALID_ARG, "q is NULL");
+    WFM_CK(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->npix() * h->nzl * h->esz();
+    WFM_CK(h, h->qdev.ensure(bytes));
+    WFM_CK(h, cudaMemcpyAsync(h->qdev.p, q_host, bytes, cudaMemcpyHostToDevice, h->stream));
+    int rc = wfm_apply_jacobian_dev(h, kinds, h->qdev.p, (double*)h->grad.p); if (rc) return rc;
+    g.resize(h->glen());
+    WFM_CK(h, cudaMemcpyAsync(g.data(), h->grad.p, 8 * g.size(), cudaMemcpyDeviceToHost, h->stream));
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    return WFM_OK;
+}
+
+int wfm_apply_j_phase(wfm_model* h, const void* q, double* out, int n) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!out || n != h->nphase || n <= 0) return h->fail(WFM_ERR_INVALID_ARG, "output length must equal nPhase");
+    std::vector<double> g;
+    int rc = apply_host(h, WFM_J_PHASE, q, g); if (rc) return rc;
+    memcpy(out, g.data() + 3, 8 * (size_t)n);
+    return WFM_OK;
+}
+
+int wfm_apply_j_defocus(wfm_model* h, const void* q, double* out, int n) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!out || (n != 1 && n != 3)) return h->fail(WFM_ERR_INVALID_ARG, "defocus gradient has 1 or 3 elements");   // Q4
+    std::vector<double> g;
+    int rc = apply_host(h, WFM_J_DEFOCUS, q, g); if (rc) return rc;
+    memcpy(out, g.data(), 8 * (size_t)n);                                      // WFM:1352-1359
+    return WFM_OK;
+}
+
+int wfm_apply_j_modulus(wfm_model* h, const void* q, double* out, int n) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!out || n != h->nmod || n <= 0) return h->fail(WFM_ERR_INVALID_ARG, "output length must equal nModulus");
+    std::vector<double> g;
+    int rc = apply_host(h, WFM_J_MODULUS, q, g); if (rc) return rc;
+    memcpy(out, g.data() + 3 + h->nphase, 8 * (size_t)n);
+    return WFM_OK;
+}
+
+int wfm_apply_jacobian(wfm_model* h, int param, const void* q, double* out, int n) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    switch (param) {                                                           // WFM:399-409
+        case WFM_DEFOCUS: return wfm_apply_j_defocus(h, q, out, n);
+        case WFM_PHASE: return wfm_apply_j_phase(h, q, out, n);
+        case WFM_MODULUS: return wfm_apply_j_modulus(h, q, out, n);
+        default: return h->fail(WFM_ERR_INVALID_ARG, "DoubleShapedVector grad does not belong to any space");
+    }
+}
+
+int wfm_apply_j_all(wfm_model* h, const void* q, double* d3, double* ph, double* mo) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    unsigned kinds = 0;
+    if (d3) kinds |= WFM_J_DEFOCUS;
+    if (ph) kinds |= WFM_J_PHASE;
+    if (mo) kinds |= WFM_J_MODULUS;
+    std::vector<double> g;
+    int rc = apply_host(h, kinds, q, g); if (rc) return rc;
+    if (d3) memcpy(d3, g.data(), 24);
+    if (ph) memcpy(ph, g.data() + 3, 8 * (size_t)h->nphase);
+    if (mo) memcpy(mo, g.data() + 3 + h->nphase, 8 * (size_t)h->nmod);
+    return WFM_OK;
+}
+
+int wfm_fill_uniform(wfm_model* h, void* dev, int precision, uint64_t seed, uint64_t first, uint64_t count) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!dev) return h->fail(WFM_ERR_INVALID_ARG, "dev_ptr is NULL");
+    WFM_CK(h, cudaSetDevice(h->device));
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    if (precision == WFM_F64) {
+        auto kfn = &k_fill_uniform<double>;
+        WFM_LAUNCH(kfn, dim3(grid), dim3(256), 0, h->stream, (double*)dev, seed, first, count);
+    } else {
+        auto kfn = &k_fill_uniform<float>;
+        WFM_LAUNCH(kfn, dim3(grid), dim3(256), 0, h->stream, (float*)dev, seed, first, count);
+    }
+    WFM_CK_LAUNCH(h, "k_fill_uniform");
+    return WFM_OK;
+}
+
+int wfm_host_alloc(void** out, size_t bytes) {
+    if (!out) return WFM_ERR_INVALID_ARG;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? WFM_OK : WFM_ERR_NOMEM;
+}
+int wfm_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? WFM_OK : WFM_ERR_CUDA; }
+
+int wfm_get_info(const wfm_model* h, int* nx, int* ny, int* nzg, int* z0, int* nzl, int* prec, int* nzern,
+                 int* nphase, int* nmod) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (nx) *nx = h->N;
+    if (ny) *ny = h->N;
+    if (nzg) *nzg = h->nz_global;
+    if (z0) *z0 = h->z0;
+    if (nzl) *nzl = h->nzl;
+    if (prec) *prec = h->precision;
+    if (nzern) *nzern = h->nzern;
+    if (nphase) *nphase = h->nphase;
+    if (nmod) *nmod = h->nmod;
+    return WFM_OK;
+}
+
+int wfm_active_extent(const wfm_model* h, int* nax, int* nay) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    int rc = rebuild_activity(const_cast<wfm_model*>(h)); if (rc) return rc;
+    if (nax) *nax = h->nax;
+    if (nay) *nay = h->nay;
+    return WFM_OK;
+}
+
+uint64_t wfm_launch_count(void) {
+#ifdef WFM_EMU
+    return emu::launch_counter().load();
+#else
+    return wfm::launch_counter().load();
+#endif
+}
+
+const char* wfm_version(void) {
+#ifdef WFM_EMU
+    return "microtipi_b200 0.1 (CPU emulation build: tests only)";
+#else
+    return "microtipi_b200 0.1 (sm_100a)";
+#endif
+}
+
+}  // extern "C"

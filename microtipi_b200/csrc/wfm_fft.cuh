@@ -1,0 +1,211 @@
+// wfm_fft.cuh -- batched in-register / shared-memory complex FFT engine for sm_100a.
+//
+// Replaces JTransforms' DoubleFFT_2D / FloatFFT_2D.complexForward (call sites
+// WideFieldModel.java:319-321, 604-605, 917-918, 1241-1242 and the Float twins 248-249,
+// 476-477, 781-782, 1099-1100): unnormalised forward transform, kernel e^{-2 pi i jk/N}.
+//
+// One transform of length N is computed by T = N/E threads, each holding E complex values in
+// registers.  N = R1*R2*R3 (R3 == 1 for a two-stage plan); every stage is a set of radix-R
+// butterflies done entirely in registers, with one shared-memory exchange between stages
+// (decimation in frequency, in place, so a stage reads and writes the same smem cells and needs a
+// single barrier).  Thread -> butterfly maps are chosen so that
+//     input  slot v[u*R1 + r] = x[(t + T*u) + (N/R1)*r]
+//     output slot v[u*RL + r] = X[(t + T*u) + (N/RL)*r]        (RL = last radix)
+// i.e. consecutive threads own consecutive indices on both sides -> coalesced global access
+// with no extra reordering pass.
+//
+// Two shared-memory layouts:
+//   RowLayout  -- the transform runs along the contiguous axis; each transform has a private,
+//                 padded row (padding chosen by tools/bank_conflicts.py: conflict-free for fp64).
+//   ColLayout  -- C transforms (adjacent columns) run side by side, column index innermost, so
+//                 every access of 8 adjacent lanes is one 128-byte wavefront by construction.
+#pragma once
+
+#include "wfm_platform.cuh"
+
+#define WFM_DEVI __device__ __forceinline__
+
+namespace wfm {
+
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+template <typename T> using cx = typename Vec2<T>::type;
+
+template <typename T> WFM_DEVI cx<T> mkc(T a, T b) { cx<T> r; r.x = a; r.y = b; return r; }
+template <typename C> WFM_DEVI C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> WFM_DEVI C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C> WFM_DEVI C cmul(C a, C w) { C r; r.x = a.x * w.x - a.y * w.y; r.y = a.x * w.y + a.y * w.x; return r; }
+// x * (-i)
+template <typename C> WFM_DEVI C mul_neg_i(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
+
+// ---- multiply by W16^M = exp(-2 pi i M/16), M in [0,8), all folded at compile time ---------
+template <typename T, int M> struct MulW16 {
+    static WFM_DEVI cx<T> run(cx<T> a) {
+        if constexpr (M == 0) {
+            return a;
+        } else if constexpr (M >= 4) {
+            return mul_neg_i(MulW16<T, M - 4>::run(a));
+        } else if constexpr (M == 2) {
+            const T s = (T)0.70710678118654752440084436210484903928;
+            return mkc<T>((a.x + a.y) * s, (a.y - a.x) * s);
+        } else {
+            const T c = (M == 1) ? (T)0.92387953251128675612818318939678828682 : (T)0.38268343236508977172845998403039886676;
+            const T s = (M == 1) ? (T)0.38268343236508977172845998403039886676 : (T)0.92387953251128675612818318939678828682;
+            return mkc<T>(a.x * c + a.y * s, a.y * c - a.x * s);
+        }
+    }
+};
+
+// ---- radix-R DFT in registers, natural-order in and out (radix-2 DIT recursion) ------------
+template <typename T, int R> struct Dft;
+
+template <typename T, int R, int K> struct DftCombine {
+    static WFM_DEVI void run(cx<T> (&v)[R], const cx<T> (&e)[R / 2], const cx<T> (&o)[R / 2]) {
+        const cx<T> t = MulW16<T, K * (16 / R)>::run(o[K]);
+        v[K] = cadd(e[K], t);
+        v[K + R / 2] = csub(e[K], t);
+        if constexpr (K + 1 < R / 2) DftCombine<T, R, K + 1>::run(v, e, o);
+    }
+};
+
+template <typename T> struct Dft<T, 1> {
+    static WFM_DEVI void run(cx<T> (&)[1]) {}
+};
+template <typename T> struct Dft<T, 2> {
+    static WFM_DEVI void run(cx<T> (&v)[2]) {
+        const cx<T> a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+template <typename T, int R> struct Dft {
+    static_assert(R == 4 || R == 8 || R == 16, "radix");
+    static WFM_DEVI void run(cx<T> (&v)[R]) {
+        cx<T> e[R / 2], o[R / 2];
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+        Dft<T, R / 2>::run(e);
+        Dft<T, R / 2>::run(o);
+        DftCombine<T, R, 0>::run(v, e, o);
+    }
+};
+
+// ---- plans ---------------------------------------------------------------------------------
+template <int N_, int E_, int R1_, int R2_, int R3_> struct PlanBase {
+    static constexpr int N = N_, E = E_, R1 = R1_, R2 = R2_, R3 = R3_;
+    static_assert(R1 * R2 * R3 == N, "factorisation");
+    static_assert(E % R1 == 0 && E % R2 == 0 && E % R3 == 0, "radix must divide E");
+    static constexpr int T = N / E;                  // threads per transform
+    static constexpr int S1 = N / R1;                // stage-1 leg stride
+    static constexpr bool THREE = (R3 > 1);
+    static constexpr int RL = THREE ? R3 : R2;       // last radix
+    static constexpr int SL = N / RL;                // output leg stride
+};
+
+template <int N> struct Plan;
+template <> struct Plan<32> : PlanBase<32, 8, 8, 4, 1> {};
+template <> struct Plan<64> : PlanBase<64, 8, 8, 8, 1> {};
+template <> struct Plan<128> : PlanBase<128, 8, 8, 4, 4> {};
+template <> struct Plan<256> : PlanBase<256, 8, 8, 8, 4> {};
+template <> struct Plan<512> : PlanBase<512, 8, 8, 8, 8> {};
+template <> struct Plan<1024> : PlanBase<1024, 16, 16, 8, 8> {};
+template <> struct Plan<2048> : PlanBase<2048, 16, 16, 16, 8> {};
+
+// Row padding shifts (PA, PB): pad(i) = i + (i >> PA) + (i >> PB), 0 disables a term.
+template <int N, int ESZ> struct RowPad;
+template <> struct RowPad<32, 16> { static constexpr int PA = 3, PB = 4; };
+template <> struct RowPad<64, 16> { static constexpr int PA = 3, PB = 0; };
+template <> struct RowPad<128, 16> { static constexpr int PA = 0, PB = 4; };
+template <> struct RowPad<256, 16> { static constexpr int PA = 3, PB = 6; };
+template <> struct RowPad<512, 16> { static constexpr int PA = 0, PB = 6; };
+template <> struct RowPad<1024, 16> { static constexpr int PA = 0, PB = 6; };
+template <> struct RowPad<2048, 16> { static constexpr int PA = 0, PB = 7; };
+template <> struct RowPad<32, 8> { static constexpr int PA = 3, PB = 4; };
+template <> struct RowPad<64, 8> { static constexpr int PA = 3, PB = 5; };
+template <> struct RowPad<128, 8> { static constexpr int PA = 2, PB = 0; };
+template <> struct RowPad<256, 8> { static constexpr int PA = 0, PB = 4; };
+template <> struct RowPad<512, 8> { static constexpr int PA = 0, PB = 6; };
+template <> struct RowPad<1024, 8> { static constexpr int PA = 0, PB = 6; };
+template <> struct RowPad<2048, 8> { static constexpr int PA = 4, PB = 8; };
+
+template <typename T, int N> struct RowLayout {
+    using P = RowPad<N, (int)sizeof(cx<T>)>;
+    __host__ __device__ static constexpr int pad_c(int i) { return i + (P::PA ? (i >> P::PA) : 0) + (P::PB ? (i >> P::PB) : 0); }
+    static constexpr int LEN = pad_c(N - 1) + 1;      // cells per transform
+    static WFM_DEVI int at(int i) { return pad_c(i); }
+};
+
+template <int C> struct ColLayout {
+    static WFM_DEVI int at(int i) { return i * C; }
+};
+
+// ---- the engine ----------------------------------------------------------------------------
+// v   : E register values of this thread (slot convention above)
+// sm  : base of this transform's shared cells (RowLayout: private row; ColLayout: smem + column)
+// t   : thread index inside the transform, [0, T)
+// tw  : W_N table in global memory, tw[m] = exp(-2 pi i m / N), m in [0, N)
+// All threads of the CTA must call this together (it contains CTA-wide barriers).  The caller
+// must place a barrier between the end of one call and the start of the next one that reuses sm.
+template <typename T, class P, class L>
+WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* __restrict__ tw) {
+    constexpr int E = P::E, R1 = P::R1, R2 = P::R2, R3 = P::R3, TT = P::T, S1 = P::S1;
+    // stage 1: radix R1 over legs of stride S1, twiddle W_N^(b*k1), scatter to cell k1*S1 + b
+#pragma unroll
+    for (int u = 0; u < E / R1; ++u) {
+        cx<T> a[R1];
+#pragma unroll
+        for (int r = 0; r < R1; ++r) a[r] = v[u * R1 + r];
+        Dft<T, R1>::run(a);
+        const int b = t + TT * u;
+        sm[L::at(b)] = a[0];
+#pragma unroll
+        for (int k = 1; k < R1; ++k) sm[L::at(k * S1 + b)] = cmul(a[k], __ldg(&tw[b * k]));
+    }
+    __syncthreads();
+    if constexpr (P::THREE) {
+        // stage 2: inside block k1, radix R2 over legs of stride R3, twiddle W_N^(R1*d3*k2)
+#pragma unroll
+        for (int u = 0; u < E / R2; ++u) {
+            const int b = t + TT * u;
+            const int k1 = b / R3, d3 = b % R3;
+            const int base = k1 * S1 + d3;
+            cx<T> a[R2];
+#pragma unroll
+            for (int r = 0; r < R2; ++r) a[r] = sm[L::at(base + r * R3)];
+            Dft<T, R2>::run(a);
+            sm[L::at(base)] = a[0];
+#pragma unroll
+            for (int k = 1; k < R2; ++k) sm[L::at(base + k * R3)] = cmul(a[k], __ldg(&tw[R1 * d3 * k]));
+        }
+        __syncthreads();
+        // stage 3: radix R3 over adjacent cells; butterfly b = k1 + R1*k2 -> X[b + (N/R3)*r]
+#pragma unroll
+        for (int u = 0; u < E / R3; ++u) {
+            const int b = t + TT * u;
+            const int k1 = b % R1, k2 = b / R1;
+            const int base = k1 * S1 + k2 * R3;
+            cx<T> a[R3];
+#pragma unroll
+            for (int r = 0; r < R3; ++r) a[r] = sm[L::at(base + r)];
+            Dft<T, R3>::run(a);
+#pragma unroll
+            for (int r = 0; r < R3; ++r) v[u * R3 + r] = a[r];
+        }
+    } else {
+        // last stage of a two-stage plan: radix R2 over adjacent cells of block k1 = b
+#pragma unroll
+        for (int u = 0; u < E / R2; ++u) {
+            const int b = t + TT * u;
+            const int base = b * S1;
+            cx<T> a[R2];
+#pragma unroll
+            for (int r = 0; r < R2; ++r) a[r] = sm[L::at(base + r)];
+            Dft<T, R2>::run(a);
+#pragma unroll
+            for (int r = 0; r < R2; ++r) v[u * R2 + r] = a[r];
+        }
+    }
+}
+
+}  // namespace wfm

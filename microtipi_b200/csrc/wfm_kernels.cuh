@@ -1,0 +1,579 @@
+// wfm_kernels.cuh -- CUDA kernels of the widefield PSF path (sm_100a).
+//
+// WFM = /root/reference/src/microTiPi/epifluorescence/WideFieldModel.java ("para" branches).
+//
+// Data layout in HBM (TiPi first-index-fastest, see include/wfm_b200.h):
+//   rho, phi, psi : double[Npix]            pupil modulus / phase / defocus function
+//   mask, support : uint8[Npix]             maskPupil; support = pixels that can be non-zero
+//   Z             : double[nzern][Npix]     orthonormal Zernike basis
+//   cpx           : cx<T>[nzl][Npix]        conj(FFT2(A_z))            (WFM:325-326)
+//   psf           : T[nzl][Npix]            |a|^2 * PSFnorm           (WFM:327)
+//   T1            : cx<T>[nzl][nay][N]      row-pass output of the PSF transform (active rows only)
+//   T2            : cx<T>[nzl][N][pitch]    row-pass output of the adjoint transform (active kx only)
+//   Gp            : double[3][nsub][N][pitch]  per-plane-group partial images of the Jacobians
+//
+// Pruning (quirk Q6): the pupil is zero outside `support`, so the forward transform only
+// row-transforms the `nay` rows that intersect it, and the adjoint transform only keeps /
+// column-transforms the `nax` columns that intersect it.  Results are identical.
+#pragma once
+#include "wfm_fft.cuh"
+
+#include <stdint.h>
+
+namespace wfm {
+
+#define WFM_MAX_COEF 128
+
+struct Coefs { double v[WFM_MAX_COEF]; };
+
+// ---- plane geometry ------------------------------------------------------------------------
+struct Geom {
+    int N;          // Nx == Ny (WFM:158)
+    int nz_global;  // Nz of the whole stack: drives PSFnorm and the wrap rule
+    int z0;         // first plane of this slab
+    int nzl;        // planes in this slab
+    double dz;
+    double psf_norm;  // 1/(Nx*Ny*Nz)  WFM:284
+};
+
+// defoc_scale = DEUXPI*(iz - Nz)*dz or DEUXPI*iz*dz, strict '>' (WFM:302-309); evaluated left to
+// right without fused multiply-add, like the JVM.
+WFM_DEVI double defoc_scale_dev(int iz, int Nz, double dz) {
+    const int zi = (iz > Nz / 2) ? iz - Nz : iz;
+    return __dmul_rn(__dmul_rn(6.283185307179586, (double)zi), dz);
+}
+// defoc = (iz - Nz)*dz or iz*dz (WFM:1220-1229)
+WFM_DEVI double defoc_depth_dev(int iz, int Nz, double dz) {
+    const int zi = (iz > Nz / 2) ? iz - Nz : iz;
+    return __dmul_rn((double)zi, dz);
+}
+WFM_DEVI int kappa_dev(int n, int N) { return (n > N / 2) ? n - N : n; }
+
+// ---- launch shapes --------------------------------------------------------------------------
+// Row kernels: RB transforms per CTA, 256 threads.  Column kernels: C adjacent columns per CTA.
+template <int N> struct RowCfg {
+    static constexpr int T = Plan<N>::T;
+    static constexpr int RB = (256 / T) < N ? (256 / T) : N;
+    static constexpr int THREADS = RB * T;
+};
+template <typename T, int N> struct ColCfg {
+    static constexpr int TT = Plan<N>::T;
+    // 8 fp64 (16 fp32) adjacent columns = one 128-byte wavefront; more columns when the transform
+    // is short so that a CTA has at least 128 threads; fewer when shared memory would overflow.
+    static constexpr int BASE = (sizeof(T) == 8) ? 8 : 16;
+    static constexpr int WANT = (128 / TT) > BASE ? (128 / TT) : BASE;
+    static constexpr int FIT = (int)((200 * 1024) / (sizeof(cx<T>) * N));
+    static constexpr int C0 = WANT < FIT ? WANT : FIT;
+    static constexpr int C = C0 >= 32 ? 32 : (C0 >= 16 ? 16 : (C0 >= 8 ? 8 : 4));
+    static constexpr int THREADS = C * TT;
+    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)N * C;
+};
+// planes accumulated in registers by one column CTA of the adjoint pass
+#define WFM_JAC_BS 4
+
+// ================================================================================================
+// pupil construction (elementwise; arithmetic mirrors the JVM: no FMA contraction)
+// ================================================================================================
+
+// computeMaskPupil() WFM:1374-1406
+__global__ void k_mask_pupil(uint8_t* __restrict__ map, uint8_t* __restrict__ mask, int N, double dxy,
+                             double radius /* NA/lambda */) {
+    const int in = blockIdx.x * blockDim.x + threadIdx.x;
+    if (in >= N * N) return;
+    const int nx = in % N, ny = in / N;
+    const double s0 = 1.0 / dxy / (double)N;          // Math.pow(1/dxy/N, 2)
+    const double scale = __dmul_rn(s0, s0);
+    const double iy = (double)(ny < N - ny ? ny : N - ny);
+    const double ix = (double)(nx < N - nx ? nx : N - nx);
+    const double ry = __dmul_rn(__dmul_rn(iy, iy), scale);
+    const double rx = __dmul_rn(__dmul_rn(ix, ix), scale);
+    const uint8_t m = (__dadd_rn(rx, ry) < __dmul_rn(radius, radius)) ? 1 : 0;
+    map[in] = m;
+    mask[in] = m;
+}
+
+// computeDefocus() WFM:1452-1499: only mapPupil pixels are touched.
+__global__ void k_compute_defocus(double* __restrict__ psi, uint8_t* __restrict__ mask,
+                                  const uint8_t* __restrict__ map, int N, double dxy, double lambda_ni,
+                                  double deltaX, double deltaY) {
+    const int in = blockIdx.x * blockDim.x + threadIdx.x;
+    if (in >= N * N) return;
+    if (!map[in]) return;
+    const int nx = in % N, ny = in / N;
+    const double scale = 1.0 / __dmul_rn((double)N, dxy);
+    const double ay = __dsub_rn(__dmul_rn(scale, (double)kappa_dev(ny, N)), deltaY);
+    const double ax = __dsub_rn(__dmul_rn(scale, (double)kappa_dev(nx, N)), deltaX);
+    const double ry = __dmul_rn(ay, ay), rx = __dmul_rn(ax, ax);
+    const double q = __dsub_rn(__dsub_rn(__dmul_rn(lambda_ni, lambda_ni), rx), ry);
+    if (q < 0.0) { psi[in] = 0.0; mask[in] = 0; }
+    else { psi[in] = __dsqrt_rn(q); mask[in] = 1; }
+}
+
+// setPhase() WFM:1625-1649: phi = sum_n Z[in + (n+off)*Npix]*alpha_n on maskPupil, else 0
+__global__ void k_set_phase(double* __restrict__ phi, const double* __restrict__ Z,
+                            const uint8_t* __restrict__ mask, Coefs alpha, int n, int off, int npix) {
+    const int in = blockIdx.x * blockDim.x + threadIdx.x;
+    if (in >= npix) return;
+    double acc = 0.0;
+    if (mask[in]) {
+        for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(Z[in + (size_t)(k + off) * npix], alpha.v[k]));
+    }
+    phi[in] = acc;
+}
+
+// setModulus() WFM:1588-1610: rho = sum_n Z[in + n*Npix]*beta_n*betaNorm on maskPupil, else 0
+__global__ void k_set_modulus(double* __restrict__ rho, const double* __restrict__ Z,
+                              const uint8_t* __restrict__ mask, Coefs beta, int n, double beta_norm, int npix) {
+    const int in = blockIdx.x * blockDim.x + threadIdx.x;
+    if (in >= npix) return;
+    double acc = 0.0;
+    if (mask[in]) {
+        for (int k = 0; k < n; ++k)
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(Z[in + (size_t)k * npix], beta.v[k]), beta_norm));
+    }
+    rho[in] = acc;
+}
+
+// ================================================================================================
+// Zernike basis on the device: Zernike.zernikeArray (Zernike.java:119-288) + Gram-Schmidt (WFM:196)
+// ================================================================================================
+#define WFM_ZERN_MAXS 16   // radial polynomial terms per mode: supports radial degree n <= 30
+
+struct ZernMode {
+    int n, m;
+    int kind;          // 0: m == 0, 1: cosine (Noll index even), 2: sine (Noll index odd)
+    double norm;       // sqrt(n+1) or sqrt(2(n+1))          Zernike.java:222,245,267
+    double R[WFM_ZERN_MAXS];   // (-1)^s (n-s)!/(s!(p-s)!(q-s)!)  Zernike.java:70-90
+};
+
+// One thread per pixel, all modes.  r = sqrt(kx^2+ky^2), theta = atan2(ky, kx) in FFT order
+// (TiPi MathUtils.fftDist1D / fftAngle1D -- source unavailable, ASSUMED).
+__global__ void k_zernike_modes(double* __restrict__ Z, const ZernMode* __restrict__ modes, int nzern,
+                                int nmax, int N, double radius_px) {
+    const int in = blockIdx.x * blockDim.x + threadIdx.x;
+    const int npix = N * N;
+    if (in >= npix) return;
+    const double kx = (double)kappa_dev(in % N, N), ky = (double)kappa_dev(in / N, N);
+    const double r = __dsqrt_rn(__dadd_rn(__dmul_rn(kx, kx), __dmul_rn(ky, ky)));
+    const bool inside = r < radius_px;                                  // strict, Zernike.java:146
+    double rP[2 * WFM_ZERN_MAXS];
+    rP[0] = inside ? 1.0 : 0.0;
+    rP[1] = inside ? __ddiv_rn(r, radius_px) : 0.0;                     // Zernike.java:150
+    for (int k = 2; k <= nmax; ++k) rP[k] = __dmul_rn(rP[k - 1], rP[1]);  // Zernike.java:171,205
+    const double theta = atan2(ky, kx);
+    Z[in] = inside ? 1.0 : 0.0;                                         // piston, Zernike.java:149
+    for (int nz = 1; nz < nzern; ++nz) {
+        const ZernMode md = modes[nz];
+        double zr = 0.0;
+        for (int s = (md.n - md.m) / 2; s >= 0; --s) zr = __dadd_rn(zr, __dmul_rn(md.R[s], rP[md.n - 2 * s]));
+        double val = __dmul_rn(md.norm, zr);
+        if (md.kind == 1) val = __dmul_rn(val, cos(__dmul_rn((double)md.m, theta)));
+        else if (md.kind == 2) val = __dmul_rn(val, sin(__dmul_rn((double)md.m, theta)));
+        Z[in + (size_t)nz * npix] = val;
+    }
+}
+
+#define WFM_DOT_THREADS 256
+// partial[b] = sum over the block's grid-stride slice of a[i]*b[i]   (warp shuffle, then block)
+__global__ void __launch_bounds__(WFM_DOT_THREADS) k_dot_partial(const double* __restrict__ a,
+                                                                const double* __restrict__ b, int n,
+                                                                double* __restrict__ partial) {
+    __shared__ double red[WFM_DOT_THREADS / 32];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += a[i] * b[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0.0;
+        for (int w = 0; w < WFM_DOT_THREADS / 32; ++w) x += red[w];
+        partial[blockIdx.x] = x;
+    }
+}
+// mode 0: zk -= dot*zj (Gram-Schmidt projection).  mode 1: zk *= 1/sqrt(dot) (normalisation).
+// dot = fixed-order sum of the partials, recomputed by every thread's block leader.
+__global__ void k_gs_update(double* __restrict__ zk, const double* __restrict__ zj,
+                            const double* __restrict__ partial, int nparts, int n, int mode) {
+    __shared__ double dot_s;
+    if (threadIdx.x == 0) {
+        double x = 0.0;
+        for (int b = 0; b < nparts; ++b) x += partial[b];
+        dot_s = x;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (mode == 0) zk[i] = zk[i] - dot_s * zj[i];
+    else zk[i] = zk[i] * (1.0 / sqrt(dot_s));
+}
+
+// counter-based splitmix64 uniform(-1,1)  (oracle: splitmix64_uniform)
+template <typename T>
+__global__ void k_fill_uniform(T* __restrict__ out, uint64_t seed, uint64_t first, uint64_t count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t z = (first + i) * 0x9E3779B97F4A7C15ull + seed + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    out[i] = (T)__dsub_rn(__dmul_rn(2.0, u), 1.0);
+}
+
+// ================================================================================================
+// computePsf()  WFM:280-350 (fp32: 209-278)
+// ================================================================================================
+template <typename T> struct PsfArgs {
+    Geom g;
+    const double* rho; const double* phi; const double* psi;
+    const int* act_y;   // [nay] active rows
+    const int* inv_y;   // [N]   row -> compact index or -1
+    int nay;
+    const cx<T>* tw;    // W_N table
+    cx<T>* T1;
+    cx<T>* cpx;
+    T* psf;
+    int plane0;         // first local plane of this launch
+};
+
+// Pass 1: A = rho*exp(i(phi + defoc_scale*psi)) synthesised in the load (WFM:311-316), FFT along x
+// for the active rows only.
+template <typename T, int N>
+__global__ void __launch_bounds__(RowCfg<N>::THREADS) k_psf_rows(PsfArgs<T> a) {
+    using P = Plan<N>;
+    using L = RowLayout<T, N>;
+    constexpr int RB = RowCfg<N>::RB, TT = P::T, E = P::E;
+    WFM_DYN_SMEM(cx<T>, smem);
+    const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
+    const int yi = blockIdx.x * RB + slot;
+    const bool valid = yi < a.nay;
+    const int y = valid ? a.act_y[yi] : 0;
+    const int pl = a.plane0 + blockIdx.y;
+    const double s = defoc_scale_dev(a.g.z0 + pl, a.g.nz_global, a.g.dz);
+    cx<T> v[E];
+#pragma unroll
+    for (int u = 0; u < E / P::R1; ++u) {
+#pragma unroll
+        for (int r = 0; r < P::R1; ++r) {
+            const int x = (t + TT * u) + P::S1 * r;
+            const int in = x + N * y;
+            const double rho = valid ? __ldg(&a.rho[in]) : 0.0;
+            cx<T> val = mkc<T>((T)0, (T)0);
+            if (rho != 0.0) {
+                const double ph = __dadd_rn(__ldg(&a.phi[in]), __dmul_rn(s, __ldg(&a.psi[in])));
+                double sn, cs;
+                sincos(ph, &sn, &cs);
+                val = mkc<T>((T)__dmul_rn(rho, cs), (T)__dmul_rn(rho, sn));
+            }
+            v[u * P::R1 + r] = val;
+        }
+    }
+    fft_inplace<T, P, L>(v, smem + slot * L::LEN, t, a.tw);
+    if (valid) {
+        cx<T>* dst = a.T1 + ((size_t)pl * a.nay + yi) * N;
+#pragma unroll
+        for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+            for (int r = 0; r < P::RL; ++r) dst[(t + TT * u) + P::SL * r] = v[u * P::RL + r];
+    }
+}
+
+// Pass 2: FFT along y for every column (inactive rows are zero), then the fused store of
+// conj(a) and |a|^2*PSFnorm (WFM:323-328).
+template <typename T, int N>
+__global__ void __launch_bounds__(ColCfg<T, N>::THREADS) k_psf_cols(PsfArgs<T> a) {
+    using P = Plan<N>;
+    constexpr int C = ColCfg<T, N>::C, TT = P::T, E = P::E;
+    using L = ColLayout<C>;
+    WFM_DYN_SMEM(cx<T>, smem);
+    const int c = threadIdx.x % C, t = threadIdx.x / C;
+    const int kx = blockIdx.x * C + c;
+    const int pl = a.plane0 + blockIdx.y;
+    const cx<T>* src = a.T1 + (size_t)pl * a.nay * N + kx;
+    cx<T> v[E];
+#pragma unroll
+    for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+        for (int r = 0; r < P::R1; ++r) {
+            const int y = (t + TT * u) + P::S1 * r;
+            const int yi = __ldg(&a.inv_y[y]);
+            v[u * P::R1 + r] = (yi >= 0) ? __ldcg(&src[(size_t)yi * N]) : mkc<T>((T)0, (T)0);
+        }
+    fft_inplace<T, P, L>(v, smem + c, t, a.tw);
+    const T norm = (T)a.g.psf_norm;
+    const size_t base = (size_t)pl * N * N + kx;
+#pragma unroll
+    for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+        for (int r = 0; r < P::RL; ++r) {
+            const int ky = (t + TT * u) + P::SL * r;
+            const cx<T> val = v[u * P::RL + r];
+            const size_t o = base + (size_t)N * ky;
+            a.cpx[o] = mkc<T>(val.x, -val.y);                     // store conjugate of A (WFM:326)
+            if constexpr (sizeof(T) == 8)
+                a.psf[o] = (T)__dmul_rn(__dadd_rn(__dmul_rn(val.x, val.x), __dmul_rn(val.y, val.y)), norm);
+            else
+                a.psf[o] = (T)__fmul_rn(__fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y)), norm);
+        }
+}
+
+// ================================================================================================
+// apply_J_phase / apply_J_defocus / apply_J_modulus   WFM:883-965, 1201-1288, 566-683
+// ================================================================================================
+template <typename T> struct JacArgs {
+    Geom g;
+    const cx<T>* cpx;
+    const T* q;
+    const double* rho; const double* phi; const double* psi;
+    const uint8_t* mask; const uint8_t* support;
+    const int* act_x;  // [nax]
+    const int* inv_x;  // [N]
+    int nax;
+    int pitch;         // nax rounded up to a multiple of the column tile
+    const cx<T>* tw;
+    cx<T>* T2;
+    double* Gp;        // [3][nsub][N][pitch]
+    int nsub;
+    int last_plane_only;  // quirk Q1 compat mode for the modulus Jacobian
+    int plane0;
+};
+
+// Pass 1: Aq = conj(a)*q fused into the load (WFM:907-914), FFT along x, keep active kx only.
+template <typename T, int N>
+__global__ void __launch_bounds__(RowCfg<N>::THREADS) k_jac_rows(JacArgs<T> a) {
+    using P = Plan<N>;
+    using L = RowLayout<T, N>;
+    constexpr int RB = RowCfg<N>::RB, TT = P::T, E = P::E;
+    WFM_DYN_SMEM(cx<T>, smem);
+    const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
+    const int y = blockIdx.x * RB + slot;
+    const bool valid = y < N;
+    const int pl = a.plane0 + blockIdx.y;
+    const size_t base = (size_t)pl * N * N + (size_t)N * (valid ? y : 0);
+    cx<T> v[E];
+#pragma unroll
+    for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+        for (int r = 0; r < P::R1; ++r) {
+            const int x = (t + TT * u) + P::S1 * r;
+            const cx<T> av = a.cpx[base + x];
+            const T qv = a.q[base + x];
+            v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
+        }
+    fft_inplace<T, P, L>(v, smem + slot * L::LEN, t, a.tw);
+    if (valid) {
+        cx<T>* dst = a.T2 + ((size_t)pl * N + y) * a.pitch;
+#pragma unroll
+        for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+            for (int r = 0; r < P::RL; ++r) {
+                const int k = (t + TT * u) + P::SL * r;
+                const int xi = __ldg(&a.inv_x[k]);
+                if (xi >= 0) dst[xi] = v[u * P::RL + r];
+            }
+    }
+}
+
+// Pass 2: FFT along y for the active columns, then the masked trig products of the three
+// Jacobians, accumulated in registers over WFM_JAC_BS consecutive planes:
+//   jin  = rho*(B_re sin ph + B_im cos ph)      on maskPupil   (WFM:925-928, 1253)
+//   gP  += jin ; gD += defoc*jin                                 (phase / defocus integrands)
+//   gM  += B_re cos ph - B_im sin ph            on the support (WFM:607-611)
+template <typename T, int N, bool MOD>
+__global__ void __launch_bounds__(ColCfg<T, N>::THREADS) k_jac_cols(JacArgs<T> a) {
+    using P = Plan<N>;
+    constexpr int C = ColCfg<T, N>::C, TT = P::T, E = P::E;
+    using L = ColLayout<C>;
+    WFM_DYN_SMEM(cx<T>, smem);
+    const int c = threadIdx.x % C, t = threadIdx.x / C;
+    const int xi = blockIdx.x * C + c;
+    const bool colvalid = xi < a.nax;
+    const int kx = colvalid ? a.act_x[xi] : 0;
+    const int sub = blockIdx.y;
+    const int p0 = a.plane0 + sub * WFM_JAC_BS;
+    const int p1 = (p0 + WFM_JAC_BS < a.g.nzl) ? p0 + WFM_JAC_BS : a.g.nzl;
+
+    double rho_e[E], phi_e[E], psi_e[E], accP[E], accD[E], accM[MOD ? E : 1];
+    unsigned mbits = 0, sbits = 0;
+#pragma unroll
+    for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+        for (int r = 0; r < P::RL; ++r) {
+            const int e = u * P::RL + r;
+            const int ky = (t + TT * u) + P::SL * r;
+            const int in = kx + N * ky;
+            const bool sup = colvalid && a.support[in];
+            const bool m = sup && a.mask[in];
+            rho_e[e] = sup ? a.rho[in] : 0.0;
+            phi_e[e] = sup ? a.phi[in] : 0.0;
+            psi_e[e] = sup ? a.psi[in] : 0.0;
+            mbits |= (m ? 1u : 0u) << e;
+            sbits |= (sup ? 1u : 0u) << e;
+            accP[e] = 0.0; accD[e] = 0.0;
+            if constexpr (MOD) accM[e] = 0.0;
+        }
+
+    for (int pl = p0; pl < p1; ++pl) {
+        const int iz = a.g.z0 + pl;
+        const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
+        const double dfc = defoc_depth_dev(iz, a.g.nz_global, a.g.dz);
+        const bool mod_plane = MOD && (!a.last_plane_only || iz == a.g.nz_global - 1);
+        const cx<T>* src = a.T2 + (size_t)pl * N * a.pitch + xi;
+        cx<T> v[E];
+#pragma unroll
+        for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+            for (int r = 0; r < P::R1; ++r) {
+                const int y = (t + TT * u) + P::S1 * r;
+                v[u * P::R1 + r] = colvalid ? __ldcg(&src[(size_t)y * a.pitch]) : mkc<T>((T)0, (T)0);
+            }
+        fft_inplace<T, P, L>(v, smem + c, t, a.tw);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const bool m = (mbits >> e) & 1u;
+            const bool sup = (sbits >> e) & 1u;
+            if (m || (mod_plane && sup)) {
+                const double ph = __dadd_rn(phi_e[e], __dmul_rn(s, psi_e[e]));
+                double sn, cs;
+                sincos(ph, &sn, &cs);
+                const double br = (double)v[e].x, bi = (double)v[e].y;
+                if (m) {
+                    const double jin = rho_e[e] * (br * sn + bi * cs);
+                    accP[e] += jin;
+                    accD[e] += dfc * jin;
+                }
+                if constexpr (MOD) { if (mod_plane) accM[e] += br * cs - bi * sn; }
+            }
+        }
+        __syncthreads();  // the next plane's stage-1 stores reuse the shared cells
+    }
+
+    const size_t img = (size_t)N * a.pitch;
+#pragma unroll
+    for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+        for (int r = 0; r < P::RL; ++r) {
+            const int e = u * P::RL + r;
+            const int ky = (t + TT * u) + P::SL * r;
+            const size_t o = (size_t)ky * a.pitch + xi;
+            a.Gp[((size_t)0 * a.nsub + sub) * img + o] = accP[e];
+            a.Gp[((size_t)1 * a.nsub + sub) * img + o] = accD[e];
+            if constexpr (MOD) a.Gp[((size_t)2 * a.nsub + sub) * img + o] = accM[e];
+        }
+}
+
+// ---- contraction of the partial images with the basis: warp-then-block reductions --------------
+struct ReduceArgs {
+    Geom g;
+    const double* Gp; int nsub; int pitch; int nax;
+    const int* act_x;
+    const double* Z; const double* psi; const uint8_t* mask;
+    int nphase, nmod, phase_off;
+    unsigned kinds;
+    double dxy, lambda_ni, deltaX, deltaY;
+    double* block_part;   // [nblocks][glen]
+    int glen;             // 3 + nphase + nmod
+};
+
+#define WFM_RED_THREADS 256
+#define WFM_RED_CHUNK 8
+
+// One thread per (ky, xi) cell of the compact pupil strip.  Sums the plane-group partials in
+// fixed order, then forms the glen dot products WFM_RED_CHUNK at a time: shuffle-reduce inside
+// each warp, then across the warps of the block through shared memory.
+__global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
+    __shared__ double red[WFM_RED_THREADS / 32][WFM_RED_CHUNK];
+    const int N = a.g.N;
+    const size_t img = (size_t)N * a.pitch;
+    const size_t cell = (size_t)blockIdx.x * WFM_RED_THREADS + threadIdx.x;
+    const bool in_range = cell < img;
+    const int ky = in_range ? (int)(cell / a.pitch) : 0;
+    const int xi = in_range ? (int)(cell % a.pitch) : 0;
+    const bool colvalid = in_range && xi < a.nax;
+    const int kx = colvalid ? a.act_x[xi] : 0;
+    const int in = kx + N * ky;
+    double gP = 0.0, gD = 0.0, gM = 0.0;
+    if (colvalid) {
+        for (int s = 0; s < a.nsub; ++s) {
+            gP += a.Gp[((size_t)0 * a.nsub + s) * img + cell];
+            gD += a.Gp[((size_t)1 * a.nsub + s) * img + cell];
+            if (a.kinds & 4u) gM += a.Gp[((size_t)2 * a.nsub + s) * img + cell];
+        }
+    }
+    const bool m = colvalid && a.mask[in];
+    // defocus weights: idef = 1/psi on maskPupil (WFM:1251); rx, ry of the prologue WFM:1040-1061
+    double wD = 0.0, rx = 0.0, ry = 0.0;
+    if (m && (a.kinds & 1u)) {
+        const double scale = 1.0 / ((double)N * a.dxy);
+        wD = gD * (1.0 / a.psi[in]);
+        rx = (double)kappa_dev(kx, N) * scale - a.deltaX;
+        ry = (double)kappa_dev(ky, N) * scale - a.deltaY;
+    }
+    const int npix = N * N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j0 = 0; j0 < a.glen; j0 += WFM_RED_CHUNK) {
+        double acc[WFM_RED_CHUNK];
+#pragma unroll
+        for (int jj = 0; jj < WFM_RED_CHUNK; ++jj) {
+            const int j = j0 + jj;
+            double val = 0.0;
+            if (j < a.glen && colvalid) {
+                if (j < 3) {
+                    if (a.kinds & 1u) val = (j == 0) ? wD * a.lambda_ni : (j == 1 ? wD * rx : wD * ry);
+                } else if (j < 3 + a.nphase) {
+                    if ((a.kinds & 2u) && m) val = gP * a.Z[(size_t)(j - 3 + a.phase_off) * npix + in];
+                } else {
+                    if (a.kinds & 4u) val = gM * a.Z[(size_t)(j - 3 - a.nphase) * npix + in];
+                }
+            }
+            acc[jj] = val;
+        }
+#pragma unroll
+        for (int jj = 0; jj < WFM_RED_CHUNK; ++jj) {
+            double x = acc[jj];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            acc[jj] = x;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int jj = 0; jj < WFM_RED_CHUNK; ++jj) red[warp][jj] = acc[jj];
+        }
+        __syncthreads();
+        if (threadIdx.x < WFM_RED_CHUNK && j0 + (int)threadIdx.x < a.glen) {
+            double x = 0.0;
+#pragma unroll
+            for (int w = 0; w < WFM_RED_THREADS / 32; ++w) x += red[w][threadIdx.x];
+            a.block_part[(size_t)blockIdx.x * a.glen + j0 + threadIdx.x] = x;
+        }
+        __syncthreads();
+    }
+}
+
+// Final fixed-order sum over blocks and the scale factors of each Jacobian:
+//   defocus: t = -2pi*PSFnorm*jin (WFM:1253), d = sum t*{lambda_ni, rx, ry}*defoc/psi (1258-1260,1278-1280)
+//   phase  : g[k] = -2*PSFnorm*sum jin*Z (WFM:937)
+//   modulus: 2*PSFnorm*sum J*Z_k * (1-(beta_k*NBeta)^2)*NBeta (WFM:674)
+__global__ void k_jac_final(const double* __restrict__ block_part, int nblocks, int glen, int nphase,
+                            double psf_norm, Coefs beta, double nbeta, unsigned kinds,
+                            double* __restrict__ grad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= glen) return;
+    double x = 0.0;
+    for (int b = 0; b < nblocks; ++b) x += block_part[(size_t)b * glen + j];
+    double out = 0.0;
+    if (j < 3) {
+        if (kinds & 1u) out = -6.283185307179586 * psf_norm * x;
+    } else if (j < 3 + nphase) {
+        if (kinds & 2u) out = -2.0 * psf_norm * x;
+    } else {
+        if (kinds & 4u) {
+            const double bk = beta.v[j - 3 - nphase] * nbeta;
+            out = 2.0 * psf_norm * x * (1.0 - bk * bk) * nbeta;
+        }
+    }
+    grad[j] = out;
+}
+
+}  // namespace wfm
