@@ -189,6 +189,18 @@ WFM_API int wfm_get_info(const wfm_model* h, int* nx, int* ny, int* nz_global, i
                          int* precision, int* nzern, int* nphase, int* nmodulus);
 /* Number of active pupil rows / columns the pruned FFT passes visit. */
 WFM_API int wfm_active_extent(const wfm_model* h, int* n_active_x, int* n_active_y);
+/* Per-kernel device timing with CUDA events on the handle's stream (off by default).  While on,
+ * every launch group below is bracketed by two events; wfm_get_kernel_times synchronises and
+ * returns the accumulated milliseconds and launch-group counts since profiling was switched on. */
+#define WFM_K_PSF_ROWS 0   /* pupil synthesis + row FFT of computePsf            */
+#define WFM_K_PSF_COLS 1   /* column FFT + conj(a), |a|^2 store of computePsf    */
+#define WFM_K_JAC_ROWS 2   /* conj(a)*q load + row FFT of apply_J_*              */
+#define WFM_K_JAC_COLS 3   /* column FFT + masked trig products of apply_J_*     */
+#define WFM_K_JAC_REDUCE 4 /* Zernike / defocus contractions (two small kernels) */
+#define WFM_K_SETTERS 5    /* setPhase                                           */
+#define WFM_KERNEL_IDS 6
+WFM_API int wfm_set_profiling(wfm_model* h, int on);
+WFM_API int wfm_get_kernel_times(wfm_model* h, double* ms_out, uint64_t* counts_out, int n);
 /* Total kernel launches issued by this library since load (all handles). */
 WFM_API uint64_t wfm_launch_count(void);
 WFM_API const char* wfm_version(void);

@@ -23,6 +23,7 @@ WFM_F64, WFM_F32 = 0, 1
 WFM_DEFOCUS, WFM_PHASE, WFM_MODULUS = 0, 1, 2
 WFM_J_DEFOCUS, WFM_J_PHASE, WFM_J_MODULUS = 1, 2, 4
 WFM_MODULUS_INTENDED, WFM_MODULUS_REFERENCE_LAST_PLANE = 0, 1
+KERNEL_NAMES = ["psf_rows", "psf_cols", "jac_rows", "jac_cols", "jac_reduce", "setters"]
 
 _vp = C.c_void_p
 _dp = C.POINTER(C.c_double)
@@ -68,6 +69,8 @@ SIGNATURES = {
     "wfm_host_free": (C.c_int, [_vp]),
     "wfm_get_info": (C.c_int, [_vp, _ip, _ip, _ip, _ip, _ip, _ip, _ip, _ip, _ip]),
     "wfm_active_extent": (C.c_int, [_vp, _ip, _ip]),
+    "wfm_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "wfm_get_kernel_times": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "wfm_launch_count": (C.c_uint64, []),
     "wfm_version": (C.c_char_p, []),
 }
@@ -95,7 +98,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         raise RuntimeError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  microtipi_b200 has no CPU fallback.")
-    lib = bind(C.CDLL(p, mode=C.RTLD_GLOBAL))
+    lib = bind(C.CDLL(p))
     if path is None:
         _LIB = lib
     return lib

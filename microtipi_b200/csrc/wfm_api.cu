@@ -68,6 +68,13 @@ struct wfm_model {
     DevBuf scratch, Gp, block_part, grad, qdev;
     int modulus_mode = WFM_MODULUS_INTENDED;
     std::string err;
+    // optional per-kernel CUDA-event timing (wfm_set_profiling)
+    bool profiling = false;
+    struct Span { int kid; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> free_events;
+    double k_ms[WFM_KERNEL_IDS] = {0};
+    uint64_t k_count[WFM_KERNEL_IDS] = {0};
 
     int npix() const { return N * N; }
     size_t esz() const { return precision == WFM_F64 ? 8 : 4; }
@@ -96,6 +103,32 @@ struct wfm_model {
     } while (0)
 
 namespace {
+
+cudaEvent_t take_event(wfm_model* h) {
+    if (!h->free_events.empty()) { cudaEvent_t e = h->free_events.back(); h->free_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+// Brackets the launches issued in its scope with two events on the handle's stream.
+struct KernelSpan {
+    wfm_model* h; int kid; cudaEvent_t a = nullptr;
+    KernelSpan(wfm_model* h_, int kid_) : h(h_), kid(kid_) {
+        if (h->profiling) { a = take_event(h); cudaEventRecord(a, h->stream); }
+    }
+    ~KernelSpan() {
+        if (a) { cudaEvent_t b = take_event(h); cudaEventRecord(b, h->stream); h->spans.push_back({kid, a, b}); }
+    }
+};
+void drain_spans(wfm_model* h) {
+    for (auto& sp : h->spans) {
+        float ms = 0.f;
+        cudaEventSynchronize(sp.b);
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { h->k_ms[sp.kid] += ms; h->k_count[sp.kid]++; }
+        h->free_events.push_back(sp.a); h->free_events.push_back(sp.b);
+    }
+    h->spans.clear();
+}
 
 bool supported_n(int n) { return n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048; }
 
@@ -191,6 +224,7 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
     a.T1 = (cx<T>*)h->scratch.p; a.cpx = (cx<T>*)h->cpx.p; a.psf = (T*)h->psf.p;
     a.plane0 = 0;
     {
+        KernelSpan span(h, WFM_K_PSF_ROWS);
         auto kfn = &k_psf_rows<T, N>;
         const size_t smem = sizeof(cx<T>) * RowLayout<T, N>::LEN * RowCfg<N>::RB;
         int rc = set_smem(h, kfn, smem); if (rc) return rc;
@@ -199,6 +233,7 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
         WFM_CK_LAUNCH(h, "k_psf_rows");
     }
     {
+        KernelSpan span(h, WFM_K_PSF_COLS);
         auto kfn = &k_psf_cols<T, N>;
         const size_t smem = ColCfg<T, N>::SMEM;
         int rc = set_smem(h, kfn, smem); if (rc) return rc;
@@ -226,6 +261,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     WFM_CK(h, h->Gp.ensure(sizeof(double) * 3 * a.nsub * img));
     a.Gp = (double*)h->Gp.p;
     {
+        KernelSpan span(h, WFM_K_JAC_ROWS);
         auto kfn = &k_jac_rows<T, N>;
         const size_t smem = sizeof(cx<T>) * RowLayout<T, N>::LEN * RowCfg<N>::RB;
         int rc = set_smem(h, kfn, smem); if (rc) return rc;
@@ -234,6 +270,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         WFM_CK_LAUNCH(h, "k_jac_rows");
     }
     {
+        KernelSpan span(h, WFM_K_JAC_COLS);
         const size_t smem = ColCfg<T, N>::SMEM;
         dim3 grid(h->pitch / ColCfg<T, N>::C, a.nsub);
         if (kinds & WFM_J_MODULUS) {
@@ -248,6 +285,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         WFM_CK_LAUNCH(h, "k_jac_cols");
     }
     {
+        KernelSpan span(h, WFM_K_JAC_REDUCE);
         ReduceArgs r;
         r.g = a.g; r.Gp = a.Gp; r.nsub = a.nsub; r.pitch = h->pitch; r.nax = h->nax;
         r.act_x = a.act_x; r.Z = (const double*)h->Z.p; r.psi = a.psi; r.mask = a.mask;
@@ -375,6 +413,8 @@ int wfm_destroy(wfm_model* h) {
                       &h->act_y, &h->inv_y, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gp, &h->block_part,
                       &h->grad, &h->qdev})
         b->release();
+    drain_spans(h);
+    for (cudaEvent_t e : h->free_events) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return WFM_OK;
@@ -533,6 +573,7 @@ int wfm_set_phase(wfm_model* h, const double* alpha, int n) {
     WFM_CK(h, cudaSetDevice(h->device));
     for (int k = 0; k < n; ++k) h->alpha.v[k] = alpha[k];
     h->nphase = n;
+    KernelSpan span(h, WFM_K_SETTERS);
     auto kfn = &k_set_phase;
     WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix())), dim3(256), 0, h->stream, (double*)h->phi.p,
                (const double*)h->Z.p, (const uint8_t*)h->mask.p, h->alpha, n, off, h->npix());
@@ -765,6 +806,23 @@ int wfm_active_extent(const wfm_model* h, int* nax, int* nay) {
     int rc = rebuild_activity(const_cast<wfm_model*>(h)); if (rc) return rc;
     if (nax) *nax = h->nax;
     if (nay) *nay = h->nay;
+    return WFM_OK;
+}
+
+int wfm_set_profiling(wfm_model* h, int on) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    drain_spans(h);
+    h->profiling = on != 0;
+    for (int i = 0; i < WFM_KERNEL_IDS; ++i) { h->k_ms[i] = 0.0; h->k_count[i] = 0; }
+    return WFM_OK;
+}
+
+int wfm_get_kernel_times(wfm_model* h, double* ms, uint64_t* counts, int n) {
+    if (!h || !ms || !counts || n < WFM_KERNEL_IDS) return WFM_ERR_INVALID_ARG;
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    drain_spans(h);
+    for (int i = 0; i < WFM_KERNEL_IDS; ++i) { ms[i] = h->k_ms[i]; counts[i] = h->k_count[i]; }
     return WFM_OK;
 }
 

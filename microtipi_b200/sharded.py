@@ -1,0 +1,87 @@
+"""z-slab sharding of the widefield PSF path across the GPUs of one box.
+
+One process per GPU.  Planes are independent given (rho, phi, psi, Z) (WFM:291-333, 888-945), so
+each rank owns the contiguous slab ``[z0, z0+nz_local)`` of the global stack and no data-path
+collective is needed for the PSF.  The only exchange is one sum-allreduce of the
+``3 + nPhase + nModulus`` gradient doubles per Jacobian evaluation (all three vectors ride one
+message); the PSF all-gather is optional and off the hot path.  ``torch.distributed`` is plumbing:
+NCCL over NVLink on the GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi as capi
+from .wide_field_model import WideFieldModel
+
+
+def slab_bounds(nz: int, world: int, rank: int):
+    """Contiguous z-slab of ``rank``: the first ``nz % world`` ranks hold one extra plane."""
+    base, rem = divmod(nz, world)
+    z0 = rank * base + min(rank, rem)
+    return z0, base + (1 if rank < rem else 0)
+
+
+class ShardedWideFieldModel:
+    """Same call surface as WideFieldModel for the hot path; every rank passes its own slab of q."""
+
+    def __init__(self, psfShape, nPhase, nModulus, NA, lambda_, ni, dxy, dz, radial=False, single=False, *,
+                 group=None, device=0, lib=None, basis=None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        nz = psfShape[2] if not hasattr(psfShape, "dimension") else psfShape.dimension(2)
+        self.z0, self.nz_local = slab_bounds(nz, self.world, self.rank)
+        if self.nz_local <= 0:
+            raise ValueError("more ranks than z-planes")
+        self.model = WideFieldModel(psfShape, nPhase, nModulus, NA, lambda_, ni, dxy, dz, radial, single,
+                                    device=device, z0=self.z0, nz_local=self.nz_local, lib=lib, basis=basis)
+
+    def __getattr__(self, name):           # setters / getters are slab-local and identical on every rank
+        return getattr(self.model, name)
+
+    # ---- gradient allreduce -----------------------------------------------------------------------
+    def _allreduce_host(self, vec: np.ndarray) -> np.ndarray:
+        if self.world == 1:
+            return vec
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64).copy())
+        backend = self._dist.get_backend(self.group)
+        if backend == "nccl":
+            t = t.cuda()
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def apply_J_phase(self, q_local):
+        return self._allreduce_host(self.model.apply_J_phase(q_local).data)
+
+    def apply_J_defocus(self, q_local):
+        return self._allreduce_host(self.model.apply_J_defocus(q_local).data)
+
+    def apply_J_modulus(self, q_local):
+        return self._allreduce_host(self.model.apply_J_modulus(q_local).data)
+
+    def apply_J_all(self, q_local):
+        d, p, m = self.model.apply_J_all(q_local)
+        full = self._allreduce_host(np.concatenate([d, p, m]))      # one message for all three
+        return full[:3], full[3:3 + p.size], full[3 + p.size:]
+
+    def applyJacobianDeviceAllReduce(self, kinds, q_tensor, grad_tensor):
+        """Device-resident path: q / grad are torch CUDA tensors; NCCL allreduce of the K-vector on
+        the current torch stream (the handle must run on that stream, see WideFieldModel.setStream)."""
+        self.model.applyJacobianDevice(kinds, q_tensor.data_ptr(), grad_tensor.data_ptr())
+        if self.world > 1:
+            self._dist.all_reduce(grad_tensor, op=self._dist.ReduceOp.SUM, group=self.group)
+        return grad_tensor
+
+    # ---- optional PSF gather ------------------------------------------------------------------------
+    def getPsf(self, gather=False):
+        local = self.model.getPsf()
+        if not gather or self.world == 1:
+            return local
+        import torch
+        parts = [None] * self.world
+        self._dist.all_gather_object(parts, local, group=self.group)
+        return np.concatenate(parts, axis=0)

@@ -294,6 +294,48 @@ class WideFieldModel(MicroscopeModel):
         self.PState = self._lib.wfm_psf_state(self._h)
         return d, p[:self.getNPhase()], m
 
+    # -- device-resident entry points (benchmark / multi-GPU plumbing) ---------------------------------
+    def gradLength(self):
+        return int(self._lib.wfm_grad_length(self._h))
+
+    def applyJacobianDevice(self, kinds, q_dev_ptr, grad_dev_ptr):
+        """wfm_apply_jacobian_dev: q and grad are raw device pointers; asynchronous on the stream.
+        grad layout: [defocus(3) | phase(nPhase) | modulus(nModulus)], this slab's partial sums."""
+        self._call("wfm_apply_jacobian_dev", int(kinds), C.c_void_p(q_dev_ptr), C.c_void_p(grad_dev_ptr))
+        self.PState = self._lib.wfm_psf_state(self._h)
+
+    def devicePsfPointer(self):
+        p = C.c_void_p()
+        self._call("wfm_device_psf", C.byref(p))
+        self.PState = 1
+        return p.value
+
+    def deviceCpxPsfPointer(self):
+        p = C.c_void_p()
+        self._call("wfm_device_cpx_psf", C.byref(p))
+        self.PState = 1
+        return p.value
+
+    def fillUniform(self, dev_ptr, seed, first_index, count, single=None):
+        prec = capi.WFM_F32 if (self.single if single is None else single) else capi.WFM_F64
+        self._call("wfm_fill_uniform", C.c_void_p(dev_ptr), prec, int(seed), int(first_index), int(count))
+
+    def setProfiling(self, on):
+        self._call("wfm_set_profiling", 1 if on else 0)
+
+    def kernelTimes(self):
+        """{kernel group: (total ms, launch groups)} since profiling was switched on."""
+        n = len(capi.KERNEL_NAMES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_uint64 * n)()
+        self._call("wfm_get_kernel_times", ms, cnt, n)
+        return {capi.KERNEL_NAMES[i]: (ms[i], int(cnt[i])) for i in range(n)}
+
+    def activeExtent(self):
+        ax, ay = C.c_int(), C.c_int()
+        self._call("wfm_active_extent", C.byref(ax), C.byref(ay))
+        return ax.value, ay.value
+
     # -- defocus -----------------------------------------------------------------------------------
     def computeDefocus(self):                                              # WFM:1452-1499
         self._call("wfm_set_defocus", (C.c_double * 3)(self.lambda_ni, self.deltaX, self.deltaY), 3)

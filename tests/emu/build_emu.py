@@ -20,7 +20,7 @@ def build(force=False, sanitize=False):
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
         return out
-    cmd = ["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing",
+    cmd = ["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-fvisibility=hidden", "-Wl,-Bsymbolic",
            "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable",
            "-DWFM_EMU", "-include", os.path.join(HERE, "cuda_emu.h"), "-x", "c++"] + SRCS + \
           ["-o", out, "-lpthread"]

@@ -80,6 +80,11 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (void*)0x2; return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 
 // ---- device intrinsics ---------------------------------------------------------------------
@@ -248,11 +253,6 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
     std::vector<std::thread> pool;
     for (int i = 0; i < nw; ++i) pool.emplace_back(worker);
     for (auto& t : pool) t.join();
-}
-
-template <class T> inline T atomic_add(T* addr, T v) {
-    T old = __atomic_load_n((volatile T*)addr, __ATOMIC_RELAXED) , nv;
-    (void)nv; return old;
 }
 
 }  // namespace emu

@@ -1,0 +1,136 @@
+"""CPU-side checks of the kernel sources and of the C-ABI host logic.
+
+The SAME .cu/.cuh files nvcc builds for sm_100a are compiled with g++ against the test-only
+emulator tests/emu/cuda_emu.h (one fiber per CUDA thread) and compared with the oracle.  This
+validates index math, shared-memory exchanges, barriers and the PState state machine in a
+container without a GPU; the parity tests proper are tests/test_gpu_parity.py (-m gpu)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import wfm_oracle as o
+from microtipi_b200 import _capi as capi, WideFieldModel
+from tests.util import P, emu_lib, make_pair, tol
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emu_lib()
+
+
+@pytest.mark.parametrize("N,Nz,single", [(32, 6, False), (64, 4, False), (128, 3, False), (64, 4, True)])
+def test_psf_and_jacobians_match_oracle(lib, N, Nz, single):
+    ref, m = make_pair(N, Nz, lib, single=single)
+    t = tol(single)
+    np.testing.assert_array_equal(m.getRho(), ref.rho.ravel())       # elementwise setters are bit exact
+    np.testing.assert_array_equal(m.getPhi(), ref.phi.ravel())
+    np.testing.assert_array_equal(m.getPsi(), ref.psi.ravel())
+    np.testing.assert_array_equal(m.getMaskPupil(), ref.maskPupil.ravel())
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= t
+    assert o.rel_l2(m.get_cpxPsf(), ref.get_cpxPsf()) <= t
+    q = o.synthetic_q(N, N, Nz, single=single)
+    tj = 20 * t if single else t
+    assert o.rel_l2(m.apply_J_phase(q).data, ref.apply_J_phase(q)) <= tj
+    assert o.rel_l2(m.apply_J_defocus(q).data, ref.apply_J_defocus(q)) <= tj
+    assert o.rel_l2(m.apply_J_modulus(q).data, ref.apply_J_modulus(q)) <= tj
+    d, p, mo = m.apply_J_all(q)
+    assert o.rel_l2(np.concatenate([d, p, mo]),
+                    np.concatenate([ref.apply_J_defocus(q), ref.apply_J_phase(q), ref.apply_J_modulus(q)])) <= tj
+    m.setModulusMode(True)                                           # quirk Q1 compat mode
+    ref.modulus_mode = o.MODULUS_REFERENCE_LAST_PLANE
+    assert o.rel_l2(m.apply_J_modulus(q).data, ref.apply_J_modulus(q)) <= tj
+    m.close()
+
+
+def test_device_side_basis_matches_oracle(lib):
+    ref, m = make_pair(32, 2, lib, device_basis=True)
+    assert o.rel_l2(m.getZernike(), ref.Z) <= 1e-12
+    G = m.getZernike() @ m.getZernike().T
+    assert np.abs(G - np.eye(len(G))).max() < 1e-12
+    m.close()
+
+
+def test_off_axis_defocus_and_dirty_state_protocol(lib):
+    ref, m = make_pair(32, 5, lib, delta=(2e4, -2e4))
+    assert m.PState == 0
+    m.computePsf()
+    assert m.PState == 1 and lib.wfm_psf_state(m.handle) == 1
+    n0 = lib.wfm_launch_count()
+    m.computePsf()                                                   # valid -> no work (WFM:207)
+    assert lib.wfm_launch_count() == n0
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+    m.setPhase(np.zeros(10))                                         # every setter ends in freeMem()
+    assert m.PState == 0 and lib.wfm_psf_state(m.handle) == 0
+    ref.setPhase(np.zeros(10))
+    q = o.synthetic_q(32, 32, 5)
+    g = m.apply_J_defocus(q).data                                    # quirk Q5: dirty -> recompute first
+    assert m.PState == 1
+    assert o.rel_l2(g, ref.apply_J_defocus(q)) <= 1e-12
+    m.close()
+
+
+def test_z_slabs_sum_to_full_gradient(lib):
+    N, Nz = 32, 7
+    ref, full = make_pair(N, Nz, lib)
+    q = o.synthetic_q(N, N, Nz)
+    want = full.apply_J_all(q)
+    acc = [np.zeros_like(w) for w in want]
+    psf = []
+    for z0, nzl in ((0, 3), (3, 4)):
+        _, part = make_pair(N, Nz, lib, z0=z0, nz_local=nzl)
+        psf.append(part.getPsf())
+        for a, g in zip(acc, part.apply_J_all(q[z0:z0 + nzl])):
+            a += g
+        part.close()
+    np.testing.assert_array_equal(np.concatenate(psf), full.getPsf())
+    for a, w in zip(acc, want):
+        assert o.rel_l2(a, w) <= 1e-12
+    full.close()
+
+
+def test_escape_hatch_identical_pupils(lib):
+    N, Nz = 32, 4
+    ref, _m = make_pair(N, Nz, lib)
+    _m.close()
+    m = WideFieldModel((N, N, Nz), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, False, lib=lib,
+                       basis=lambda nz: ref.Z[:nz])
+    m.setPupilArrays(ref.rho, ref.phi, ref.psi, ref.maskPupil)
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+    q = o.synthetic_q(N, N, Nz)
+    assert o.rel_l2(m.apply_J_phase(q).data, ref.apply_J_phase(q)) <= 1e-12
+    m.close()
+
+
+def test_error_behaviour_mirrors_reference(lib):
+    with pytest.raises(ValueError, match="Nx should equal Ny"):       # WFM:158
+        WideFieldModel((32, 64, 4), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib)
+    with pytest.raises(ValueError):                                   # not a supported power of two
+        WideFieldModel((48, 48, 4), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib)
+    ref, m = make_pair(32, 2, lib)
+    with pytest.raises(ValueError):                                   # quirk Q4: length-2 defocus
+        m.setDefocus([1.0, 2.0])
+    two = (C.c_double * 2)(1.0, 2.0)
+    assert lib.wfm_set_defocus(m.handle, two, 2) == capi.WFM_ERR_INVALID_ARG
+    assert b"bad defocus" in lib.wfm_last_error(m.handle)             # WFM:1530
+    with pytest.raises(ValueError):                                   # WFM:1629
+        m.setPhase(m.parameterSpace[m.MODULUS].create(0.0))
+    with pytest.raises(ValueError, match="does not belong to any space"):   # WFM:407
+        m.apply_Jacobian(np.zeros((2, 32, 32)), object())
+    g = m.apply_Jacobian(o.synthetic_q(32, 32, 2), m.parameterSpace[m.PHASE])
+    assert g.getNumber() == 10 and g.belongsTo(m.parameterSpace[m.PHASE])
+    h = m.handle
+    out = (C.c_double * 10)()
+    assert lib.wfm_apply_j_phase(h, None, out, 10) == capi.WFM_ERR_INVALID_ARG
+    assert lib.wfm_apply_j_phase(h, out, out, 9) == capi.WFM_ERR_INVALID_ARG
+    assert b"nPhase" in lib.wfm_last_error(h)
+    m.close()
+
+
+def test_fill_uniform_matches_oracle_generator(lib):
+    ref, m = make_pair(32, 2, lib)
+    n = 1000
+    buf = np.zeros(n)
+    m.fillUniform(buf.ctypes.data, seed=42, first_index=12345, count=n)   # emulated "device" memory is host memory
+    np.testing.assert_array_equal(buf, o.splitmix64_uniform(42, 12345, n))
+    m.close()

@@ -1,0 +1,217 @@
+"""Parity tests proper: the sm_100a library, called through the C ABI, against the oracle, the
+committed golden vectors, and size-independent properties at BASELINE's full sizes.
+Tolerances are north_star's: rel-L2 <= 1e-12 (fp64), <= 1e-5 (fp32)."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import wfm_oracle as o
+from microtipi_b200 import _capi as capi, WideFieldModel
+from tests.util import BETA4, P, gpu_lib, make_pair, oracle_basis, tol
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    import __graft_entry__ as g
+    g.build_library()
+    return gpu_lib()
+
+
+def _check_all(ref, m, N, Nz, single):
+    t = tol(single)
+    np.testing.assert_array_equal(m.getRho(), ref.rho.ravel())
+    np.testing.assert_array_equal(m.getPhi(), ref.phi.ravel())
+    np.testing.assert_array_equal(m.getPsi(), ref.psi.ravel())
+    np.testing.assert_array_equal(m.getMaskPupil(), ref.maskPupil.ravel())
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= t
+    assert o.rel_l2(m.get_cpxPsf(), ref.get_cpxPsf()) <= t
+    q = o.synthetic_q(N, N, Nz, single=single)
+    tj = 20 * t if single else t
+    gp, gd, gm = ref.apply_J_phase(q), ref.apply_J_defocus(q), ref.apply_J_modulus(q)
+    assert o.rel_l2(m.apply_J_phase(q).data, gp) <= tj
+    assert o.rel_l2(m.apply_J_defocus(q).data, gd) <= tj
+    assert o.rel_l2(m.apply_J_modulus(q).data, gm) <= tj
+    d, p, mo = m.apply_J_all(q)
+    assert o.rel_l2(np.concatenate([d, p, mo]), np.concatenate([gd, gp, gm])) <= tj
+    m.setModulusMode(True)
+    ref.modulus_mode = o.MODULUS_REFERENCE_LAST_PLANE
+    assert o.rel_l2(m.apply_J_modulus(q).data, ref.apply_J_modulus(q)) <= tj
+
+
+@pytest.mark.parametrize("N,Nz,single", [
+    (32, 8, False), (64, 32, False),            # BASELINE config 1: 64x64x32 fp64
+    (128, 9, False), (256, 16, False), (512, 6, False), (1024, 3, False), (2048, 1, False),
+    (32, 8, True), (64, 32, True), (256, 16, True), (512, 6, True), (1024, 3, True),
+])
+def test_psf_and_jacobians_match_oracle(lib, N, Nz, single):
+    ref, m = make_pair(N, Nz, lib, single=single)
+    _check_all(ref, m, N, Nz, single)
+    m.close()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*.npz"))))
+def test_against_committed_golden_vectors(lib, path):
+    g = np.load(path)
+    N, Nz, single = int(g["N"]), int(g["Nz"]), bool(g["single"])
+    m = WideFieldModel((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, single, lib=lib,
+                       basis=oracle_basis(N))
+    m.setPhase(g["alpha"])
+    m.setModulus(g["beta"])
+    if np.any(g["delta"]):
+        m.setDefocus([P["ni"] / P["lam"], g["delta"][0], g["delta"][1]])
+    t = tol(single)
+    assert o.rel_l2(m.getPsf(), g["psf"]) <= t
+    cpx = m.get_cpxPsf()
+    if "cpx_planes" in g:
+        cpx = cpx[g["cpx_planes"]]
+    assert o.rel_l2(cpx, g["cpx"]) <= t
+    q = o.synthetic_q(N, N, Nz, single=single)
+    tj = 20 * t if single else t
+    assert o.rel_l2(m.apply_J_phase(q).data, g["j_phase"]) <= tj
+    assert o.rel_l2(m.apply_J_defocus(q).data, g["j_defocus"]) <= tj
+    assert o.rel_l2(m.apply_J_modulus(q).data, g["j_modulus"]) <= tj
+    m.setModulusMode(True)
+    assert o.rel_l2(m.apply_J_modulus(q).data, g["j_modulus_last_plane"]) <= tj
+    m.close()
+
+
+def test_device_side_basis(lib):
+    for N in (64, 256):
+        ref, m = make_pair(N, 2, lib, device_basis=True)
+        Z = m.getZernike()
+        assert o.rel_l2(Z, ref.Z) <= 1e-12
+        assert np.abs(Z @ Z.T - np.eye(len(Z))).max() < 1e-12
+        assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12      # whole constructor path on the device
+        m.close()
+
+
+def test_off_axis_and_state_protocol(lib):
+    ref, m = make_pair(128, 5, lib, delta=(2e4, -2e4))
+    assert m.PState == 0
+    m.computePsf()
+    n0 = lib.wfm_launch_count()
+    m.computePsf()                                               # WFM:207: valid -> no kernels
+    assert lib.wfm_launch_count() == n0
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+    m.setDefocus([P["ni"] / P["lam"] * 1.01, 1e4, 3e4])
+    ref.setDefocus([P["ni"] / P["lam"] * 1.01, 1e4, 3e4])
+    assert m.PState == 0
+    q = o.synthetic_q(128, 128, 5)
+    assert o.rel_l2(m.apply_J_defocus(q).data, ref.apply_J_defocus(q)) <= 1e-12   # Q5: recompute
+    np.testing.assert_array_equal(m.getPsi(), ref.psi.ravel())
+    np.testing.assert_array_equal(m.getMaskPupil(), ref.maskPupil.ravel())
+    m.close()
+
+
+def test_edge_cases(lib):
+    # single plane; odd slab at the wrap point (Nz/2 is positive, Nz/2+1 negative); zero gradient
+    ref, m = make_pair(64, 1, lib)
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+    m.close()
+    N, Nz = 64, 9
+    ref, full = make_pair(N, Nz, lib)
+    q = o.synthetic_q(N, N, Nz)
+    want = full.apply_J_all(q)
+    acc = [np.zeros_like(w) for w in want]
+    psf = []
+    for z0, nzl in ((0, 4), (4, 1), (5, 4)):
+        _, part = make_pair(N, Nz, lib, z0=z0, nz_local=nzl)
+        psf.append(part.getPsf())
+        for a, g in zip(acc, part.apply_J_all(q[z0:z0 + nzl])):
+            a += g
+        part.close()
+    np.testing.assert_array_equal(np.concatenate(psf), full.getPsf())   # shard invariance (KAT 8)
+    for a, w in zip(acc, want):
+        assert o.rel_l2(a, w) <= 1e-12
+    z = full.apply_J_all(np.zeros_like(q))
+    assert all(not np.any(v) for v in z)
+    # no phase coefficients (nPhase = 0): PSF symmetric in z and in (x, y)  (KAT 3)
+    ref0, m0 = make_pair(64, 8, lib, nPhase=0, nModulus=1)
+    psf0 = m0.getPsf()
+    for iz in range(1, 4):
+        np.testing.assert_allclose(psf0[iz], psf0[8 - iz], rtol=0, atol=1e-18)
+    with pytest.raises(ValueError):
+        m0.apply_J_phase(q)
+    m0.close()
+    full.close()
+
+
+def test_errors(lib):
+    with pytest.raises(ValueError, match="Nx should equal Ny"):
+        WideFieldModel((64, 32, 4), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib)
+    with pytest.raises(ValueError):
+        WideFieldModel((100, 100, 4), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib)
+    ref, m = make_pair(32, 2, lib)
+    with pytest.raises(ValueError):
+        m.setDefocus([1.0, 2.0])
+    with pytest.raises(ValueError, match="does not belong to any space"):
+        m.apply_Jacobian(np.zeros((2, 32, 32)), object())
+    m.close()
+
+
+def test_full_size_properties_512x512x256(lib):
+    """BASELINE's headline shape: size-independent properties instead of a full oracle run."""
+    import torch
+    N, Nz = 512, 256
+    m = WideFieldModel((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, False, lib=lib)
+    alpha = o.synthetic_alpha(10)
+    m.setPhase(alpha)
+    m.setModulus(BETA4)
+    rho, phi, psi = m.getRho(), m.getPhi(), m.getPsi()
+    psf = m.getPsf()
+    # KAT 1: per plane sum psf = sum rho^2 / Nz (Parseval with PSFnorm)
+    e = float(np.sum(rho * rho))
+    assert abs(e - 1.0) < 1e-12
+    np.testing.assert_allclose(psf.sum(axis=(1, 2), dtype=np.float64), e / Nz, rtol=1e-12)
+    # planes against the oracle on identical pupils (focal plane, wrap planes, last)
+    for iz in (0, 1, 128, 129, 255):
+        c, p = o.compute_psf(rho.reshape(N, N), phi.reshape(N, N), psi.reshape(N, N), Nz, P["dz"], z0=iz, nz_local=1)
+        assert o.rel_l2(psf[iz], p[0]) <= 1e-12
+    # device-resident Jacobian: linearity in q and agreement of a q supported on 2 planes with the oracle
+    dev = torch.device("cuda:0")
+    vox = N * N * Nz
+    q1 = torch.empty(vox, dtype=torch.float64, device=dev)
+    q2 = torch.empty(vox, dtype=torch.float64, device=dev)
+    m.fillUniform(q1.data_ptr(), 42, 0, vox)
+    m.fillUniform(q2.data_ptr(), 43, 0, vox)
+    m.synchronize()
+    np.testing.assert_array_equal(q1[:1000].cpu().numpy(), o.splitmix64_uniform(42, 0, 1000))
+    L = m.gradLength()
+    g = torch.zeros((3, L), dtype=torch.float64, device=dev)
+    comb = 2.0 * q1 - 3.0 * q2
+    for i, qq in enumerate((q1, q2, comb)):
+        m.applyJacobianDevice(7, qq.data_ptr(), g[i].data_ptr())
+    m.synchronize()
+    gh = g.cpu().numpy()
+    assert o.rel_l2(gh[2], 2.0 * gh[0] - 3.0 * gh[1]) <= 1e-11
+    qs = torch.zeros(vox, dtype=torch.float64, device=dev)
+    sel = (3, 200)
+    for iz in sel:
+        qs[iz * N * N:(iz + 1) * N * N] = q1[iz * N * N:(iz + 1) * N * N]
+    m.applyJacobianDevice(7, qs.data_ptr(), g[0].data_ptr())
+    m.synchronize()
+    got = g[0].cpu().numpy()
+    Z = m.getZernike()
+    mask = m.getMaskPupil().reshape(N, N)
+    want_p = np.zeros(10)
+    want_d = np.zeros(3)
+    want_m = np.zeros(4)
+    for iz in sel:
+        qpl = q1[iz * N * N:(iz + 1) * N * N].cpu().numpy().reshape(1, N, N)
+        c, _ = o.compute_psf(rho.reshape(N, N), phi.reshape(N, N), psi.reshape(N, N), Nz, P["dz"], z0=iz, nz_local=1)
+        args = (qpl, c, rho.reshape(N, N), phi.reshape(N, N), psi.reshape(N, N), mask)
+        want_p += o.apply_J_phase(*args, Z, 10, Nz, P["dz"], z0=iz)
+        want_d += o.apply_J_defocus(*args, Nz, P["dz"], P["dxy"], P["ni"] / P["lam"], 0.0, 0.0, z0=iz)
+        want_m += o.apply_J_modulus(*args, Z, BETA4, Nz, P["dz"], z0=iz)
+    assert o.rel_l2(got[:3], want_d) <= 1e-12
+    assert o.rel_l2(got[3:13], want_p) <= 1e-12
+    assert o.rel_l2(got[13:], want_m) <= 1e-12
+    m.close()
