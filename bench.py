@@ -218,9 +218,11 @@ def run_b200(args):
     grad = torch.zeros(L, dtype=torch.float64, device=dev)
     kinds = args.kinds
 
+    x = m.parameterCoefs[m.PHASE]                                  # PSF_Estimation.java:117
+
     def step(i):
-        a = alpha + 1e-3 * (i % 7)                                 # a new parameter vector every evaluation
-        m.setPhase(a)                                              # -> freeMem(): PSF dirty
+        x.data[:] = alpha + 1e-3 * (i % 7)                         # a new parameter vector every evaluation
+        m.setParam(x)                                              # PSF_Estimation.java:202 -> setPhase -> freeMem()
         m.computePsf()
         m.applyJacobianDevice(kinds, q.data_ptr(), grad.data_ptr())
         if world > 1:

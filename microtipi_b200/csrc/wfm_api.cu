@@ -305,7 +305,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
             nbeta = 1.0 / std::sqrt(s);                                        // WFM:435
         }
         auto kfin = &k_jac_final;
-        WFM_LAUNCH(kfin, dim3((r.glen + 127) / 128), dim3(128), 0, h->stream, (const double*)r.block_part, nblocks,
+        WFM_LAUNCH(kfin, dim3(r.glen), dim3(WFM_FINAL_THREADS), 0, h->stream, (const double*)r.block_part, nblocks,
                    r.glen, h->nphase, a.g.psf_norm, h->beta, nbeta, kinds, grad_dev);
         WFM_CK_LAUNCH(h, "k_jac_final");
     }

@@ -555,13 +555,23 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
 //   defocus: t = -2pi*PSFnorm*jin (WFM:1253), d = sum t*{lambda_ni, rx, ry}*defoc/psi (1258-1260,1278-1280)
 //   phase  : g[k] = -2*PSFnorm*sum jin*Z (WFM:937)
 //   modulus: 2*PSFnorm*sum J*Z_k * (1-(beta_k*NBeta)^2)*NBeta (WFM:674)
-__global__ void k_jac_final(const double* __restrict__ block_part, int nblocks, int glen, int nphase,
-                            double psf_norm, Coefs beta, double nbeta, unsigned kinds,
-                            double* __restrict__ grad) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= glen) return;
+#define WFM_FINAL_THREADS 128
+// One CTA per gradient component: strided partial sums, warp shuffle, then across warps.
+__global__ void __launch_bounds__(WFM_FINAL_THREADS) k_jac_final(const double* __restrict__ block_part, int nblocks,
+                                                                int glen, int nphase, double psf_norm, Coefs beta,
+                                                                double nbeta, unsigned kinds,
+                                                                double* __restrict__ grad) {
+    __shared__ double red[WFM_FINAL_THREADS / 32];
+    const int j = blockIdx.x;
     double x = 0.0;
-    for (int b = 0; b < nblocks; ++b) x += block_part[(size_t)b * glen + j];
+    for (int b = threadIdx.x; b < nblocks; b += WFM_FINAL_THREADS) x += block_part[(size_t)b * glen + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    x = 0.0;
+    for (int w = 0; w < WFM_FINAL_THREADS / 32; ++w) x += red[w];
     double out = 0.0;
     if (j < 3) {
         if (kinds & 1u) out = -6.283185307179586 * psf_norm * x;
