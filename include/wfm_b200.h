@@ -192,13 +192,11 @@ WFM_API int wfm_active_extent(const wfm_model* h, int* n_active_x, int* n_active
 /* Per-kernel device timing with CUDA events on the handle's stream (off by default).  While on,
  * every launch group below is bracketed by two events; wfm_get_kernel_times synchronises and
  * returns the accumulated milliseconds and launch-group counts since profiling was switched on. */
-#define WFM_K_PSF_ROWS 0   /* pupil synthesis + row FFT of computePsf            */
-#define WFM_K_PSF_COLS 1   /* column FFT + conj(a), |a|^2 store of computePsf    */
-#define WFM_K_JAC_ROWS 2   /* conj(a)*q load + row FFT of apply_J_*              */
-#define WFM_K_JAC_COLS 3   /* column FFT + masked trig products of apply_J_*     */
-#define WFM_K_JAC_REDUCE 4 /* Zernike / defocus contractions (two small kernels) */
-#define WFM_K_SETTERS 5    /* setPhase                                           */
-#define WFM_KERNEL_IDS 6
+#define WFM_K_PSF 0        /* k_psf_pipeline: pupil synthesis, row FFT, column FFT, conj(a) + |a|^2 store */
+#define WFM_K_JAC 1        /* k_jac_pipeline: conj(a)*q load, row FFT, column FFT, masked trig products   */
+#define WFM_K_JAC_REDUCE 2 /* k_jac_reduce + k_jac_final: sum over z, Zernike / defocus contractions     */
+#define WFM_K_SETTERS 3    /* k_set_phase                                                                  */
+#define WFM_KERNEL_IDS 4
 WFM_API int wfm_set_profiling(wfm_model* h, int on);
 WFM_API int wfm_get_kernel_times(wfm_model* h, double* ms_out, uint64_t* counts_out, int n);
 /* Total kernel launches issued by this library since load (all handles). */

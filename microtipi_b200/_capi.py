@@ -23,7 +23,7 @@ WFM_F64, WFM_F32 = 0, 1
 WFM_DEFOCUS, WFM_PHASE, WFM_MODULUS = 0, 1, 2
 WFM_J_DEFOCUS, WFM_J_PHASE, WFM_J_MODULUS = 1, 2, 4
 WFM_MODULUS_INTENDED, WFM_MODULUS_REFERENCE_LAST_PLANE = 0, 1
-KERNEL_NAMES = ["psf_rows", "psf_cols", "jac_rows", "jac_cols", "jac_reduce", "setters"]
+KERNEL_NAMES = ["psf_pipeline", "jac_pipeline", "jac_reduce", "setters"]
 
 _vp = C.c_void_p
 _dp = C.POINTER(C.c_double)

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -65,7 +66,9 @@ struct wfm_model {
     DevBuf cpx, psf;
     int pstate = 0;
     // scratch
-    DevBuf scratch, Gp, block_part, grad, qdev;
+    DevBuf scratch, Gj, Gm, ctl, block_part, grad, qdev;
+    int num_sms = 148;
+    unsigned long pipe_checks = 0;
     int modulus_mode = WFM_MODULUS_INTENDED;
     std::string err;
     // optional per-kernel CUDA-event timing (wfm_set_profiling)
@@ -214,38 +217,81 @@ template <class K> int set_smem(wfm_model* h, K kfn, size_t bytes) {
     return WFM_OK;
 }
 
+// ---- pipeline control ---------------------------------------------------------------------------------
+// Ring / lag sizing: LAG ~ 1.5x the planes whose A-items are in flight at once, RING = 2*LAG + 2, with the
+// ring kept within ~48 MB so that it stays L2-resident (126 MB L2 shared with the streaming traffic).
+struct PipePlan { int ring, lag, nA, nB, grid; };
+
+PipePlan plan_pipeline(const wfm_model* h, int nA, int nB, size_t plane_bytes, int ctas_per_sm) {
+    PipePlan p;
+    p.nA = nA; p.nB = nB;
+    const int nctas = h->num_sms * ctas_per_sm;
+    int lag = (3 * nctas + 2 * nA - 1) / (2 * nA);
+    if (lag < 2) lag = 2;
+    const size_t budget = 48u << 20;
+    while (lag > 2 && (size_t)(2 * lag + 2) * plane_bytes > budget) --lag;
+    int ring = 2 * lag + 2;
+    if (ring > h->nzl) ring = h->nzl;
+    if (lag >= ring) lag = ring > 1 ? ring - 1 : 1;
+    if (const char* e = getenv("WFM_PIPE_LAG")) { int v = atoi(e); if (v >= 1 && v < ring) lag = v; }
+    p.ring = ring; p.lag = lag;
+    const long items = (long)h->nzl * (nA + nB);
+    p.grid = (int)(items < nctas ? items : nctas);
+    return p;
+}
+
+int prepare_ctl(wfm_model* h, const PipePlan& pp, PipeCtl& ctl, int roles) {
+    const size_t words = 2 + 2 * (size_t)h->nzl;
+    WFM_CK(h, h->ctl.ensure(sizeof(unsigned) * words));
+    WFM_CK(h, cudaMemsetAsync(h->ctl.p, 0, sizeof(unsigned) * words, h->stream));
+    unsigned* base = (unsigned*)h->ctl.p;
+    ctl.queue = base; ctl.err = base + 1; ctl.cntA = base + 2; ctl.cntB = base + 2 + h->nzl;
+    ctl.ring = pp.ring; ctl.lag = pp.lag; ctl.nA = pp.nA; ctl.nB = pp.nB; ctl.roles = roles;
+    return WFM_OK;
+}
+
+int pipe_roles() {
+    const char* e = getenv("WFM_PIPE_ROLES");      // debugging / profiling aid: 1 = A only, 2 = B only
+    int r = e ? atoi(e) : 3;
+    return (r >= 1 && r <= 3) ? r : 3;
+}
+
 // ---- computePsf ---------------------------------------------------------------------------------
 template <typename T, int N> int launch_psf(wfm_model* h) {
+    using Cfg = PipeCfg<T, N>;
+    auto kfn = &k_psf_pipeline<T, N>;
+    int rc = set_smem(h, kfn, Cfg::SMEM); if (rc) return rc;
+    const int nA = (h->nay + Cfg::C - 1) / Cfg::C, nB = N / Cfg::C;
+    const size_t plane_bytes = sizeof(cx<T>) * (size_t)h->nay * N;
+    const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, Cfg::MINB);
+    WFM_CK(h, h->scratch.ensure(plane_bytes * pp.ring));
     PsfArgs<T> a;
     a.g = geom_of(h);
     a.rho = (const double*)h->rho.p; a.phi = (const double*)h->phi.p; a.psi = (const double*)h->psi.p;
     a.act_y = (const int*)h->act_y.p; a.inv_y = (const int*)h->inv_y.p; a.nay = h->nay;
     a.tw = (const cx<T>*)h->tw.p;
     a.T1 = (cx<T>*)h->scratch.p; a.cpx = (cx<T>*)h->cpx.p; a.psf = (T*)h->psf.p;
-    a.plane0 = 0;
-    {
-        KernelSpan span(h, WFM_K_PSF_ROWS);
-        auto kfn = &k_psf_rows<T, N>;
-        const size_t smem = sizeof(cx<T>) * RowLayout<T, N>::LEN * RowCfg<N>::RB;
-        int rc = set_smem(h, kfn, smem); if (rc) return rc;
-        dim3 grid((h->nay + RowCfg<N>::RB - 1) / RowCfg<N>::RB, h->nzl);
-        WFM_LAUNCH(kfn, grid, dim3(RowCfg<N>::THREADS), smem, h->stream, a);
-        WFM_CK_LAUNCH(h, "k_psf_rows");
-    }
-    {
-        KernelSpan span(h, WFM_K_PSF_COLS);
-        auto kfn = &k_psf_cols<T, N>;
-        const size_t smem = ColCfg<T, N>::SMEM;
-        int rc = set_smem(h, kfn, smem); if (rc) return rc;
-        dim3 grid(N / ColCfg<T, N>::C, h->nzl);
-        WFM_LAUNCH(kfn, grid, dim3(ColCfg<T, N>::THREADS), smem, h->stream, a);
-        WFM_CK_LAUNCH(h, "k_psf_cols");
-    }
+    PipeCtl ctl;
+    rc = prepare_ctl(h, pp, ctl, pipe_roles()); if (rc) return rc;
+    KernelSpan span(h, WFM_K_PSF);
+    WFM_LAUNCH(kfn, dim3(pp.grid), dim3(Cfg::THREADS), Cfg::SMEM, h->stream, a, ctl);
+    WFM_CK_LAUNCH(h, "k_psf_pipeline");
+    h->pipe_checks++;
     return WFM_OK;
 }
 
 // ---- apply_J_* ------------------------------------------------------------------------------------
 template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev) {
+    using Cfg = PipeCfg<T, N>;
+    auto kfn = &k_jac_pipeline<T, N>;
+    int rc = set_smem(h, kfn, Cfg::SMEM); if (rc) return rc;
+    const int nA = N / Cfg::C, nB = h->pitch / Cfg::C;
+    const size_t plane_bytes = sizeof(cx<T>) * (size_t)N * h->pitch;
+    const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, Cfg::MINB);
+    WFM_CK(h, h->scratch.ensure(plane_bytes * pp.ring));
+    const size_t img = (size_t)N * h->pitch;
+    WFM_CK(h, h->Gj.ensure(sizeof(double) * img * h->nzl));
+    if (kinds & WFM_J_MODULUS) WFM_CK(h, h->Gm.ensure(sizeof(double) * img * h->nzl));
     JacArgs<T> a;
     a.g = geom_of(h);
     a.cpx = (const cx<T>*)h->cpx.p; a.q = (const T*)q_dev;
@@ -254,49 +300,32 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     a.act_x = (const int*)h->act_x.p; a.inv_x = (const int*)h->inv_x.p; a.nax = h->nax; a.pitch = h->pitch;
     a.tw = (const cx<T>*)h->tw.p;
     a.T2 = (cx<T>*)h->scratch.p;
-    a.nsub = (h->nzl + WFM_JAC_BS - 1) / WFM_JAC_BS;
+    a.Gj = (double*)h->Gj.p;
+    a.Gm = (kinds & WFM_J_MODULUS) ? (double*)h->Gm.p : nullptr;
     a.last_plane_only = (h->modulus_mode == WFM_MODULUS_REFERENCE_LAST_PLANE) ? 1 : 0;
-    a.plane0 = 0;
-    const size_t img = (size_t)N * h->pitch;
-    WFM_CK(h, h->Gp.ensure(sizeof(double) * 3 * a.nsub * img));
-    a.Gp = (double*)h->Gp.p;
     {
-        KernelSpan span(h, WFM_K_JAC_ROWS);
-        auto kfn = &k_jac_rows<T, N>;
-        const size_t smem = sizeof(cx<T>) * RowLayout<T, N>::LEN * RowCfg<N>::RB;
-        int rc = set_smem(h, kfn, smem); if (rc) return rc;
-        dim3 grid((N + RowCfg<N>::RB - 1) / RowCfg<N>::RB, h->nzl);
-        WFM_LAUNCH(kfn, grid, dim3(RowCfg<N>::THREADS), smem, h->stream, a);
-        WFM_CK_LAUNCH(h, "k_jac_rows");
-    }
-    {
-        KernelSpan span(h, WFM_K_JAC_COLS);
-        const size_t smem = ColCfg<T, N>::SMEM;
-        dim3 grid(h->pitch / ColCfg<T, N>::C, a.nsub);
-        if (kinds & WFM_J_MODULUS) {
-            auto kfn = &k_jac_cols<T, N, true>;
-            int rc = set_smem(h, kfn, smem); if (rc) return rc;
-            WFM_LAUNCH(kfn, grid, dim3(ColCfg<T, N>::THREADS), smem, h->stream, a);
-        } else {
-            auto kfn = &k_jac_cols<T, N, false>;
-            int rc = set_smem(h, kfn, smem); if (rc) return rc;
-            WFM_LAUNCH(kfn, grid, dim3(ColCfg<T, N>::THREADS), smem, h->stream, a);
-        }
-        WFM_CK_LAUNCH(h, "k_jac_cols");
+        PipeCtl ctl;
+        rc = prepare_ctl(h, pp, ctl, pipe_roles()); if (rc) return rc;
+        KernelSpan span(h, WFM_K_JAC);
+        WFM_LAUNCH(kfn, dim3(pp.grid), dim3(Cfg::THREADS), Cfg::SMEM, h->stream, a, ctl);
+        WFM_CK_LAUNCH(h, "k_jac_pipeline");
+        h->pipe_checks++;
     }
     {
         KernelSpan span(h, WFM_K_JAC_REDUCE);
         ReduceArgs r;
-        r.g = a.g; r.Gp = a.Gp; r.nsub = a.nsub; r.pitch = h->pitch; r.nax = h->nax;
-        r.act_x = a.act_x; r.Z = (const double*)h->Z.p; r.psi = a.psi; r.mask = a.mask;
+        r.g = a.g; r.Gj = a.Gj; r.Gm = a.Gm; r.pitch = h->pitch; r.nax = h->nax;
+        r.act_x = a.act_x; r.Z = (const double*)h->Z.p; r.psi = a.psi; r.mask = a.mask; r.support = a.support;
         r.nphase = h->nphase; r.nmod = h->nmod; r.phase_off = h->radial ? 1 : 3;
-        r.kinds = kinds; r.dxy = h->dxy; r.lambda_ni = h->lambda_ni; r.deltaX = h->deltaX; r.deltaY = h->deltaY;
+        r.kinds = kinds; r.last_plane_only = a.last_plane_only;
+        r.dxy = h->dxy; r.lambda_ni = h->lambda_ni; r.deltaX = h->deltaX; r.deltaY = h->deltaY;
         r.glen = h->glen();
         const int nblocks = (int)((img + WFM_RED_THREADS - 1) / WFM_RED_THREADS);
-        WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * r.glen));
+        const int nchunks = (h->nzl + WFM_RED_PLANES - 1) / WFM_RED_PLANES;
+        WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * nchunks * r.glen));
         r.block_part = (double*)h->block_part.p;
-        auto kfn = &k_jac_reduce;
-        WFM_LAUNCH(kfn, dim3(nblocks), dim3(WFM_RED_THREADS), 0, h->stream, r);
+        auto kred = &k_jac_reduce;
+        WFM_LAUNCH(kred, dim3(nblocks, nchunks), dim3(WFM_RED_THREADS), 0, h->stream, r);
         WFM_CK_LAUNCH(h, "k_jac_reduce");
         double nbeta = 0.0;
         if (h->nmod > 0) {
@@ -305,8 +334,8 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
             nbeta = 1.0 / std::sqrt(s);                                        // WFM:435
         }
         auto kfin = &k_jac_final;
-        WFM_LAUNCH(kfin, dim3(r.glen), dim3(WFM_FINAL_THREADS), 0, h->stream, (const double*)r.block_part, nblocks,
-                   r.glen, h->nphase, a.g.psf_norm, h->beta, nbeta, kinds, grad_dev);
+        WFM_LAUNCH(kfin, dim3(r.glen), dim3(WFM_FINAL_THREADS), 0, h->stream, (const double*)r.block_part,
+                   nblocks * nchunks, r.glen, h->nphase, a.g.psf_norm, h->beta, nbeta, kinds, grad_dev);
         WFM_CK_LAUNCH(h, "k_jac_final");
     }
     return WFM_OK;
@@ -329,20 +358,11 @@ template <typename T> int dispatch_jac(wfm_model* h, unsigned kinds, const void*
     WFM_DISPATCH_N(launch_jac, h, kinds, q, g)
 }
 
-int ensure_scratch(wfm_model* h) {
-    const size_t c = 2 * h->esz();
-    const size_t t1 = (size_t)h->nzl * h->nay * h->N * c;
-    const size_t t2 = (size_t)h->nzl * h->N * h->pitch * c;
-    WFM_CK(h, h->scratch.ensure(t1 > t2 ? t1 : t2));
-    return WFM_OK;
-}
-
 int compute_psf_impl(wfm_model* h) {
     if (h->pstate > 0) return WFM_OK;                                          // WFM:207
     if (!h->have_rho) return h->fail(WFM_ERR_STATE, "pupil modulus not set: call wfm_set_modulus or wfm_set_pupil_arrays first");
     WFM_CK(h, cudaSetDevice(h->device));
     int rc = rebuild_activity(h); if (rc) return rc;
-    rc = ensure_scratch(h); if (rc) return rc;
     const size_t vox = (size_t)h->npix() * h->nzl;
     WFM_CK(h, h->cpx.ensure(vox * 2 * h->esz()));
     WFM_CK(h, h->psf.ensure(vox * h->esz()));
@@ -352,7 +372,18 @@ int compute_psf_impl(wfm_model* h) {
     return WFM_OK;
 }
 
-int invalidate(wfm_model* h) { h->pstate = 0; return WFM_OK; }                 // WFM:1970-1974
+int invalidate(wfm_model* h) { h->pstate = 0; return WFM_OK; }
+
+// After a synchronisation point: did a pipeline dependency wait time out?  (It cannot by
+// construction; the flag turns a would-be hang into an error code.)
+int check_pipeline(wfm_model* h) {
+    if (!h->pipe_checks || !h->ctl.p) return WFM_OK;
+    h->pipe_checks = 0;
+    unsigned flag = 0;
+    WFM_CK(h, cudaMemcpy(&flag, (unsigned*)h->ctl.p + 1, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (flag) return h->fail(WFM_ERR_INTERNAL, "pipeline dependency wait timed out");
+    return WFM_OK;
+}                 // WFM:1970-1974
 
 int elementwise_grid(int n) { return (n + 255) / 256; }
 
@@ -389,6 +420,11 @@ int wfm_create_slab(wfm_model** out, int nx, int ny, int nz_global, int z0, int 
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(WFM_ERR_CUDA, "cudaStreamCreate failed");
     h->stream = h->own_stream;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)
+            h->num_sms = prop.multiProcessorCount;
+    }
     const size_t npix = (size_t)nx * nx;
     // this.phi = new double[Ny*Nx]; this.psi = new double[Ny*Nx]  (WFM:167-168); rho starts empty
     if (h->rho.ensure(8 * npix) || h->phi.ensure(8 * npix) || h->psi.ensure(8 * npix) || h->mask.ensure(npix) ||
@@ -410,7 +446,7 @@ int wfm_destroy(wfm_model* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->Z, &h->rho, &h->phi, &h->psi, &h->mask, &h->map, &h->support, &h->act_x, &h->inv_x,
-                      &h->act_y, &h->inv_y, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gp, &h->block_part,
+                      &h->act_y, &h->inv_y, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gj, &h->Gm, &h->ctl, &h->block_part,
                       &h->grad, &h->qdev})
         b->release();
     drain_spans(h);
@@ -432,7 +468,7 @@ int wfm_set_stream(wfm_model* h, void* s) {
 int wfm_synchronize(wfm_model* h) {
     if (!h) return WFM_ERR_INVALID_ARG;
     WFM_CK(h, cudaStreamSynchronize(h->stream));
-    return WFM_OK;
+    return check_pipeline(h);
 }
 
 int wfm_set_optics(wfm_model* h, double NA, double lambda, double ni) {
@@ -651,7 +687,7 @@ static int copy_out(wfm_model* h, void* out, const void* dev, size_t bytes) {
     WFM_CK(h, cudaSetDevice(h->device));
     WFM_CK(h, cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
     WFM_CK(h, cudaStreamSynchronize(h->stream));
-    return WFM_OK;
+    return check_pipeline(h);
 }
 
 int wfm_get_rho(wfm_model* h, double* out) { return h ? copy_out(h, out, h->rho.p, 8 * (size_t)h->npix()) : WFM_ERR_INVALID_ARG; }
@@ -710,7 +746,7 @@ static int apply_host(wfm_model* h, unsigned kinds, const void* q_host, std::vec
     g.resize(h->glen());
     WFM_CK(h, cudaMemcpyAsync(g.data(), h->grad.p, 8 * g.size(), cudaMemcpyDeviceToHost, h->stream));
     WFM_CK(h, cudaStreamSynchronize(h->stream));
-    return WFM_OK;
+    return check_pipeline(h);
 }
 
 int wfm_apply_j_phase(wfm_model* h, const void* q, double* out, int n) {

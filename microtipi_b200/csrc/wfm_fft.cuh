@@ -144,11 +144,14 @@ template <int C> struct ColLayout {
 // v   : E register values of this thread (slot convention above)
 // sm  : base of this transform's shared cells (RowLayout: private row; ColLayout: smem + column)
 // t   : thread index inside the transform, [0, T)
-// tw  : W_N table in global memory, tw[m] = exp(-2 pi i m / N), m in [0, N)
+// tw  : W_N table in SHARED memory, tw[m] = exp(-2 pi i m / N), m in [0, N).  Only the base twiddle
+//       of each butterfly is read (one LDS per butterfly); its powers w^2..w^(R-1) are formed by
+//       complex multiplication in registers.  (ncu on the first revision showed the LSU data pipe
+//       95 % busy with 2/3 of its wavefronts spent on per-leg twiddle loads; profiles/r01a_*.)
 // All threads of the CTA must call this together (it contains CTA-wide barriers).  The caller
 // must place a barrier between the end of one call and the start of the next one that reuses sm.
 template <typename T, class P, class L>
-WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* __restrict__ tw) {
+WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* tw) {
     constexpr int E = P::E, R1 = P::R1, R2 = P::R2, R3 = P::R3, TT = P::T, S1 = P::S1;
     // stage 1: radix R1 over legs of stride S1, twiddle W_N^(b*k1), scatter to cell k1*S1 + b
 #pragma unroll
@@ -159,8 +162,13 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
         Dft<T, R1>::run(a);
         const int b = t + TT * u;
         sm[L::at(b)] = a[0];
+        const cx<T> w = tw[b];
+        cx<T> wk = w;
 #pragma unroll
-        for (int k = 1; k < R1; ++k) sm[L::at(k * S1 + b)] = cmul(a[k], __ldg(&tw[b * k]));
+        for (int k = 1; k < R1; ++k) {
+            sm[L::at(k * S1 + b)] = cmul(a[k], wk);
+            if (k + 1 < R1) wk = cmul(wk, w);
+        }
     }
     __syncthreads();
     if constexpr (P::THREE) {
@@ -175,8 +183,13 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
             for (int r = 0; r < R2; ++r) a[r] = sm[L::at(base + r * R3)];
             Dft<T, R2>::run(a);
             sm[L::at(base)] = a[0];
+            const cx<T> w = tw[R1 * d3];
+            cx<T> wk = w;
 #pragma unroll
-            for (int k = 1; k < R2; ++k) sm[L::at(base + k * R3)] = cmul(a[k], __ldg(&tw[R1 * d3 * k]));
+            for (int k = 1; k < R2; ++k) {
+                sm[L::at(base + k * R3)] = cmul(a[k], wk);
+                if (k + 1 < R2) wk = cmul(wk, w);
+            }
         }
         __syncthreads();
         // stage 3: radix R3 over adjacent cells; butterfly b = k1 + R1*k2 -> X[b + (N/R3)*r]

@@ -8,9 +8,9 @@
 //   Z             : double[nzern][Npix]     orthonormal Zernike basis
 //   cpx           : cx<T>[nzl][Npix]        conj(FFT2(A_z))            (WFM:325-326)
 //   psf           : T[nzl][Npix]            |a|^2 * PSFnorm           (WFM:327)
-//   T1            : cx<T>[nzl][nay][N]      row-pass output of the PSF transform (active rows only)
-//   T2            : cx<T>[nzl][N][pitch]    row-pass output of the adjoint transform (active kx only)
-//   Gp            : double[3][nsub][N][pitch]  per-plane-group partial images of the Jacobians
+//   T1 ring       : cx<T>[ring][nay][N]     row-pass output of the PSF transform (active rows only)
+//   T2 ring       : cx<T>[ring][N][pitch]   row-pass output of the adjoint transform (active kx only)
+//   Gj, Gm        : double[nzl][N][pitch]   per-plane Jacobian integrands on the compact pupil strip
 //
 // Pruning (quirk Q6): the pupil is zero outside `support`, so the forward transform only
 // row-transforms the `nay` rows that intersect it, and the adjoint transform only keeps /
@@ -68,8 +68,6 @@ template <typename T, int N> struct ColCfg {
     static constexpr int THREADS = C * TT;
     static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)N * C;
 };
-// planes accumulated in registers by one column CTA of the adjoint pass
-#define WFM_JAC_BS 4
 
 // ================================================================================================
 // pupil construction (elementwise; arithmetic mirrors the JVM: no FMA contraction)
@@ -222,6 +220,94 @@ __global__ void k_fill_uniform(T* __restrict__ out, uint64_t seed, uint64_t firs
 }
 
 // ================================================================================================
+// Persistent two-stage pipelines.
+//
+// Both directions of the path are "row transform -> pruned intermediate -> column transform":
+//   computePsf (WFM:280-350):   A: pupil synthesis + FFT_x of the active rows  -> T ring
+//                               B: FFT_y of every column + conj(a), |a|^2 store (HBM stream out)
+//   apply_J_*  (WFM:883-965..): A: conj(a)*q load (HBM stream in) + FFT_x, keep active kx -> T ring
+//                               B: FFT_y of the active columns + masked trig products -> integrands
+// One persistent kernel per direction: CTAs pull work items from a global queue whose order
+// interleaves A-items of plane p with B-items of plane p-LAG; B(p) waits on a per-plane counter
+// until all A(p) items are published, A(p) waits until the ring slot's previous tenant B(p-RING)
+// is finished.  An item only ever waits for items that were dequeued before it, by CTAs that are
+// therefore running: no deadlock, no co-residency requirement.  The intermediate lives in a small
+// ring (RING planes) that stays L2-resident instead of making an HBM round trip.
+// ================================================================================================
+struct PipeCtl {
+    unsigned* queue;   // [1] next item
+    unsigned* err;     // [1] set when a dependency wait times out
+    unsigned* cntA;    // [nzl] published A-items per plane
+    unsigned* cntB;    // [nzl] finished  B-items per plane
+    int ring;          // planes in the intermediate ring
+    int lag;           // B(p - lag) is queued next to A(p)
+    int nA, nB;        // items per plane
+    int roles;         // bit 0: run A items, bit 1: run B items (both set in production)
+};
+
+template <typename T, int N> struct PipeCfg {
+    using P = Plan<N>;
+    static constexpr int C = ColCfg<T, N>::C;           // columns per B-item == rows per A-item
+    static constexpr int TT = P::T;
+    static constexpr int THREADS = C * TT;
+    static constexpr int ROWLEN = RowLayout<T, N>::LEN;
+    static constexpr int CELLS = C * ROWLEN;            // >= C * N
+    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N) + sizeof(int) * (size_t)N;
+    // two CTAs per SM when registers (<= 64/thread at 512 threads) and shared memory allow it
+    static constexpr int MINB = (THREADS <= 512 && SMEM <= 110 * 1024) ? 2 : 1;
+};
+
+struct PipeItem { int type; int plane; int sub; };   // type 0 = A, 1 = B, -1 = done
+
+WFM_DEVI PipeItem pipe_decode(unsigned idx, int P, const PipeCtl& c) {
+    PipeItem it;
+    const int lag = c.lag < P ? c.lag : P;
+    const unsigned headA = (unsigned)lag * c.nA;
+    const unsigned per = (unsigned)(c.nA + c.nB);
+    const unsigned mid = (unsigned)(P - lag) * per;
+    if (idx < headA) { it.type = 0; it.plane = (int)(idx / c.nA); it.sub = (int)(idx % c.nA); return it; }
+    unsigned r = idx - headA;
+    if (r < mid) {
+        const int ph = (int)(r / per);
+        const int w = (int)(r % per);
+        if (w < c.nB) { it.type = 1; it.plane = ph; it.sub = w; }
+        else { it.type = 0; it.plane = lag + ph; it.sub = w - c.nB; }
+        return it;
+    }
+    r -= mid;
+    if (r < (unsigned)lag * c.nB) { it.type = 1; it.plane = (P - lag) + (int)(r / c.nB); it.sub = (int)(r % c.nB); return it; }
+    it.type = -1; it.plane = 0; it.sub = 0;
+    return it;
+}
+
+// thread 0 polls a counter (L2, volatile) until it reaches `target`; everybody then passes a barrier
+WFM_DEVI void pipe_wait(const unsigned* cnt, unsigned target, unsigned* err) {
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while (*(volatile const unsigned*)cnt < target) {
+            if (++spins > (1u << 22)) { *(volatile unsigned*)err = 1u; break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+// all global stores of the item are fenced, then thread 0 publishes
+WFM_DEVI void pipe_signal(unsigned* cnt) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(cnt, 1u);
+}
+
+// Dequeue the next item for the whole CTA (thread 0 claims, shared broadcast).
+WFM_DEVI PipeItem pipe_next(const PipeCtl& c, int P) {
+    __shared__ unsigned s_item;
+    __syncthreads();                       // previous item's readers of s_item and of the data cells are done
+    if (threadIdx.x == 0) s_item = atomicAdd(c.queue, 1u);
+    __syncthreads();
+    return pipe_decode(s_item, P, c);
+}
+
+// ================================================================================================
 // computePsf()  WFM:280-350 (fp32: 209-278)
 // ================================================================================================
 template <typename T> struct PsfArgs {
@@ -230,26 +316,23 @@ template <typename T> struct PsfArgs {
     const int* act_y;   // [nay] active rows
     const int* inv_y;   // [N]   row -> compact index or -1
     int nay;
-    const cx<T>* tw;    // W_N table
-    cx<T>* T1;
+    const cx<T>* tw;    // W_N table (global; copied to shared memory once per CTA)
+    cx<T>* T1;          // ring: [ring][nay][N]
     cx<T>* cpx;
     T* psf;
-    int plane0;         // first local plane of this launch
 };
 
-// Pass 1: A = rho*exp(i(phi + defoc_scale*psi)) synthesised in the load (WFM:311-316), FFT along x
-// for the active rows only.
+// A-item: rows yi0 .. yi0+C-1 of plane pl.  A = rho*exp(i(phi + defoc_scale*psi)) is synthesised in
+// the load (WFM:311-316; sincos only where rho != 0, quirk Q6), then FFT along x.
 template <typename T, int N>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS) k_psf_rows(PsfArgs<T> a) {
+WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
-    constexpr int RB = RowCfg<N>::RB, TT = P::T, E = P::E;
-    WFM_DYN_SMEM(cx<T>, smem);
+    constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
-    const int yi = blockIdx.x * RB + slot;
+    const int yi = sub * C + slot;
     const bool valid = yi < a.nay;
-    const int y = valid ? a.act_y[yi] : 0;
-    const int pl = a.plane0 + blockIdx.y;
+    const int y = valid ? __ldg(&a.act_y[yi]) : 0;
     const double s = defoc_scale_dev(a.g.z0 + pl, a.g.nz_global, a.g.dz);
     cx<T> v[E];
 #pragma unroll
@@ -269,38 +352,36 @@ __global__ void __launch_bounds__(RowCfg<N>::THREADS) k_psf_rows(PsfArgs<T> a) {
             v[u * P::R1 + r] = val;
         }
     }
-    fft_inplace<T, P, L>(v, smem + slot * L::LEN, t, a.tw);
+    fft_inplace<T, P, L>(v, cells + slot * L::LEN, t, tw_s);
     if (valid) {
-        cx<T>* dst = a.T1 + ((size_t)pl * a.nay + yi) * N;
+        cx<T>* dst = a.T1 + ((size_t)(pl % ring) * a.nay + yi) * N;
 #pragma unroll
         for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
-            for (int r = 0; r < P::RL; ++r) dst[(t + TT * u) + P::SL * r] = v[u * P::RL + r];
+            for (int r = 0; r < P::RL; ++r) __stcg(&dst[(t + TT * u) + P::SL * r], v[u * P::RL + r]);
     }
 }
 
-// Pass 2: FFT along y for every column (inactive rows are zero), then the fused store of
-// conj(a) and |a|^2*PSFnorm (WFM:323-328).
+// B-item: columns kx0 .. kx0+C-1 of plane pl: FFT along y (inactive rows are zero), then the fused
+// streaming store of conj(a) and |a|^2*PSFnorm (WFM:323-328).
 template <typename T, int N>
-__global__ void __launch_bounds__(ColCfg<T, N>::THREADS) k_psf_cols(PsfArgs<T> a) {
+WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+                            const int* inv_s) {
     using P = Plan<N>;
-    constexpr int C = ColCfg<T, N>::C, TT = P::T, E = P::E;
+    constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = ColLayout<C>;
-    WFM_DYN_SMEM(cx<T>, smem);
     const int c = threadIdx.x % C, t = threadIdx.x / C;
-    const int kx = blockIdx.x * C + c;
-    const int pl = a.plane0 + blockIdx.y;
-    const cx<T>* src = a.T1 + (size_t)pl * a.nay * N + kx;
+    const int kx = sub * C + c;
+    const cx<T>* src = a.T1 + (size_t)(pl % ring) * a.nay * N + kx;
     cx<T> v[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r) {
-            const int y = (t + TT * u) + P::S1 * r;
-            const int yi = __ldg(&a.inv_y[y]);
+            const int yi = inv_s[(t + TT * u) + P::S1 * r];
             v[u * P::R1 + r] = (yi >= 0) ? __ldcg(&src[(size_t)yi * N]) : mkc<T>((T)0, (T)0);
         }
-    fft_inplace<T, P, L>(v, smem + c, t, a.tw);
+    fft_inplace<T, P, L>(v, cells + c, t, tw_s);
     const T norm = (T)a.g.psf_norm;
     const size_t base = (size_t)pl * N * N + kx;
 #pragma unroll
@@ -310,12 +391,37 @@ __global__ void __launch_bounds__(ColCfg<T, N>::THREADS) k_psf_cols(PsfArgs<T> a
             const int ky = (t + TT * u) + P::SL * r;
             const cx<T> val = v[u * P::RL + r];
             const size_t o = base + (size_t)N * ky;
-            a.cpx[o] = mkc<T>(val.x, -val.y);                     // store conjugate of A (WFM:326)
+            __stcs(&a.cpx[o], mkc<T>(val.x, -val.y));            // store conjugate of A (WFM:326)
             if constexpr (sizeof(T) == 8)
-                a.psf[o] = (T)__dmul_rn(__dadd_rn(__dmul_rn(val.x, val.x), __dmul_rn(val.y, val.y)), norm);
+                __stcs(&a.psf[o], (T)__dmul_rn(__dadd_rn(__dmul_rn(val.x, val.x), __dmul_rn(val.y, val.y)), norm));
             else
-                a.psf[o] = (T)__fmul_rn(__fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y)), norm);
+                __stcs(&a.psf[o], (T)__fmul_rn(__fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y)), norm));
         }
+}
+
+template <typename T, int N>
+__global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k_psf_pipeline(PsfArgs<T> a, PipeCtl ctl) {
+    using Cfg = PipeCfg<T, N>;
+    WFM_DYN_SMEM(cx<T>, cells);
+    cx<T>* tw_s = cells + Cfg::CELLS;
+    int* inv_s = reinterpret_cast<int*>(tw_s + N);
+    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; inv_s[i] = a.inv_y[i]; }
+    const int P = a.g.nzl;
+    for (;;) {
+        const PipeItem it = pipe_next(ctl, P);
+        if (it.type < 0) break;
+        if (it.type == 0) {
+            if (!(ctl.roles & 1)) continue;
+            if ((ctl.roles & 2) && it.plane >= ctl.ring) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
+            psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+            pipe_signal(&ctl.cntA[it.plane]);
+        } else {
+            if (!(ctl.roles & 2)) continue;
+            if (ctl.roles & 1) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
+            psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s);
+            pipe_signal(&ctl.cntB[it.plane]);
+        }
+    }
 }
 
 // ================================================================================================
@@ -332,156 +438,139 @@ template <typename T> struct JacArgs {
     int nax;
     int pitch;         // nax rounded up to a multiple of the column tile
     const cx<T>* tw;
-    cx<T>* T2;
-    double* Gp;        // [3][nsub][N][pitch]
-    int nsub;
+    cx<T>* T2;         // ring: [ring][N][pitch]
+    double* Gj;        // [nzl][N][pitch]  jin  = rho*(B_re sin ph + B_im cos ph)  on maskPupil
+    double* Gm;        // [nzl][N][pitch]  J    = B_re cos ph - B_im sin ph        on the support (or NULL)
     int last_plane_only;  // quirk Q1 compat mode for the modulus Jacobian
-    int plane0;
 };
 
-// Pass 1: Aq = conj(a)*q fused into the load (WFM:907-914), FFT along x, keep active kx only.
+// A-item: rows y0 .. y0+C-1 of plane pl.  Aq = conj(a)*q fused into the streaming load
+// (WFM:907-914), FFT along x, keep the active kx only.
 template <typename T, int N>
-__global__ void __launch_bounds__(RowCfg<N>::THREADS) k_jac_rows(JacArgs<T> a) {
+WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+                            const int* inv_s) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
-    constexpr int RB = RowCfg<N>::RB, TT = P::T, E = P::E;
-    WFM_DYN_SMEM(cx<T>, smem);
+    constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
-    const int y = blockIdx.x * RB + slot;
-    const bool valid = y < N;
-    const int pl = a.plane0 + blockIdx.y;
-    const size_t base = (size_t)pl * N * N + (size_t)N * (valid ? y : 0);
+    const int y = sub * C + slot;                      // N % C == 0: always a valid row
+    const size_t base = (size_t)pl * N * N + (size_t)N * y;
     cx<T> v[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r) {
             const int x = (t + TT * u) + P::S1 * r;
-            const cx<T> av = a.cpx[base + x];
-            const T qv = a.q[base + x];
+            const cx<T> av = __ldcs(&a.cpx[base + x]);
+            const T qv = __ldcs(&a.q[base + x]);
             v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
         }
-    fft_inplace<T, P, L>(v, smem + slot * L::LEN, t, a.tw);
-    if (valid) {
-        cx<T>* dst = a.T2 + ((size_t)pl * N + y) * a.pitch;
-#pragma unroll
-        for (int u = 0; u < E / P::RL; ++u)
-#pragma unroll
-            for (int r = 0; r < P::RL; ++r) {
-                const int k = (t + TT * u) + P::SL * r;
-                const int xi = __ldg(&a.inv_x[k]);
-                if (xi >= 0) dst[xi] = v[u * P::RL + r];
-            }
-    }
-}
-
-// Pass 2: FFT along y for the active columns, then the masked trig products of the three
-// Jacobians, accumulated in registers over WFM_JAC_BS consecutive planes:
-//   jin  = rho*(B_re sin ph + B_im cos ph)      on maskPupil   (WFM:925-928, 1253)
-//   gP  += jin ; gD += defoc*jin                                 (phase / defocus integrands)
-//   gM  += B_re cos ph - B_im sin ph            on the support (WFM:607-611)
-template <typename T, int N, bool MOD>
-__global__ void __launch_bounds__(ColCfg<T, N>::THREADS) k_jac_cols(JacArgs<T> a) {
-    using P = Plan<N>;
-    constexpr int C = ColCfg<T, N>::C, TT = P::T, E = P::E;
-    using L = ColLayout<C>;
-    WFM_DYN_SMEM(cx<T>, smem);
-    const int c = threadIdx.x % C, t = threadIdx.x / C;
-    const int xi = blockIdx.x * C + c;
-    const bool colvalid = xi < a.nax;
-    const int kx = colvalid ? a.act_x[xi] : 0;
-    const int sub = blockIdx.y;
-    const int p0 = a.plane0 + sub * WFM_JAC_BS;
-    const int p1 = (p0 + WFM_JAC_BS < a.g.nzl) ? p0 + WFM_JAC_BS : a.g.nzl;
-
-    double rho_e[E], phi_e[E], psi_e[E], accP[E], accD[E], accM[MOD ? E : 1];
-    unsigned mbits = 0, sbits = 0;
+    fft_inplace<T, P, L>(v, cells + slot * L::LEN, t, tw_s);
+    cx<T>* dst = a.T2 + ((size_t)(pl % ring) * N + y) * a.pitch;
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
         for (int r = 0; r < P::RL; ++r) {
-            const int e = u * P::RL + r;
+            const int xi = inv_s[(t + TT * u) + P::SL * r];
+            if (xi >= 0) __stcg(&dst[xi], v[u * P::RL + r]);
+        }
+}
+
+// B-item: active columns xi0 .. xi0+C-1 of plane pl: FFT along y, then the masked trig products
+// shared by the three Jacobians, written per plane (summed over z by k_jac_reduce in fixed order):
+//   jin = rho*(B_re sin ph + B_im cos ph)   on maskPupil   (WFM:925-928, 1253)
+//   J   = B_re cos ph - B_im sin ph         on the support (WFM:607-611)
+template <typename T, int N>
+WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s) {
+    using P = Plan<N>;
+    constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
+    using L = ColLayout<C>;
+    const int c = threadIdx.x % C, t = threadIdx.x / C;
+    const int xi = sub * C + c;
+    const bool colvalid = xi < a.nax;
+    const int kx = colvalid ? __ldg(&a.act_x[xi]) : 0;
+    const cx<T>* src = a.T2 + (size_t)(pl % ring) * N * a.pitch + xi;
+    cx<T> v[E];
+#pragma unroll
+    for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+        for (int r = 0; r < P::R1; ++r) {
+            const int y = (t + TT * u) + P::S1 * r;
+            v[u * P::R1 + r] = colvalid ? __ldcg(&src[(size_t)y * a.pitch]) : mkc<T>((T)0, (T)0);
+        }
+    fft_inplace<T, P, L>(v, cells + c, t, tw_s);
+    if (!colvalid) return;
+    const int iz = a.g.z0 + pl;
+    const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
+    const bool mod_plane = (a.Gm != nullptr) && (!a.last_plane_only || iz == a.g.nz_global - 1);
+    const size_t obase = (size_t)pl * N * a.pitch + xi;
+#pragma unroll
+    for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+        for (int r = 0; r < P::RL; ++r) {
             const int ky = (t + TT * u) + P::SL * r;
             const int in = kx + N * ky;
-            const bool sup = colvalid && a.support[in];
-            const bool m = sup && a.mask[in];
-            rho_e[e] = sup ? a.rho[in] : 0.0;
-            phi_e[e] = sup ? a.phi[in] : 0.0;
-            psi_e[e] = sup ? a.psi[in] : 0.0;
-            mbits |= (m ? 1u : 0u) << e;
-            sbits |= (sup ? 1u : 0u) << e;
-            accP[e] = 0.0; accD[e] = 0.0;
-            if constexpr (MOD) accM[e] = 0.0;
-        }
-
-    for (int pl = p0; pl < p1; ++pl) {
-        const int iz = a.g.z0 + pl;
-        const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
-        const double dfc = defoc_depth_dev(iz, a.g.nz_global, a.g.dz);
-        const bool mod_plane = MOD && (!a.last_plane_only || iz == a.g.nz_global - 1);
-        const cx<T>* src = a.T2 + (size_t)pl * N * a.pitch + xi;
-        cx<T> v[E];
-#pragma unroll
-        for (int u = 0; u < E / P::R1; ++u)
-#pragma unroll
-            for (int r = 0; r < P::R1; ++r) {
-                const int y = (t + TT * u) + P::S1 * r;
-                v[u * P::R1 + r] = colvalid ? __ldcg(&src[(size_t)y * a.pitch]) : mkc<T>((T)0, (T)0);
-            }
-        fft_inplace<T, P, L>(v, smem + c, t, a.tw);
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const bool m = (mbits >> e) & 1u;
-            const bool sup = (sbits >> e) & 1u;
-            if (m || (mod_plane && sup)) {
-                const double ph = __dadd_rn(phi_e[e], __dmul_rn(s, psi_e[e]));
-                double sn, cs;
-                sincos(ph, &sn, &cs);
-                const double br = (double)v[e].x, bi = (double)v[e].y;
-                if (m) {
-                    const double jin = rho_e[e] * (br * sn + bi * cs);
-                    accP[e] += jin;
-                    accD[e] += dfc * jin;
-                }
-                if constexpr (MOD) { if (mod_plane) accM[e] += br * cs - bi * sn; }
-            }
-        }
-        __syncthreads();  // the next plane's stage-1 stores reuse the shared cells
-    }
-
-    const size_t img = (size_t)N * a.pitch;
-#pragma unroll
-    for (int u = 0; u < E / P::RL; ++u)
-#pragma unroll
-        for (int r = 0; r < P::RL; ++r) {
-            const int e = u * P::RL + r;
-            const int ky = (t + TT * u) + P::SL * r;
-            const size_t o = (size_t)ky * a.pitch + xi;
-            a.Gp[((size_t)0 * a.nsub + sub) * img + o] = accP[e];
-            a.Gp[((size_t)1 * a.nsub + sub) * img + o] = accD[e];
-            if constexpr (MOD) a.Gp[((size_t)2 * a.nsub + sub) * img + o] = accM[e];
+            if (!__ldg(&a.support[in])) continue;
+            const bool m = __ldg(&a.mask[in]) != 0;
+            if (!m && !mod_plane) continue;
+            const double ph = __dadd_rn(__ldg(&a.phi[in]), __dmul_rn(s, __ldg(&a.psi[in])));
+            double sn, cs;
+            sincos(ph, &sn, &cs);
+            const cx<T> b = v[u * P::RL + r];
+            const double br = (double)b.x, bi = (double)b.y;
+            const size_t o = obase + (size_t)ky * a.pitch;
+            if (m) a.Gj[o] = __ldg(&a.rho[in]) * (br * sn + bi * cs);
+            if (mod_plane) a.Gm[o] = br * cs - bi * sn;
         }
 }
 
-// ---- contraction of the partial images with the basis: warp-then-block reductions --------------
+template <typename T, int N>
+__global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k_jac_pipeline(JacArgs<T> a, PipeCtl ctl) {
+    using Cfg = PipeCfg<T, N>;
+    WFM_DYN_SMEM(cx<T>, cells);
+    cx<T>* tw_s = cells + Cfg::CELLS;
+    int* inv_s = reinterpret_cast<int*>(tw_s + N);
+    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; inv_s[i] = a.inv_x[i]; }
+    const int P = a.g.nzl;
+    for (;;) {
+        const PipeItem it = pipe_next(ctl, P);
+        if (it.type < 0) break;
+        if (it.type == 0) {
+            if (!(ctl.roles & 1)) continue;
+            if ((ctl.roles & 2) && it.plane >= ctl.ring) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
+            jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s);
+            pipe_signal(&ctl.cntA[it.plane]);
+        } else {
+            if (!(ctl.roles & 2)) continue;
+            if (ctl.roles & 1) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
+            jac_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+            pipe_signal(&ctl.cntB[it.plane]);
+        }
+    }
+}
+
+// ---- contraction of the per-plane integrands with the basis: warp-then-block reductions --------
 struct ReduceArgs {
     Geom g;
-    const double* Gp; int nsub; int pitch; int nax;
+    const double* Gj; const double* Gm; int pitch; int nax;
     const int* act_x;
-    const double* Z; const double* psi; const uint8_t* mask;
+    const double* Z; const double* psi; const uint8_t* mask; const uint8_t* support;
     int nphase, nmod, phase_off;
     unsigned kinds;
+    int last_plane_only;
     double dxy, lambda_ni, deltaX, deltaY;
-    double* block_part;   // [nblocks][glen]
+    double* block_part;   // [nchunks][nblocks][glen]
     int glen;             // 3 + nphase + nmod
 };
 
 #define WFM_RED_THREADS 256
 #define WFM_RED_CHUNK 8
+#define WFM_RED_PLANES 16   // planes summed by one CTA (grid.y = ceil(nzl / WFM_RED_PLANES))
 
-// One thread per (ky, xi) cell of the compact pupil strip.  Sums the plane-group partials in
-// fixed order, then forms the glen dot products WFM_RED_CHUNK at a time: shuffle-reduce inside
-// each warp, then across the warps of the block through shared memory.
+// One thread per (ky, xi) cell of the compact pupil strip and per chunk of WFM_RED_PLANES planes.
+// Sums the planes of the chunk in fixed order (gP = sum jin, gD = sum defoc*jin, gM = sum J), then
+// forms the glen dot products WFM_RED_CHUNK at a time: shuffle-reduce inside each warp, then across
+// the warps of the block through shared memory.
 __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     __shared__ double red[WFM_RED_THREADS / 32][WFM_RED_CHUNK];
     const int N = a.g.N;
@@ -493,15 +582,23 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     const bool colvalid = in_range && xi < a.nax;
     const int kx = colvalid ? a.act_x[xi] : 0;
     const int in = kx + N * ky;
+    const bool sup = colvalid && a.support[in];
+    const bool m = sup && a.mask[in];
+    const int p0 = blockIdx.y * WFM_RED_PLANES;
+    const int p1 = (p0 + WFM_RED_PLANES < a.g.nzl) ? p0 + WFM_RED_PLANES : a.g.nzl;
     double gP = 0.0, gD = 0.0, gM = 0.0;
-    if (colvalid) {
-        for (int s = 0; s < a.nsub; ++s) {
-            gP += a.Gp[((size_t)0 * a.nsub + s) * img + cell];
-            gD += a.Gp[((size_t)1 * a.nsub + s) * img + cell];
-            if (a.kinds & 4u) gM += a.Gp[((size_t)2 * a.nsub + s) * img + cell];
+    if (m) {
+#pragma unroll 4
+        for (int pl = p0; pl < p1; ++pl) {
+            const double jin = a.Gj[(size_t)pl * img + cell];
+            gP += jin;
+            gD += defoc_depth_dev(a.g.z0 + pl, a.g.nz_global, a.g.dz) * jin;
         }
     }
-    const bool m = colvalid && a.mask[in];
+    if (sup && (a.kinds & 4u)) {
+        for (int pl = p0; pl < p1; ++pl)
+            if (!a.last_plane_only || a.g.z0 + pl == a.g.nz_global - 1) gM += a.Gm[(size_t)pl * img + cell];
+    }
     // defocus weights: idef = 1/psi on maskPupil (WFM:1251); rx, ry of the prologue WFM:1040-1061
     double wD = 0.0, rx = 0.0, ry = 0.0;
     if (m && (a.kinds & 1u)) {
@@ -512,13 +609,14 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     }
     const int npix = N * N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* out = a.block_part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * a.glen;
     for (int j0 = 0; j0 < a.glen; j0 += WFM_RED_CHUNK) {
         double acc[WFM_RED_CHUNK];
 #pragma unroll
         for (int jj = 0; jj < WFM_RED_CHUNK; ++jj) {
             const int j = j0 + jj;
             double val = 0.0;
-            if (j < a.glen && colvalid) {
+            if (j < a.glen && sup) {
                 if (j < 3) {
                     if (a.kinds & 1u) val = (j == 0) ? wD * a.lambda_ni : (j == 1 ? wD * rx : wD * ry);
                 } else if (j < 3 + a.nphase) {
@@ -545,7 +643,7 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
             double x = 0.0;
 #pragma unroll
             for (int w = 0; w < WFM_RED_THREADS / 32; ++w) x += red[w][threadIdx.x];
-            a.block_part[(size_t)blockIdx.x * a.glen + j0 + threadIdx.x] = x;
+            out[j0 + threadIdx.x] = x;
         }
         __syncthreads();
     }
