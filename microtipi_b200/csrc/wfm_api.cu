@@ -341,6 +341,13 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     return WFM_OK;
 }
 
+#ifdef WFM_ONLY_512   /* quick experiment builds: instantiate the headline size only */
+#define WFM_DISPATCH_N(FN, h, ...)                                                     \
+    switch ((h)->N) {                                                                  \
+        case 512: return FN<T, 512>(h, ##__VA_ARGS__);                                 \
+        default: return (h)->fail(WFM_ERR_UNSUPPORTED, "unsupported N=%d", (h)->N);    \
+    }
+#else
 #define WFM_DISPATCH_N(FN, h, ...)                                                     \
     switch ((h)->N) {                                                                  \
         case 32: return FN<T, 32>(h, ##__VA_ARGS__);                                   \
@@ -352,6 +359,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         case 2048: return FN<T, 2048>(h, ##__VA_ARGS__);                               \
         default: return (h)->fail(WFM_ERR_UNSUPPORTED, "unsupported N=%d", (h)->N);    \
     }
+#endif
 
 template <typename T> int dispatch_psf(wfm_model* h) { WFM_DISPATCH_N(launch_psf, h) }
 template <typename T> int dispatch_jac(wfm_model* h, unsigned kinds, const void* q, double* g) {

@@ -136,8 +136,35 @@ template <typename T, int N> struct RowLayout {
     static WFM_DEVI int at(int i) { return pad_c(i); }
 };
 
-template <int C> struct ColLayout {
-    static WFM_DEVI int at(int i) { return i * C; }
+// Column layout: cell = (i + (i >> SH)) * C + column.  With SH = log2(N/R1) the stage-3 reads of a
+// narrow tile (C = 4 fp64 columns, two index values per 128-byte wavefront) are conflict free too
+// (tools/bank_conflicts.py, score_cols).
+template <int C, int SH> struct ColLayout {
+    __host__ __device__ static constexpr int pad_c(int i) { return i + (i >> SH); }
+    static WFM_DEVI int at(int i) { return pad_c(i) * C; }
+};
+__host__ __device__ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
+
+// ---- barrier scopes --------------------------------------------------------------------------
+// A column tile is transposed through shared memory by all warps of the CTA: CTA-wide barrier.
+struct CtaSync {
+    static WFM_DEVI void sync(int) { __syncthreads(); }
+};
+// A row transform is private to its TT threads: a named barrier over those warps when TT >= 64,
+// a warp barrier when the transform fits in one warp.  (ncu on the first pipeline revision:
+// barrier stalls dominated with 16-warp CTA barriers; profiles/r01b_*.)
+template <int TT> struct RowSync {
+    static WFM_DEVI void sync(int slot) {
+        if constexpr (TT >= 64) {
+#ifdef WFM_EMU
+            emu::named_barrier(1 + slot, TT);
+#else
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(TT) : "memory");
+#endif
+        } else {
+            __syncwarp();
+        }
+    }
 };
 
 // ---- the engine ----------------------------------------------------------------------------
@@ -148,10 +175,10 @@ template <int C> struct ColLayout {
 //       of each butterfly is read (one LDS per butterfly); its powers w^2..w^(R-1) are formed by
 //       complex multiplication in registers.  (ncu on the first revision showed the LSU data pipe
 //       95 % busy with 2/3 of its wavefronts spent on per-leg twiddle loads; profiles/r01a_*.)
-// All threads of the CTA must call this together (it contains CTA-wide barriers).  The caller
+// S   : barrier scope (CtaSync / RowSync); every thread inside that scope must call this together.  The caller
 // must place a barrier between the end of one call and the start of the next one that reuses sm.
-template <typename T, class P, class L>
-WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* tw) {
+template <typename T, class P, class L, class S>
+WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* tw, const int sync_id) {
     constexpr int E = P::E, R1 = P::R1, R2 = P::R2, R3 = P::R3, TT = P::T, S1 = P::S1;
     // stage 1: radix R1 over legs of stride S1, twiddle W_N^(b*k1), scatter to cell k1*S1 + b
 #pragma unroll
@@ -170,7 +197,7 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
             if (k + 1 < R1) wk = cmul(wk, w);
         }
     }
-    __syncthreads();
+    S::sync(sync_id);
     if constexpr (P::THREE) {
         // stage 2: inside block k1, radix R2 over legs of stride R3, twiddle W_N^(R1*d3*k2)
 #pragma unroll
@@ -191,7 +218,7 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
                 if (k + 1 < R2) wk = cmul(wk, w);
             }
         }
-        __syncthreads();
+        S::sync(sync_id);
         // stage 3: radix R3 over adjacent cells; butterfly b = k1 + R1*k2 -> X[b + (N/R3)*r]
 #pragma unroll
         for (int u = 0; u < E / R3; ++u) {

@@ -245,16 +245,26 @@ struct PipeCtl {
     int roles;         // bit 0: run A items, bit 1: run B items (both set in production)
 };
 
+// fp64 column tile of the pipelines for N >= 256: 4 columns (64-byte segments of conj(a)) give
+// 256-thread CTAs at N = 512, i.e. four independent barrier domains per SM instead of two.
+#ifndef WFM_PIPE_C64
+#define WFM_PIPE_C64 4
+#endif
 template <typename T, int N> struct PipeCfg {
     using P = Plan<N>;
-    static constexpr int C = ColCfg<T, N>::C;           // columns per B-item == rows per A-item
+    static constexpr int C = (sizeof(T) == 8 && N >= 256) ? WFM_PIPE_C64 : ColCfg<T, N>::C;   // columns per B-item == rows per A-item
     static constexpr int TT = P::T;
     static constexpr int THREADS = C * TT;
+    static constexpr int SH = ilog2_c(P::S1);
+    using ColL = ColLayout<C, SH>;
     static constexpr int ROWLEN = RowLayout<T, N>::LEN;
-    static constexpr int CELLS = C * ROWLEN;            // >= C * N
+    static constexpr int COLLEN = ColL::pad_c(N - 1) + 1;
+    static constexpr int CELLS = C * (ROWLEN > COLLEN ? ROWLEN : COLLEN);
     static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N) + sizeof(int) * (size_t)N;
-    // two CTAs per SM when registers (<= 64/thread at 512 threads) and shared memory allow it
-    static constexpr int MINB = (THREADS <= 512 && SMEM <= 110 * 1024) ? 2 : 1;
+    // resident CTAs per SM the register allocation is tuned for: 1024 threads (64 registers each)
+    static constexpr int BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
+    static constexpr int BY_SMEM = (int)((220 * 1024) / SMEM) < 1 ? 1 : (int)((220 * 1024) / SMEM);
+    static constexpr int MINB = BY_THREADS < BY_SMEM ? BY_THREADS : BY_SMEM;
 };
 
 struct PipeItem { int type; int plane; int sub; };   // type 0 = A, 1 = B, -1 = done
@@ -285,27 +295,39 @@ WFM_DEVI void pipe_wait(const unsigned* cnt, unsigned target, unsigned* err) {
     if (threadIdx.x == 0) {
         unsigned spins = 0;
         while (*(volatile const unsigned*)cnt < target) {
-            if (++spins > (1u << 22)) { *(volatile unsigned*)err = 1u; break; }
+            if (++spins > (1u << 22)) { *(volatile unsigned*)err = 1u; break; }   // ~seconds: never a hang
+            WFM_SPIN_PAUSE();
         }
         __threadfence();
     }
     __syncthreads();
 }
-// all global stores of the item are fenced, then thread 0 publishes
+// CTA barrier (all stores of the item issued), then thread 0 fences at GPU scope and publishes --
+// the arrive half of a cooperative-groups grid barrier.
 WFM_DEVI void pipe_signal(unsigned* cnt) {
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(cnt, 1u);
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(cnt, 1u); }
 }
 
-// Dequeue the next item for the whole CTA (thread 0 claims, shared broadcast).
-WFM_DEVI PipeItem pipe_next(const PipeCtl& c, int P) {
-    __shared__ unsigned s_item;
-    __syncthreads();                       // previous item's readers of s_item and of the data cells are done
-    if (threadIdx.x == 0) s_item = atomicAdd(c.queue, 1u);
-    __syncthreads();
-    return pipe_decode(s_item, P, c);
-}
+// Work-item queue of a persistent CTA.  Thread 0 claims item i+1 while item i is being processed
+// (the atomic's latency is off the critical path); the claim becomes visible to the CTA through the
+// barriers every item executes.
+struct PipeQueue {
+    unsigned* s_item;   // [2] shared
+    int cur;
+    WFM_DEVI void init(unsigned* smem2, const PipeCtl& c) {
+        s_item = smem2; cur = 0;
+        if (threadIdx.x == 0) s_item[0] = atomicAdd(c.queue, 1u);
+        __syncthreads();
+    }
+    WFM_DEVI PipeItem take(const PipeCtl& c, int P) {
+        const unsigned idx = s_item[cur];
+        const PipeItem it = pipe_decode(idx, P, c);
+        if (threadIdx.x == 0 && it.type >= 0) s_item[cur ^ 1] = atomicAdd(c.queue, 1u);
+        cur ^= 1;
+        return it;
+    }
+};
 
 // ================================================================================================
 // computePsf()  WFM:280-350 (fp32: 209-278)
@@ -352,7 +374,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
             v[u * P::R1 + r] = val;
         }
     }
-    fft_inplace<T, P, L>(v, cells + slot * L::LEN, t, tw_s);
+    fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
     if (valid) {
         cx<T>* dst = a.T1 + ((size_t)(pl % ring) * a.nay + yi) * N;
 #pragma unroll
@@ -369,7 +391,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
                             const int* inv_s) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
-    using L = ColLayout<C>;
+    using L = typename PipeCfg<T, N>::ColL;
     const int c = threadIdx.x % C, t = threadIdx.x / C;
     const int kx = sub * C + c;
     const cx<T>* src = a.T1 + (size_t)(pl % ring) * a.nay * N + kx;
@@ -381,7 +403,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
             const int yi = inv_s[(t + TT * u) + P::S1 * r];
             v[u * P::R1 + r] = (yi >= 0) ? __ldcg(&src[(size_t)yi * N]) : mkc<T>((T)0, (T)0);
         }
-    fft_inplace<T, P, L>(v, cells + c, t, tw_s);
+    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, 0);
     const T norm = (T)a.g.psf_norm;
     const size_t base = (size_t)pl * N * N + kx;
 #pragma unroll
@@ -406,19 +428,25 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     cx<T>* tw_s = cells + Cfg::CELLS;
     int* inv_s = reinterpret_cast<int*>(tw_s + N);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; inv_s[i] = a.inv_y[i]; }
+    __shared__ unsigned s_queue[2];
+    PipeQueue qu;
+    qu.init(s_queue, ctl);
     const int P = a.g.nzl;
     for (;;) {
-        const PipeItem it = pipe_next(ctl, P);
+        const PipeItem it = qu.take(ctl, P);
         if (it.type < 0) break;
         if (it.type == 0) {
-            if (!(ctl.roles & 1)) continue;
-            if ((ctl.roles & 2) && it.plane >= ctl.ring) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
-            psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+            if (ctl.roles & 1) {
+                if ((ctl.roles & 2) && it.plane >= ctl.ring) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
+                psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+            }
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
-            if (!(ctl.roles & 2)) continue;
-            if (ctl.roles & 1) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-            psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s);
+            if (ctl.roles & 2) {
+                if (ctl.roles & 1) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
+                else __syncthreads();
+                psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s);
+            }
             pipe_signal(&ctl.cntB[it.plane]);
         }
     }
@@ -465,7 +493,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
             const T qv = __ldcs(&a.q[base + x]);
             v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
         }
-    fft_inplace<T, P, L>(v, cells + slot * L::LEN, t, tw_s);
+    fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
     cx<T>* dst = a.T2 + ((size_t)(pl % ring) * N + y) * a.pitch;
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
@@ -484,7 +512,7 @@ template <typename T, int N>
 WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
-    using L = ColLayout<C>;
+    using L = typename PipeCfg<T, N>::ColL;
     const int c = threadIdx.x % C, t = threadIdx.x / C;
     const int xi = sub * C + c;
     const bool colvalid = xi < a.nax;
@@ -498,7 +526,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
             const int y = (t + TT * u) + P::S1 * r;
             v[u * P::R1 + r] = colvalid ? __ldcg(&src[(size_t)y * a.pitch]) : mkc<T>((T)0, (T)0);
         }
-    fft_inplace<T, P, L>(v, cells + c, t, tw_s);
+    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, 0);
     if (!colvalid) return;
     const int iz = a.g.z0 + pl;
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
@@ -531,19 +559,25 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     cx<T>* tw_s = cells + Cfg::CELLS;
     int* inv_s = reinterpret_cast<int*>(tw_s + N);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; inv_s[i] = a.inv_x[i]; }
+    __shared__ unsigned s_queue[2];
+    PipeQueue qu;
+    qu.init(s_queue, ctl);
     const int P = a.g.nzl;
     for (;;) {
-        const PipeItem it = pipe_next(ctl, P);
+        const PipeItem it = qu.take(ctl, P);
         if (it.type < 0) break;
         if (it.type == 0) {
-            if (!(ctl.roles & 1)) continue;
-            if ((ctl.roles & 2) && it.plane >= ctl.ring) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
-            jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s);
+            if (ctl.roles & 1) {
+                if ((ctl.roles & 2) && it.plane >= ctl.ring) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
+                jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s);
+            }
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
-            if (!(ctl.roles & 2)) continue;
-            if (ctl.roles & 1) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-            jac_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+            if (ctl.roles & 2) {
+                if (ctl.roles & 1) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
+                else __syncthreads();
+                jac_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+            }
             pipe_signal(&ctl.cntB[it.plane]);
         }
     }

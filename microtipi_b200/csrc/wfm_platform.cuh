@@ -20,6 +20,8 @@ inline std::atomic<unsigned long long>& launch_counter() {
     extern __shared__ __align__(16) unsigned char wfm_dyn_smem_raw[];      \
     T* name = reinterpret_cast<T*>(wfm_dyn_smem_raw)
 
+#define WFM_SPIN_PAUSE() __nanosleep(40)
+
 #define WFM_LAUNCH(kfn, grid, block, smem, stream, ...)                    \
     do {                                                                   \
         ::wfm::launch_counter()++;                                         \

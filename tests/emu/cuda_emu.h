@@ -122,6 +122,8 @@ struct Block {
     // per-warp shuffle state
     struct Warp { int count = 0; unsigned gen = 0; uint64_t slot[32]; };
     std::vector<Warp> warps;
+    struct Named { int count = 0; unsigned gen = 0; };
+    Named named[16];
     uint3_emu bid{0, 0, 0};
     dim3 bdim, gdim;
     char* smem = nullptr;
@@ -142,6 +144,15 @@ inline void syncthreads() {
     unsigned g = b->bar_gen;
     if (++b->bar_count == b->nthreads) { b->bar_count = 0; b->bar_gen++; b->progress++; }
     else while (b->bar_gen == g) yield_fiber();
+}
+
+// bar.sync id, count: `count` threads rendezvous on barrier `id`
+inline void named_barrier(int id, int count) {
+    Block* b = cur();
+    Block::Named& nb = b->named[id & 15];
+    unsigned g = nb.gen;
+    if (++nb.count == count) { nb.count = 0; nb.gen++; b->progress++; }
+    else while (nb.gen == g) yield_fiber();
 }
 
 inline int lane_id() { Block* b = cur(); const Fiber& f = b->fibers[b->current]; (void)f; return b->current & 31; }
@@ -196,6 +207,7 @@ inline void run_block(Block& b) {
     }
     b.bar_count = 0;
     for (auto& w : b.warps) w.count = 0;
+    for (auto& n : b.named) n.count = 0;
     while (remaining > 0) {
         unsigned long before = b.progress;
         for (int i = 0; i < b.nthreads; ++i) {
@@ -276,6 +288,10 @@ static inline double atomicAdd(double* addr, double v) {
 }
 static inline unsigned atomicAdd(unsigned* addr, unsigned v) { return __atomic_fetch_add(addr, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* addr, int v) { return __atomic_fetch_add(addr, v, __ATOMIC_SEQ_CST); }
+
+// polling back-off of the pipeline kernels: let the producer CTA's OS thread run
+#include <chrono>
+#define WFM_SPIN_PAUSE() std::this_thread::sleep_for(std::chrono::microseconds(50))
 
 // dynamic shared memory of the running CTA
 #define WFM_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::cur()->smem)

@@ -72,3 +72,33 @@ if __name__ == "__main__":
             s0, _ = score(N, E, R1, R2, R3, 0, 0, esz)
             print(f"  N={N:5d} plan={E,R1,R2,R3} unpadded={s0:.2f} best pa={best[1]} pb={best[2]} "
                   f"score={best[0][0]:.3f} rowlen={best[0][1]}")
+
+
+def score_cols(N, E, R1, R2, R3, C, shift, esz):
+    """Column layout: cell = (i + (i >> shift)) * C + c, thread id = t * C + c."""
+    T = N // E
+    S1 = N // R1
+    nthreads = C * T
+    tot = ideal = 0
+
+    def padc(i):
+        return i + ((i >> shift) if shift else 0)
+
+    def run(posfn, nb, legs):
+        nonlocal tot, ideal
+        for u in range(nb):
+            for r in range(legs):
+                for w0 in range(0, nthreads, 32):
+                    addrs = []
+                    for tid in range(w0, min(w0 + 32, nthreads)):
+                        t, c = divmod(tid, C)
+                        addrs.append(padc(posfn(t + T * u, r)) * C + c)
+                    tot += wavefronts(addrs, esz)
+                    ideal += (len(addrs) * esz + 127) // 128
+    run(lambda b, k1: k1 * S1 + b, E // R1, R1)
+    if R3 > 1:
+        run(lambda b, r: (b // R3) * S1 + r * R3 + (b % R3), E // R2, R2)
+        run(lambda b, r: (b % R1) * S1 + (b // R1) * R3 + r, E // R3, R3)
+    else:
+        run(lambda b, r: b * S1 + r, E // R2, R2)
+    return tot / ideal
