@@ -59,7 +59,8 @@ struct wfm_model {
     std::vector<uint8_t> h_map, h_zsup, h_esc;
     bool activity_dirty = true;
     int nax = 0, nay = 0, pitch = 0;
-    DevBuf act_x, inv_x, act_y, inv_y;
+    DevBuf act_x, inv_x, act_y, inv_y, cell_list;
+    int ncells = 0;
     // FFT twiddles
     DevBuf tw;
     // outputs + PState (MicroscopeModel.java:42)
@@ -202,7 +203,15 @@ int rebuild_activity(wfm_model* h) {
     WFM_CK(h, h->inv_x.ensure(sizeof(int) * N));
     WFM_CK(h, h->inv_y.ensure(sizeof(int) * N));
     WFM_CK(h, h->support.ensure(npix));
+    std::vector<int> cells;                       // support cells of the compact strip [N][pitch]
+    for (int ky = 0; ky < N; ++ky)
+        for (int xi = 0; xi < h->nax; ++xi)
+            if (sup[ax[xi] + N * ky]) cells.push_back(ky * h->pitch + xi);
+    h->ncells = (int)cells.size();
+    WFM_CK(h, h->cell_list.ensure(sizeof(int) * (cells.size() + 1)));
     WFM_CK(h, cudaStreamSynchronize(h->stream));
+    if (!cells.empty())
+        WFM_CK(h, cudaMemcpy(h->cell_list.p, cells.data(), sizeof(int) * cells.size(), cudaMemcpyHostToDevice));
     WFM_CK(h, cudaMemcpy(h->act_x.p, ax.data(), sizeof(int) * ax.size(), cudaMemcpyHostToDevice));
     WFM_CK(h, cudaMemcpy(h->act_y.p, ay.data(), sizeof(int) * ay.size(), cudaMemcpyHostToDevice));
     WFM_CK(h, cudaMemcpy(h->inv_x.p, ix.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
@@ -320,7 +329,8 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         r.kinds = kinds; r.last_plane_only = a.last_plane_only;
         r.dxy = h->dxy; r.lambda_ni = h->lambda_ni; r.deltaX = h->deltaX; r.deltaY = h->deltaY;
         r.glen = h->glen();
-        const int nblocks = (int)((img + WFM_RED_THREADS - 1) / WFM_RED_THREADS);
+        r.cell_list = (const int*)h->cell_list.p; r.ncells = h->ncells;
+        const int nblocks = h->ncells > 0 ? (h->ncells + WFM_RED_THREADS - 1) / WFM_RED_THREADS : 1;
         const int nchunks = (h->nzl + WFM_RED_PLANES - 1) / WFM_RED_PLANES;
         WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * nchunks * r.glen));
         r.block_part = (double*)h->block_part.p;
@@ -454,7 +464,7 @@ int wfm_destroy(wfm_model* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->Z, &h->rho, &h->phi, &h->psi, &h->mask, &h->map, &h->support, &h->act_x, &h->inv_x,
-                      &h->act_y, &h->inv_y, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gj, &h->Gm, &h->ctl, &h->block_part,
+                      &h->act_y, &h->inv_y, &h->cell_list, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gj, &h->Gm, &h->ctl, &h->block_part,
                       &h->grad, &h->qdev})
         b->release();
     drain_spans(h);

@@ -252,7 +252,8 @@ struct PipeCtl {
 #endif
 template <typename T, int N> struct PipeCfg {
     using P = Plan<N>;
-    static constexpr int C = (sizeof(T) == 8 && N >= 256) ? WFM_PIPE_C64 : ColCfg<T, N>::C;   // columns per B-item == rows per A-item
+    static constexpr int C = (N >= 256) ? (sizeof(T) == 8 ? WFM_PIPE_C64 : 2 * WFM_PIPE_C64) : ColCfg<T, N>::C;   // columns per B-item == rows per A-item
+    static_assert(P::T < 64 || C <= 15, "one named barrier per row transform");
     static constexpr int TT = P::T;
     static constexpr int THREADS = C * TT;
     static constexpr int SH = ilog2_c(P::S1);
@@ -310,24 +311,49 @@ WFM_DEVI void pipe_signal(unsigned* cnt) {
 }
 
 // Work-item queue of a persistent CTA.  Thread 0 claims item i+1 while item i is being processed
-// (the atomic's latency is off the critical path); the claim becomes visible to the CTA through the
-// barriers every item executes.
+// and probes that item's dependency counter once (acquire): in steady state the dependency is
+// already met, so neither the atomic nor the L2 poll is on the critical path.  The claim becomes
+// visible to the CTA through the barriers every item executes.
 struct PipeQueue {
-    unsigned* s_item;   // [2] shared
+    unsigned* s;   // shared: s[0..1] item index, s[2..3] dependency already satisfied
     int cur;
-    WFM_DEVI void init(unsigned* smem2, const PipeCtl& c) {
-        s_item = smem2; cur = 0;
-        if (threadIdx.x == 0) s_item[0] = atomicAdd(c.queue, 1u);
+    WFM_DEVI static bool probe(const PipeItem& it, const PipeCtl& c) {
+        const unsigned* cnt; unsigned target;
+        if (it.type == 0) {
+            if (it.plane < c.ring || !(c.roles & 2)) return true;
+            cnt = &c.cntB[it.plane - c.ring]; target = (unsigned)c.nB;
+        } else {
+            if (!(c.roles & 1)) return true;
+            cnt = &c.cntA[it.plane]; target = (unsigned)c.nA;
+        }
+        const bool ok = *(volatile const unsigned*)cnt >= target;
+        if (ok) __threadfence();
+        return ok;
+    }
+    WFM_DEVI void claim(int slot, const PipeCtl& c, int P) {
+        const unsigned idx = atomicAdd(c.queue, 1u);
+        const PipeItem it = pipe_decode(idx, P, c);
+        s[slot] = idx;
+        s[2 + slot] = (it.type < 0 || probe(it, c)) ? 1u : 0u;
+    }
+    WFM_DEVI void init(unsigned* smem4, const PipeCtl& c, int P) {
+        s = smem4; cur = 0;
+        if (threadIdx.x == 0) claim(0, c, P);
         __syncthreads();
     }
-    WFM_DEVI PipeItem take(const PipeCtl& c, int P) {
-        const unsigned idx = s_item[cur];
-        const PipeItem it = pipe_decode(idx, P, c);
-        if (threadIdx.x == 0 && it.type >= 0) s_item[cur ^ 1] = atomicAdd(c.queue, 1u);
+    // returns the current item; `ready` tells whether its dependency was already observed as met
+    WFM_DEVI PipeItem take(const PipeCtl& c, int P, bool& ready) {
+        const PipeItem it = pipe_decode(s[cur], P, c);
+        ready = s[2 + cur] != 0u;
+        if (threadIdx.x == 0 && it.type >= 0) claim(cur ^ 1, c, P);
         cur ^= 1;
         return it;
     }
 };
+
+// What an item must wait for before it may touch the ring slot (NULL counter: nothing).
+struct PipeDep { const unsigned* cnt; unsigned target; unsigned* err; };
+WFM_DEVI void pipe_wait(const PipeDep& d) { if (d.cnt) pipe_wait(d.cnt, d.target, d.err); }
 
 // ================================================================================================
 // computePsf()  WFM:280-350 (fp32: 209-278)
@@ -347,7 +373,8 @@ template <typename T> struct PsfArgs {
 // A-item: rows yi0 .. yi0+C-1 of plane pl.  A = rho*exp(i(phi + defoc_scale*psi)) is synthesised in
 // the load (WFM:311-316; sincos only where rho != 0, quirk Q6), then FFT along x.
 template <typename T, int N>
-WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s) {
+WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+                            const PipeDep& dep) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
@@ -375,6 +402,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
         }
     }
     fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
+    pipe_wait(dep);                                   // ring slot free? (its previous tenant's column items are done)
     if (valid) {
         cx<T>* dst = a.T1 + ((size_t)(pl % ring) * a.nay + yi) * N;
 #pragma unroll
@@ -428,23 +456,24 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     cx<T>* tw_s = cells + Cfg::CELLS;
     int* inv_s = reinterpret_cast<int*>(tw_s + N);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; inv_s[i] = a.inv_y[i]; }
-    __shared__ unsigned s_queue[2];
+    __shared__ unsigned s_queue[4];
     PipeQueue qu;
-    qu.init(s_queue, ctl);
     const int P = a.g.nzl;
+    qu.init(s_queue, ctl, P);
     for (;;) {
-        const PipeItem it = qu.take(ctl, P);
+        bool ready;
+        const PipeItem it = qu.take(ctl, P, ready);
         if (it.type < 0) break;
         if (it.type == 0) {
             if (ctl.roles & 1) {
-                if ((ctl.roles & 2) && it.plane >= ctl.ring) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
-                psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+                PipeDep dep;
+                dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
+                psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, dep);
             }
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
             if (ctl.roles & 2) {
-                if (ctl.roles & 1) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                else __syncthreads();
+                if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
                 psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s);
             }
             pipe_signal(&ctl.cntB[it.plane]);
@@ -476,7 +505,7 @@ template <typename T> struct JacArgs {
 // (WFM:907-914), FFT along x, keep the active kx only.
 template <typename T, int N>
 WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
-                            const int* inv_s) {
+                            const int* inv_s, const PipeDep& dep) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
@@ -494,6 +523,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
             v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
         }
     fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
+    pipe_wait(dep);                                   // ring slot free?
     cx<T>* dst = a.T2 + ((size_t)(pl % ring) * N + y) * a.pitch;
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
@@ -559,23 +589,24 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     cx<T>* tw_s = cells + Cfg::CELLS;
     int* inv_s = reinterpret_cast<int*>(tw_s + N);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; inv_s[i] = a.inv_x[i]; }
-    __shared__ unsigned s_queue[2];
+    __shared__ unsigned s_queue[4];
     PipeQueue qu;
-    qu.init(s_queue, ctl);
     const int P = a.g.nzl;
+    qu.init(s_queue, ctl, P);
     for (;;) {
-        const PipeItem it = qu.take(ctl, P);
+        bool ready;
+        const PipeItem it = qu.take(ctl, P, ready);
         if (it.type < 0) break;
         if (it.type == 0) {
             if (ctl.roles & 1) {
-                if ((ctl.roles & 2) && it.plane >= ctl.ring) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
-                jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s);
+                PipeDep dep;
+                dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
+                jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s, dep);
             }
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
             if (ctl.roles & 2) {
-                if (ctl.roles & 1) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                else __syncthreads();
+                if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
                 jac_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
             }
             pipe_signal(&ctl.cntB[it.plane]);
@@ -595,13 +626,15 @@ struct ReduceArgs {
     double dxy, lambda_ni, deltaX, deltaY;
     double* block_part;   // [nchunks][nblocks][glen]
     int glen;             // 3 + nphase + nmod
+    const int* cell_list; // [ncells] strip cells (ky*pitch + xi) that lie on the support
+    int ncells;
 };
 
 #define WFM_RED_THREADS 256
 #define WFM_RED_CHUNK 8
 #define WFM_RED_PLANES 16   // planes summed by one CTA (grid.y = ceil(nzl / WFM_RED_PLANES))
 
-// One thread per (ky, xi) cell of the compact pupil strip and per chunk of WFM_RED_PLANES planes.
+// One thread per support cell (ky, xi) of the compact pupil strip and per chunk of WFM_RED_PLANES planes.
 // Sums the planes of the chunk in fixed order (gP = sum jin, gD = sum defoc*jin, gM = sum J), then
 // forms the glen dot products WFM_RED_CHUNK at a time: shuffle-reduce inside each warp, then across
 // the warps of the block through shared memory.
@@ -609,8 +642,9 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     __shared__ double red[WFM_RED_THREADS / 32][WFM_RED_CHUNK];
     const int N = a.g.N;
     const size_t img = (size_t)N * a.pitch;
-    const size_t cell = (size_t)blockIdx.x * WFM_RED_THREADS + threadIdx.x;
-    const bool in_range = cell < img;
+    const int li = blockIdx.x * WFM_RED_THREADS + threadIdx.x;
+    const bool in_range = li < a.ncells;
+    const size_t cell = in_range ? (size_t)a.cell_list[li] : 0;
     const int ky = in_range ? (int)(cell / a.pitch) : 0;
     const int xi = in_range ? (int)(cell % a.pitch) : 0;
     const bool colvalid = in_range && xi < a.nax;
