@@ -270,14 +270,15 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
     using Cfg = PipeCfg<T, N>;
     auto kfn = &k_psf_pipeline<T, N>;
     int rc = set_smem(h, kfn, Cfg::SMEM); if (rc) return rc;
-    const int nA = (h->nay + Cfg::C - 1) / Cfg::C, nB = N / Cfg::C;
-    const size_t plane_bytes = sizeof(cx<T>) * (size_t)h->nay * N;
+    const int nA = h->pitch / Cfg::C, nB = N / Cfg::C;
+    const size_t plane_bytes = sizeof(cx<T>) * (size_t)N * h->pitch;
     const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, Cfg::MINB);
     WFM_CK(h, h->scratch.ensure(plane_bytes * pp.ring));
     PsfArgs<T> a;
     a.g = geom_of(h);
     a.rho = (const double*)h->rho.p; a.phi = (const double*)h->phi.p; a.psi = (const double*)h->psi.p;
-    a.act_y = (const int*)h->act_y.p; a.inv_y = (const int*)h->inv_y.p; a.nay = h->nay;
+    a.act_x = (const int*)h->act_x.p; a.inv_x = (const int*)h->inv_x.p; a.inv_y = (const int*)h->inv_y.p;
+    a.nax = h->nax; a.pitch = h->pitch;
     a.tw = (const cx<T>*)h->tw.p;
     a.T1 = (cx<T>*)h->scratch.p; a.cpx = (cx<T>*)h->cpx.p; a.psf = (T*)h->psf.p;
     PipeCtl ctl;

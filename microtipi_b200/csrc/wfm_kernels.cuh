@@ -8,7 +8,7 @@
 //   Z             : double[nzern][Npix]     orthonormal Zernike basis
 //   cpx           : cx<T>[nzl][Npix]        conj(FFT2(A_z))            (WFM:325-326)
 //   psf           : T[nzl][Npix]            |a|^2 * PSFnorm           (WFM:327)
-//   T1 ring       : cx<T>[ring][nay][N]     row-pass output of the PSF transform (active rows only)
+//   T1 ring       : cx<T>[ring][N][pitch]   column-pass output of the PSF transform (active columns only)
 //   T2 ring       : cx<T>[ring][N][pitch]   row-pass output of the adjoint transform (active kx only)
 //   Gj, Gm        : double[nzl][N][pitch]   per-plane Jacobian integrands on the compact pupil strip
 //
@@ -261,7 +261,7 @@ template <typename T, int N> struct PipeCfg {
     static constexpr int ROWLEN = RowLayout<T, N>::LEN;
     static constexpr int COLLEN = ColL::pad_c(N - 1) + 1;
     static constexpr int CELLS = C * (ROWLEN > COLLEN ? ROWLEN : COLLEN);
-    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N) + sizeof(int) * (size_t)N;
+    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N) + sizeof(int) * (size_t)(2 * N);
     // resident CTAs per SM the register allocation is tuned for: 1024 threads (64 registers each)
     static constexpr int BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
     static constexpr int BY_SMEM = (int)((220 * 1024) / SMEM) < 1 ? 1 : (int)((220 * 1024) / SMEM);
@@ -357,40 +357,47 @@ WFM_DEVI void pipe_wait(const PipeDep& d) { if (d.cnt) pipe_wait(d.cnt, d.target
 
 // ================================================================================================
 // computePsf()  WFM:280-350 (fp32: 209-278)
+//
+// a = FFT2(A) is evaluated columns first, rows second: the pupil is zero outside `nax` active
+// columns, so pass A transforms only those (FFT along y, pupil synthesis fused into the load), and
+// pass B -- the big one, all N rows -- runs along the contiguous axis: every warp stores full,
+// consecutive 512-byte runs of conj(a) and 256-byte runs of psf straight from registers.
 // ================================================================================================
 template <typename T> struct PsfArgs {
     Geom g;
     const double* rho; const double* phi; const double* psi;
-    const int* act_y;   // [nay] active rows
-    const int* inv_y;   // [N]   row -> compact index or -1
-    int nay;
+    const int* act_x;   // [nax] active columns
+    const int* inv_x;   // [N]   column -> compact index or -1
+    const int* inv_y;   // [N]   row -> compact index or -1 (only its sign is used: is the row active?)
+    int nax;
+    int pitch;          // nax rounded up to a multiple of the column tile
     const cx<T>* tw;    // W_N table (global; copied to shared memory once per CTA)
-    cx<T>* T1;          // ring: [ring][nay][N]
+    cx<T>* T1;          // ring: [ring][N][pitch]
     cx<T>* cpx;
     T* psf;
 };
 
-// A-item: rows yi0 .. yi0+C-1 of plane pl.  A = rho*exp(i(phi + defoc_scale*psi)) is synthesised in
-// the load (WFM:311-316; sincos only where rho != 0, quirk Q6), then FFT along x.
+// A-item: active columns xi0 .. xi0+C-1 of plane pl.  A = rho*exp(i(phi + defoc_scale*psi)) is
+// synthesised in the load (WFM:311-316; sincos only where rho != 0, quirk Q6), then FFT along y.
 template <typename T, int N>
-WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
-                            const PipeDep& dep) {
+WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+                            const int* invy_s, const PipeDep& dep) {
     using P = Plan<N>;
-    using L = RowLayout<T, N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
-    const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
-    const int yi = sub * C + slot;
-    const bool valid = yi < a.nay;
-    const int y = valid ? __ldg(&a.act_y[yi]) : 0;
+    using L = typename PipeCfg<T, N>::ColL;
+    const int c = threadIdx.x % C, t = threadIdx.x / C;
+    const int xi = sub * C + c;
+    const bool colvalid = xi < a.nax;
+    const int x = colvalid ? __ldg(&a.act_x[xi]) : 0;
     const double s = defoc_scale_dev(a.g.z0 + pl, a.g.nz_global, a.g.dz);
     cx<T> v[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u) {
 #pragma unroll
         for (int r = 0; r < P::R1; ++r) {
-            const int x = (t + TT * u) + P::S1 * r;
+            const int y = (t + TT * u) + P::S1 * r;
             const int in = x + N * y;
-            const double rho = valid ? __ldg(&a.rho[in]) : 0.0;
+            const double rho = (colvalid && invy_s[y] >= 0) ? __ldg(&a.rho[in]) : 0.0;
             cx<T> val = mkc<T>((T)0, (T)0);
             if (rho != 0.0) {
                 const double ph = __dadd_rn(__ldg(&a.phi[in]), __dmul_rn(s, __ldg(&a.psi[in])));
@@ -401,51 +408,50 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
             v[u * P::R1 + r] = val;
         }
     }
-    fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
-    pipe_wait(dep);                                   // ring slot free? (its previous tenant's column items are done)
-    if (valid) {
-        cx<T>* dst = a.T1 + ((size_t)(pl % ring) * a.nay + yi) * N;
+    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, 0);
+    pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
+    if (colvalid) {
+        cx<T>* dst = a.T1 + (size_t)(pl % ring) * N * a.pitch + xi;
 #pragma unroll
         for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
-            for (int r = 0; r < P::RL; ++r) __stcg(&dst[(t + TT * u) + P::SL * r], v[u * P::RL + r]);
+            for (int r = 0; r < P::RL; ++r) __stcg(&dst[(size_t)((t + TT * u) + P::SL * r) * a.pitch], v[u * P::RL + r]);
     }
 }
 
-// B-item: columns kx0 .. kx0+C-1 of plane pl: FFT along y (inactive rows are zero), then the fused
-// streaming store of conj(a) and |a|^2*PSFnorm (WFM:323-328).
+// B-item: rows ky0 .. ky0+C-1 of plane pl: FFT along x (inactive columns are zero), then the fused
+// streaming store of conj(a) and |a|^2*PSFnorm (WFM:323-328) as full contiguous rows.
 template <typename T, int N>
-WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
-                            const int* inv_s) {
+WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+                            const int* invx_s) {
     using P = Plan<N>;
+    using L = RowLayout<T, N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
-    using L = typename PipeCfg<T, N>::ColL;
-    const int c = threadIdx.x % C, t = threadIdx.x / C;
-    const int kx = sub * C + c;
-    const cx<T>* src = a.T1 + (size_t)(pl % ring) * a.nay * N + kx;
+    const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
+    const int ky = sub * C + slot;                     // N % C == 0: always a valid row
+    const cx<T>* src = a.T1 + ((size_t)(pl % ring) * N + ky) * a.pitch;
     cx<T> v[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r) {
-            const int yi = inv_s[(t + TT * u) + P::S1 * r];
-            v[u * P::R1 + r] = (yi >= 0) ? __ldcg(&src[(size_t)yi * N]) : mkc<T>((T)0, (T)0);
+            const int xi = invx_s[(t + TT * u) + P::S1 * r];
+            v[u * P::R1 + r] = (xi >= 0) ? __ldcg(&src[xi]) : mkc<T>((T)0, (T)0);
         }
-    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, 0);
+    fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
     const T norm = (T)a.g.psf_norm;
-    const size_t base = (size_t)pl * N * N + kx;
+    const size_t base = (size_t)pl * N * N + (size_t)N * ky;
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
         for (int r = 0; r < P::RL; ++r) {
-            const int ky = (t + TT * u) + P::SL * r;
+            const int kx = (t + TT * u) + P::SL * r;
             const cx<T> val = v[u * P::RL + r];
-            const size_t o = base + (size_t)N * ky;
-            __stcs(&a.cpx[o], mkc<T>(val.x, -val.y));            // store conjugate of A (WFM:326)
+            __stcs(&a.cpx[base + kx], mkc<T>(val.x, -val.y));     // store conjugate of A (WFM:326)
             if constexpr (sizeof(T) == 8)
-                __stcs(&a.psf[o], (T)__dmul_rn(__dadd_rn(__dmul_rn(val.x, val.x), __dmul_rn(val.y, val.y)), norm));
+                __stcs(&a.psf[base + kx], (T)__dmul_rn(__dadd_rn(__dmul_rn(val.x, val.x), __dmul_rn(val.y, val.y)), norm));
             else
-                __stcs(&a.psf[o], (T)__fmul_rn(__fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y)), norm));
+                __stcs(&a.psf[base + kx], (T)__fmul_rn(__fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y)), norm));
         }
 }
 
@@ -454,8 +460,9 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     using Cfg = PipeCfg<T, N>;
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
-    int* inv_s = reinterpret_cast<int*>(tw_s + N);
-    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; inv_s[i] = a.inv_y[i]; }
+    int* invx_s = reinterpret_cast<int*>(tw_s + N);
+    int* invy_s = invx_s + N;
+    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; invy_s[i] = a.inv_y[i]; }
     __shared__ unsigned s_queue[4];
     PipeQueue qu;
     const int P = a.g.nzl;
@@ -468,13 +475,13 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, dep);
+                psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invy_s, dep);
             }
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s);
+                psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s);
             }
             pipe_signal(&ctl.cntB[it.plane]);
         }
