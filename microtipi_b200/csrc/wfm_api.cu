@@ -60,6 +60,8 @@ struct wfm_model {
     bool activity_dirty = true;
     int nax = 0, nay = 0, pitch = 0;
     DevBuf act_x, inv_x, act_y, inv_y, cell_list;
+    DevBuf s_rho, s_phi, s_psi, s_flags;          // pupil strip [N][pitch]
+    bool strip_dirty = true;
     int ncells = 0;
     // FFT twiddles
     DevBuf tw;
@@ -226,6 +228,29 @@ template <class K> int set_smem(wfm_model* h, K kfn, size_t bytes) {
     return WFM_OK;
 }
 
+// Pupil arrays -> strip layout (after any setter, before the next pipeline launch).
+int pack_strip(wfm_model* h) {
+    if (!h->strip_dirty) return WFM_OK;
+    const size_t cells = (size_t)h->N * h->pitch;
+    WFM_CK(h, h->s_rho.ensure(8 * cells)); WFM_CK(h, h->s_phi.ensure(8 * cells));
+    WFM_CK(h, h->s_psi.ensure(8 * cells)); WFM_CK(h, h->s_flags.ensure(cells));
+    KernelSpan span(h, WFM_K_SETTERS);
+    auto kfn = &k_pack_strip;
+    WFM_LAUNCH(kfn, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, h->stream, (double*)h->s_rho.p,
+               (double*)h->s_phi.p, (double*)h->s_psi.p, (uint8_t*)h->s_flags.p, (const double*)h->rho.p,
+               (const double*)h->phi.p, (const double*)h->psi.p, (const uint8_t*)h->mask.p,
+               (const uint8_t*)h->support.p, (const int*)h->act_x.p, h->N, h->nax, h->pitch);
+    WFM_CK_LAUNCH(h, "k_pack_strip");
+    h->strip_dirty = false;
+    return WFM_OK;
+}
+Strip strip_of(const wfm_model* h) {
+    Strip st;
+    st.rho = (const double*)h->s_rho.p; st.phi = (const double*)h->s_phi.p; st.psi = (const double*)h->s_psi.p;
+    st.flags = (const uint8_t*)h->s_flags.p;
+    return st;
+}
+
 // ---- pipeline control ---------------------------------------------------------------------------------
 // Ring / lag sizing: LAG ~ 1.5x the planes whose A-items are in flight at once, RING = 2*LAG + 2, with the
 // ring kept within ~48 MB so that it stays L2-resident (126 MB L2 shared with the streaming traffic).
@@ -270,14 +295,15 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
     using Cfg = PipeCfg<T, N>;
     auto kfn = &k_psf_pipeline<T, N>;
     int rc = set_smem(h, kfn, Cfg::SMEM); if (rc) return rc;
-    const int nA = h->pitch / Cfg::C, nB = N / Cfg::C;
+    rc = pack_strip(h); if (rc) return rc;
+    const int nA = h->pitch / Cfg::C, nB = N / Cfg::ROWS_PER_ITEM;
     const size_t plane_bytes = sizeof(cx<T>) * (size_t)N * h->pitch;
     const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, Cfg::MINB);
     WFM_CK(h, h->scratch.ensure(plane_bytes * pp.ring));
     PsfArgs<T> a;
     a.g = geom_of(h);
-    a.rho = (const double*)h->rho.p; a.phi = (const double*)h->phi.p; a.psi = (const double*)h->psi.p;
-    a.act_x = (const int*)h->act_x.p; a.inv_x = (const int*)h->inv_x.p; a.inv_y = (const int*)h->inv_y.p;
+    a.st = strip_of(h);
+    a.inv_x = (const int*)h->inv_x.p;
     a.nax = h->nax; a.pitch = h->pitch;
     a.tw = (const cx<T>*)h->tw.p;
     a.T1 = (cx<T>*)h->scratch.p; a.cpx = (cx<T>*)h->cpx.p; a.psf = (T*)h->psf.p;
@@ -295,7 +321,8 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     using Cfg = PipeCfg<T, N>;
     auto kfn = &k_jac_pipeline<T, N>;
     int rc = set_smem(h, kfn, Cfg::SMEM); if (rc) return rc;
-    const int nA = N / Cfg::C, nB = h->pitch / Cfg::C;
+    rc = pack_strip(h); if (rc) return rc;
+    const int nA = N / Cfg::ROWS_PER_ITEM, nB = h->pitch / Cfg::C;
     const size_t plane_bytes = sizeof(cx<T>) * (size_t)N * h->pitch;
     const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, Cfg::MINB);
     WFM_CK(h, h->scratch.ensure(plane_bytes * pp.ring));
@@ -305,9 +332,8 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     JacArgs<T> a;
     a.g = geom_of(h);
     a.cpx = (const cx<T>*)h->cpx.p; a.q = (const T*)q_dev;
-    a.rho = (const double*)h->rho.p; a.phi = (const double*)h->phi.p; a.psi = (const double*)h->psi.p;
-    a.mask = (const uint8_t*)h->mask.p; a.support = (const uint8_t*)h->support.p;
-    a.act_x = (const int*)h->act_x.p; a.inv_x = (const int*)h->inv_x.p; a.nax = h->nax; a.pitch = h->pitch;
+    a.st = strip_of(h);
+    a.inv_x = (const int*)h->inv_x.p; a.nax = h->nax; a.pitch = h->pitch;
     a.tw = (const cx<T>*)h->tw.p;
     a.T2 = (cx<T>*)h->scratch.p;
     a.Gj = (double*)h->Gj.p;
@@ -325,7 +351,8 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         KernelSpan span(h, WFM_K_JAC_REDUCE);
         ReduceArgs r;
         r.g = a.g; r.Gj = a.Gj; r.Gm = a.Gm; r.pitch = h->pitch; r.nax = h->nax;
-        r.act_x = a.act_x; r.Z = (const double*)h->Z.p; r.psi = a.psi; r.mask = a.mask; r.support = a.support;
+        r.act_x = (const int*)h->act_x.p; r.Z = (const double*)h->Z.p; r.psi = (const double*)h->psi.p;
+        r.mask = (const uint8_t*)h->mask.p; r.support = (const uint8_t*)h->support.p;
         r.nphase = h->nphase; r.nmod = h->nmod; r.phase_off = h->radial ? 1 : 3;
         r.kinds = kinds; r.last_plane_only = a.last_plane_only;
         r.dxy = h->dxy; r.lambda_ni = h->lambda_ni; r.deltaX = h->deltaX; r.deltaY = h->deltaY;
@@ -391,7 +418,7 @@ int compute_psf_impl(wfm_model* h) {
     return WFM_OK;
 }
 
-int invalidate(wfm_model* h) { h->pstate = 0; return WFM_OK; }
+int invalidate(wfm_model* h) { h->pstate = 0; h->strip_dirty = true; return WFM_OK; }
 
 // After a synchronisation point: did a pipeline dependency wait time out?  (It cannot by
 // construction; the flag turns a would-be hang into an error code.)
@@ -465,7 +492,7 @@ int wfm_destroy(wfm_model* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->Z, &h->rho, &h->phi, &h->psi, &h->mask, &h->map, &h->support, &h->act_x, &h->inv_x,
-                      &h->act_y, &h->inv_y, &h->cell_list, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gj, &h->Gm, &h->ctl, &h->block_part,
+                      &h->act_y, &h->inv_y, &h->cell_list, &h->s_rho, &h->s_phi, &h->s_psi, &h->s_flags, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gj, &h->Gm, &h->ctl, &h->block_part,
                       &h->grad, &h->qdev})
         b->release();
     drain_spans(h);

@@ -48,6 +48,11 @@ WFM_DEVI double defoc_depth_dev(int iz, int Nz, double dz) {
     return __dmul_rn((double)zi, dz);
 }
 WFM_DEVI int kappa_dev(int n, int N) { return (n > N / 2) ? n - N : n; }
+#ifdef WFM_FAKE_TRIG   /* profiling experiment only: how much of an item is the trig? */
+#define WFM_SINCOS(x, s, c) do { *(s) = (x) * 0.5; *(c) = 1.0 - (x); } while (0)
+#else
+#define WFM_SINCOS(x, s, c) sincos((x), (s), (c))
+#endif
 
 // ---- launch shapes --------------------------------------------------------------------------
 // Row kernels: RB transforms per CTA, 256 threads.  Column kernels: C adjacent columns per CTA.
@@ -220,6 +225,34 @@ __global__ void k_fill_uniform(T* __restrict__ out, uint64_t seed, uint64_t firs
 }
 
 // ================================================================================================
+// Pupil strip: rho, phi, psi and the mask/support flags gathered into the compact [N][pitch] layout
+// of the active columns, so that a column tile reads them as contiguous, independent loads.
+// ================================================================================================
+struct Strip {
+    const double* rho; const double* phi; const double* psi;   // [N][pitch]
+    const uint8_t* flags;                                        // bit 0: maskPupil, bit 1: support
+};
+__global__ void k_pack_strip(double* __restrict__ s_rho, double* __restrict__ s_phi, double* __restrict__ s_psi,
+                             uint8_t* __restrict__ s_flags, const double* __restrict__ rho,
+                             const double* __restrict__ phi, const double* __restrict__ psi,
+                             const uint8_t* __restrict__ mask, const uint8_t* __restrict__ support,
+                             const int* __restrict__ act_x, int N, int nax, int pitch) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= N * pitch) return;
+    const int ky = cell / pitch, xi = cell % pitch;
+    double r = 0.0, f = 0.0, p = 0.0;
+    uint8_t fl = 0;
+    if (xi < nax) {
+        const int in = act_x[xi] + N * ky;
+        if (support[in]) {
+            fl = (uint8_t)(2u | (mask[in] ? 1u : 0u));
+            r = rho[in]; f = phi[in]; p = psi[in];
+        }
+    }
+    s_rho[cell] = r; s_phi[cell] = f; s_psi[cell] = p; s_flags[cell] = fl;
+}
+
+// ================================================================================================
 // Persistent two-stage pipelines.
 //
 // Both directions of the path are "row transform -> pruned intermediate -> column transform":
@@ -252,16 +285,20 @@ struct PipeCtl {
 #endif
 template <typename T, int N> struct PipeCfg {
     using P = Plan<N>;
-    static constexpr int C = (N >= 256) ? (sizeof(T) == 8 ? WFM_PIPE_C64 : 2 * WFM_PIPE_C64) : ColCfg<T, N>::C;   // columns per B-item == rows per A-item
+    static constexpr int C = (N >= 256) ? (sizeof(T) == 8 ? WFM_PIPE_C64 : 8) : ColCfg<T, N>::C;   // columns per B-item == rows per A-item
     static_assert(P::T < 64 || C <= 15, "one named barrier per row transform");
     static constexpr int TT = P::T;
     static constexpr int THREADS = C * TT;
+    // a row item gives every TT-thread group KR consecutive-in-time rows: the CTA-wide barrier and the
+    // queue claim at the item boundary are paid once per C*KR rows
+    static constexpr int KR = ((N / C) % 4 == 0 && N >= 256) ? 4 : 1;
+    static constexpr int ROWS_PER_ITEM = C * KR;
     static constexpr int SH = ilog2_c(P::S1);
     using ColL = ColLayout<C, SH>;
     static constexpr int ROWLEN = RowLayout<T, N>::LEN;
     static constexpr int COLLEN = ColL::pad_c(N - 1) + 1;
     static constexpr int CELLS = C * (ROWLEN > COLLEN ? ROWLEN : COLLEN);
-    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N) + sizeof(int) * (size_t)(2 * N);
+    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N) + sizeof(int) * (size_t)N;
     // resident CTAs per SM the register allocation is tuned for: 1024 threads (64 registers each)
     static constexpr int BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
     static constexpr int BY_SMEM = (int)((220 * 1024) / SMEM) < 1 ? 1 : (int)((220 * 1024) / SMEM);
@@ -365,10 +402,8 @@ WFM_DEVI void pipe_wait(const PipeDep& d) { if (d.cnt) pipe_wait(d.cnt, d.target
 // ================================================================================================
 template <typename T> struct PsfArgs {
     Geom g;
-    const double* rho; const double* phi; const double* psi;
-    const int* act_x;   // [nax] active columns
+    Strip st;           // pupil in strip layout
     const int* inv_x;   // [N]   column -> compact index or -1
-    const int* inv_y;   // [N]   row -> compact index or -1 (only its sign is used: is the row active?)
     int nax;
     int pitch;          // nax rounded up to a multiple of the column tile
     const cx<T>* tw;    // W_N table (global; copied to shared memory once per CTA)
@@ -381,78 +416,85 @@ template <typename T> struct PsfArgs {
 // synthesised in the load (WFM:311-316; sincos only where rho != 0, quirk Q6), then FFT along y.
 template <typename T, int N>
 WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
-                            const int* invy_s, const PipeDep& dep) {
+                            const PipeDep& dep) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
     const int c = threadIdx.x % C, t = threadIdx.x / C;
-    const int xi = sub * C + c;
-    const bool colvalid = xi < a.nax;
-    const int x = colvalid ? __ldg(&a.act_x[xi]) : 0;
+    const int xi = sub * C + c;                        // xi < pitch: strip cells of padding columns are zero
     const double s = defoc_scale_dev(a.g.z0 + pl, a.g.nz_global, a.g.dz);
+    double rho[E];
+#pragma unroll
+    for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+        for (int r = 0; r < P::R1; ++r)
+            rho[u * P::R1 + r] = __ldg(&a.st.rho[(size_t)((t + TT * u) + P::S1 * r) * a.pitch + xi]);
     cx<T> v[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u) {
 #pragma unroll
         for (int r = 0; r < P::R1; ++r) {
-            const int y = (t + TT * u) + P::S1 * r;
-            const int in = x + N * y;
-            const double rho = (colvalid && invy_s[y] >= 0) ? __ldg(&a.rho[in]) : 0.0;
+            const int e = u * P::R1 + r;
             cx<T> val = mkc<T>((T)0, (T)0);
-            if (rho != 0.0) {
-                const double ph = __dadd_rn(__ldg(&a.phi[in]), __dmul_rn(s, __ldg(&a.psi[in])));
+            if (rho[e] != 0.0) {
+                const size_t cell = (size_t)((t + TT * u) + P::S1 * r) * a.pitch + xi;
+                const double ph = __dadd_rn(__ldg(&a.st.phi[cell]), __dmul_rn(s, __ldg(&a.st.psi[cell])));
                 double sn, cs;
-                sincos(ph, &sn, &cs);
-                val = mkc<T>((T)__dmul_rn(rho, cs), (T)__dmul_rn(rho, sn));
+                WFM_SINCOS(ph, &sn, &cs);
+                val = mkc<T>((T)__dmul_rn(rho[e], cs), (T)__dmul_rn(rho[e], sn));
             }
-            v[u * P::R1 + r] = val;
+            v[e] = val;
         }
     }
     fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, 0);
     pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
-    if (colvalid) {
-        cx<T>* dst = a.T1 + (size_t)(pl % ring) * N * a.pitch + xi;
+    cx<T>* dst = a.T1 + (size_t)(pl % ring) * N * a.pitch + xi;
 #pragma unroll
-        for (int u = 0; u < E / P::RL; ++u)
+    for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
-            for (int r = 0; r < P::RL; ++r) __stcg(&dst[(size_t)((t + TT * u) + P::SL * r) * a.pitch], v[u * P::RL + r]);
-    }
+        for (int r = 0; r < P::RL; ++r) __stcg(&dst[(size_t)((t + TT * u) + P::SL * r) * a.pitch], v[u * P::RL + r]);
 }
 
-// B-item: rows ky0 .. ky0+C-1 of plane pl: FFT along x (inactive columns are zero), then the fused
-// streaming store of conj(a) and |a|^2*PSFnorm (WFM:323-328) as full contiguous rows.
+// B-item: ROWS_PER_ITEM rows of plane pl (each TT-thread group walks KR of them): FFT along x
+// (inactive columns are zero), then the fused streaming store of conj(a) and |a|^2*PSFnorm
+// (WFM:323-328) as full contiguous rows.  No CTA-wide barrier inside.
 template <typename T, int N>
 WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
                             const int* invx_s) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
-    constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
+    using Cfg = PipeCfg<T, N>;
+    constexpr int C = Cfg::C, TT = P::T, E = P::E;
     const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
-    const int ky = sub * C + slot;                     // N % C == 0: always a valid row
-    const cx<T>* src = a.T1 + ((size_t)(pl % ring) * N + ky) * a.pitch;
-    cx<T> v[E];
+    const T norm = (T)a.g.psf_norm;
+    int xis[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
-        for (int r = 0; r < P::R1; ++r) {
-            const int xi = invx_s[(t + TT * u) + P::S1 * r];
-            v[u * P::R1 + r] = (xi >= 0) ? __ldcg(&src[xi]) : mkc<T>((T)0, (T)0);
-        }
-    fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
-    const T norm = (T)a.g.psf_norm;
-    const size_t base = (size_t)pl * N * N + (size_t)N * ky;
+        for (int r = 0; r < P::R1; ++r) xis[u * P::R1 + r] = invx_s[(t + TT * u) + P::S1 * r];
+#pragma unroll 1
+    for (int kk = 0; kk < Cfg::KR; ++kk) {
+        const int ky = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;     // N % ROWS_PER_ITEM == 0
+        const cx<T>* src = a.T1 + ((size_t)(pl % ring) * N + ky) * a.pitch;
+        cx<T> v[E];
 #pragma unroll
-    for (int u = 0; u < E / P::RL; ++u)
+        for (int e = 0; e < E; ++e) v[e] = (xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
+        fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
+        const size_t base = (size_t)pl * N * N + (size_t)N * ky;
 #pragma unroll
-        for (int r = 0; r < P::RL; ++r) {
-            const int kx = (t + TT * u) + P::SL * r;
-            const cx<T> val = v[u * P::RL + r];
-            __stcs(&a.cpx[base + kx], mkc<T>(val.x, -val.y));     // store conjugate of A (WFM:326)
-            if constexpr (sizeof(T) == 8)
-                __stcs(&a.psf[base + kx], (T)__dmul_rn(__dadd_rn(__dmul_rn(val.x, val.x), __dmul_rn(val.y, val.y)), norm));
-            else
-                __stcs(&a.psf[base + kx], (T)__fmul_rn(__fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y)), norm));
-        }
+        for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+            for (int r = 0; r < P::RL; ++r) {
+                const int kx = (t + TT * u) + P::SL * r;
+                const cx<T> val = v[u * P::RL + r];
+                __stcs(&a.cpx[base + kx], mkc<T>(val.x, -val.y));     // store conjugate of A (WFM:326)
+                if constexpr (sizeof(T) == 8)
+                    __stcs(&a.psf[base + kx], (T)__dmul_rn(__dadd_rn(__dmul_rn(val.x, val.x), __dmul_rn(val.y, val.y)), norm));
+                else
+                    __stcs(&a.psf[base + kx], (T)__fmul_rn(__fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y)), norm));
+            }
+        if (kk + 1 < Cfg::KR) RowSync<TT>::sync(slot);    // the next row's stage-1 stores reuse the cells
+    }
 }
 
 template <typename T, int N>
@@ -461,8 +503,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
     int* invx_s = reinterpret_cast<int*>(tw_s + N);
-    int* invy_s = invx_s + N;
-    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; invy_s[i] = a.inv_y[i]; }
+    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
     __shared__ unsigned s_queue[4];
     PipeQueue qu;
     const int P = a.g.nzl;
@@ -475,7 +516,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invy_s, dep);
+                psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, dep);
             }
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
@@ -495,9 +536,7 @@ template <typename T> struct JacArgs {
     Geom g;
     const cx<T>* cpx;
     const T* q;
-    const double* rho; const double* phi; const double* psi;
-    const uint8_t* mask; const uint8_t* support;
-    const int* act_x;  // [nax]
+    Strip st;          // pupil in strip layout
     const int* inv_x;  // [N]
     int nax;
     int pitch;         // nax rounded up to a multiple of the column tile
@@ -508,37 +547,43 @@ template <typename T> struct JacArgs {
     int last_plane_only;  // quirk Q1 compat mode for the modulus Jacobian
 };
 
-// A-item: rows y0 .. y0+C-1 of plane pl.  Aq = conj(a)*q fused into the streaming load
-// (WFM:907-914), FFT along x, keep the active kx only.
+// A-item: ROWS_PER_ITEM rows of plane pl (each TT-thread group walks KR of them).  Aq = conj(a)*q
+// fused into the streaming load (WFM:907-914), FFT along x, keep the active kx only.
 template <typename T, int N>
 WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
-                            const int* inv_s, const PipeDep& dep) {
+                            const int* invx_s, const PipeDep& dep) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
-    constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
+    using Cfg = PipeCfg<T, N>;
+    constexpr int C = Cfg::C, TT = P::T, E = P::E;
     const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
-    const int y = sub * C + slot;                      // N % C == 0: always a valid row
-    const size_t base = (size_t)pl * N * N + (size_t)N * y;
-    cx<T> v[E];
-#pragma unroll
-    for (int u = 0; u < E / P::R1; ++u)
-#pragma unroll
-        for (int r = 0; r < P::R1; ++r) {
-            const int x = (t + TT * u) + P::S1 * r;
-            const cx<T> av = __ldcs(&a.cpx[base + x]);
-            const T qv = __ldcs(&a.q[base + x]);
-            v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
-        }
-    fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
-    pipe_wait(dep);                                   // ring slot free?
-    cx<T>* dst = a.T2 + ((size_t)(pl % ring) * N + y) * a.pitch;
+    pipe_wait(dep);                                    // ring slot free? (rarely taken: probed at claim time)
+    int xis[E];
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
-        for (int r = 0; r < P::RL; ++r) {
-            const int xi = inv_s[(t + TT * u) + P::SL * r];
-            if (xi >= 0) __stcg(&dst[xi], v[u * P::RL + r]);
-        }
+        for (int r = 0; r < P::RL; ++r) xis[u * P::RL + r] = invx_s[(t + TT * u) + P::SL * r];
+#pragma unroll 1
+    for (int kk = 0; kk < Cfg::KR; ++kk) {
+        const int y = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;      // N % ROWS_PER_ITEM == 0
+        const size_t base = (size_t)pl * N * N + (size_t)N * y;
+        cx<T> v[E];
+#pragma unroll
+        for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+            for (int r = 0; r < P::R1; ++r) {
+                const int x = (t + TT * u) + P::S1 * r;
+                const cx<T> av = __ldcs(&a.cpx[base + x]);
+                const T qv = __ldcs(&a.q[base + x]);
+                v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
+            }
+        fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
+        cx<T>* dst = a.T2 + ((size_t)(pl % ring) * N + y) * a.pitch;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (xis[e] >= 0) __stcg(&dst[xis[e]], v[e]);
+        if (kk + 1 < Cfg::KR) RowSync<TT>::sync(slot);
+    }
 }
 
 // B-item: active columns xi0 .. xi0+C-1 of plane pl: FFT along y, then the masked trig products
@@ -553,7 +598,6 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
     const int c = threadIdx.x % C, t = threadIdx.x / C;
     const int xi = sub * C + c;
     const bool colvalid = xi < a.nax;
-    const int kx = colvalid ? __ldg(&a.act_x[xi]) : 0;
     const cx<T>* src = a.T2 + (size_t)(pl % ring) * N * a.pitch + xi;
     cx<T> v[E];
 #pragma unroll
@@ -563,29 +607,34 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
             const int y = (t + TT * u) + P::S1 * r;
             v[u * P::R1 + r] = colvalid ? __ldcg(&src[(size_t)y * a.pitch]) : mkc<T>((T)0, (T)0);
         }
+    // the flags of this thread's output cells: independent loads, in flight during the transform
+    unsigned fl = 0;
+#pragma unroll
+    for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+        for (int r = 0; r < P::RL; ++r)
+            fl |= (unsigned)__ldg(&a.st.flags[(size_t)((t + TT * u) + P::SL * r) * a.pitch + xi]) << (2 * (u * P::RL + r));
     fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, 0);
-    if (!colvalid) return;
     const int iz = a.g.z0 + pl;
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
     const bool mod_plane = (a.Gm != nullptr) && (!a.last_plane_only || iz == a.g.nz_global - 1);
-    const size_t obase = (size_t)pl * N * a.pitch + xi;
+    const unsigned want = mod_plane ? 3u : 1u;         // mask bit, plus the support bit when J is needed
+    const size_t obase = (size_t)pl * N * a.pitch;
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
         for (int r = 0; r < P::RL; ++r) {
-            const int ky = (t + TT * u) + P::SL * r;
-            const int in = kx + N * ky;
-            if (!__ldg(&a.support[in])) continue;
-            const bool m = __ldg(&a.mask[in]) != 0;
-            if (!m && !mod_plane) continue;
-            const double ph = __dadd_rn(__ldg(&a.phi[in]), __dmul_rn(s, __ldg(&a.psi[in])));
+            const int e = u * P::RL + r;
+            const unsigned f = (fl >> (2 * e)) & want;
+            if (!f) continue;
+            const size_t cell = (size_t)((t + TT * u) + P::SL * r) * a.pitch + xi;
+            const double ph = __dadd_rn(__ldg(&a.st.phi[cell]), __dmul_rn(s, __ldg(&a.st.psi[cell])));
+            const double rho = __ldg(&a.st.rho[cell]);
             double sn, cs;
-            sincos(ph, &sn, &cs);
-            const cx<T> b = v[u * P::RL + r];
-            const double br = (double)b.x, bi = (double)b.y;
-            const size_t o = obase + (size_t)ky * a.pitch;
-            if (m) a.Gj[o] = __ldg(&a.rho[in]) * (br * sn + bi * cs);
-            if (mod_plane) a.Gm[o] = br * cs - bi * sn;
+            WFM_SINCOS(ph, &sn, &cs);
+            const double br = (double)v[e].x, bi = (double)v[e].y;
+            if (f & 1u) a.Gj[obase + cell] = rho * (br * sn + bi * cs);
+            if (mod_plane) a.Gm[obase + cell] = br * cs - bi * sn;
         }
 }
 
@@ -594,8 +643,8 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     using Cfg = PipeCfg<T, N>;
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
-    int* inv_s = reinterpret_cast<int*>(tw_s + N);
-    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; inv_s[i] = a.inv_x[i]; }
+    int* invx_s = reinterpret_cast<int*>(tw_s + N);
+    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
     __shared__ unsigned s_queue[4];
     PipeQueue qu;
     const int P = a.g.nzl;
@@ -608,7 +657,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, inv_s, dep);
+                jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, dep);
             }
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
