@@ -58,7 +58,7 @@ struct wfm_model {
     DevBuf rho, phi, psi, mask, map, support;
     std::vector<uint8_t> h_map, h_zsup, h_esc;
     bool activity_dirty = true;
-    int nax = 0, nay = 0, pitch = 0;
+    int nax = 0, nay = 0, pitch = 0, ctile = 1;
     DevBuf act_x, inv_x, act_y, inv_y, cell_list;
     DevBuf s_rho, s_phi, s_psi, s_flags;          // pupil strip [N][pitch]
     bool strip_dirty = true;
@@ -147,13 +147,13 @@ Geom geom_of(const wfm_model* h) {
 
 template <typename T> int col_tile(int N) {
     switch (N) {
-        case 32: return ColCfg<T, 32>::C;
-        case 64: return ColCfg<T, 64>::C;
-        case 128: return ColCfg<T, 128>::C;
-        case 256: return ColCfg<T, 256>::C;
-        case 512: return ColCfg<T, 512>::C;
-        case 1024: return ColCfg<T, 1024>::C;
-        default: return ColCfg<T, 2048>::C;
+        case 32: return PipeCfg<T, 32>::C;
+        case 64: return PipeCfg<T, 64>::C;
+        case 128: return PipeCfg<T, 128>::C;
+        case 256: return PipeCfg<T, 256>::C;
+        case 512: return PipeCfg<T, 512>::C;
+        case 1024: return PipeCfg<T, 1024>::C;
+        default: return PipeCfg<T, 2048>::C;
     }
 }
 
@@ -200,15 +200,17 @@ int rebuild_activity(wfm_model* h) {
     h->nax = (int)ax.size(); h->nay = (int)ay.size();
     const int C = h->precision == WFM_F64 ? col_tile<double>(N) : col_tile<float>(N);
     h->pitch = (h->nax + C - 1) / C * C;
+    h->ctile = C;
     WFM_CK(h, h->act_x.ensure(sizeof(int) * ax.size()));
     WFM_CK(h, h->act_y.ensure(sizeof(int) * ay.size()));
     WFM_CK(h, h->inv_x.ensure(sizeof(int) * N));
     WFM_CK(h, h->inv_y.ensure(sizeof(int) * N));
     WFM_CK(h, h->support.ensure(npix));
     std::vector<int> cells;                       // support cells of the compact strip [N][pitch]
-    for (int ky = 0; ky < N; ++ky)
-        for (int xi = 0; xi < h->nax; ++xi)
-            if (sup[ax[xi] + N * ky]) cells.push_back(ky * h->pitch + xi);
+    for (int tile = 0; tile * C < h->nax; ++tile)          // tile-major order == memory order of the strip
+        for (int ky = 0; ky < N; ++ky)
+            for (int c = 0; c < C && tile * C + c < h->nax; ++c)
+                if (sup[ax[tile * C + c] + N * ky]) cells.push_back((tile * N + ky) * C + c);
     h->ncells = (int)cells.size();
     WFM_CK(h, h->cell_list.ensure(sizeof(int) * (cells.size() + 1)));
     WFM_CK(h, cudaStreamSynchronize(h->stream));
@@ -239,7 +241,7 @@ int pack_strip(wfm_model* h) {
     WFM_LAUNCH(kfn, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, h->stream, (double*)h->s_rho.p,
                (double*)h->s_phi.p, (double*)h->s_psi.p, (uint8_t*)h->s_flags.p, (const double*)h->rho.p,
                (const double*)h->phi.p, (const double*)h->psi.p, (const uint8_t*)h->mask.p,
-               (const uint8_t*)h->support.p, (const int*)h->act_x.p, h->N, h->nax, h->pitch);
+               (const uint8_t*)h->support.p, (const int*)h->act_x.p, h->N, h->nax, h->pitch, h->ctile);
     WFM_CK_LAUNCH(h, "k_pack_strip");
     h->strip_dirty = false;
     return WFM_OK;
@@ -357,7 +359,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         r.kinds = kinds; r.last_plane_only = a.last_plane_only;
         r.dxy = h->dxy; r.lambda_ni = h->lambda_ni; r.deltaX = h->deltaX; r.deltaY = h->deltaY;
         r.glen = h->glen();
-        r.cell_list = (const int*)h->cell_list.p; r.ncells = h->ncells;
+        r.cell_list = (const int*)h->cell_list.p; r.ncells = h->ncells; r.ctile = h->ctile;
         const int nblocks = h->ncells > 0 ? (h->ncells + WFM_RED_THREADS - 1) / WFM_RED_THREADS : 1;
         const int nchunks = (h->nzl + WFM_RED_PLANES - 1) / WFM_RED_PLANES;
         WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * nchunks * r.glen));

@@ -171,6 +171,8 @@ template <int TT> struct RowSync {
 // v   : E register values of this thread (slot convention above)
 // sm  : base of this transform's shared cells (RowLayout: private row; ColLayout: smem + column)
 // t   : thread index inside the transform, [0, T)
+// tw2 : stage-2 base twiddles in SHARED memory, tw2[d] = W_N^(R1*d), d in [0, R3) (a strided read of
+//       tw was an 8-way bank conflict: 13 % of all shared wavefronts in profiles/r01d_*)
 // tw  : W_N table in SHARED memory, tw[m] = exp(-2 pi i m / N), m in [0, N).  Only the base twiddle
 //       of each butterfly is read (one LDS per butterfly); its powers w^2..w^(R-1) are formed by
 //       complex multiplication in registers.  (ncu on the first revision showed the LSU data pipe
@@ -178,7 +180,8 @@ template <int TT> struct RowSync {
 // S   : barrier scope (CtaSync / RowSync); every thread inside that scope must call this together.  The caller
 // must place a barrier between the end of one call and the start of the next one that reuses sm.
 template <typename T, class P, class L, class S>
-WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* tw, const int sync_id) {
+WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* tw, const cx<T>* tw2,
+                          const int sync_id) {
     constexpr int E = P::E, R1 = P::R1, R2 = P::R2, R3 = P::R3, TT = P::T, S1 = P::S1;
     // stage 1: radix R1 over legs of stride S1, twiddle W_N^(b*k1), scatter to cell k1*S1 + b
 #pragma unroll
@@ -210,7 +213,7 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
             for (int r = 0; r < R2; ++r) a[r] = sm[L::at(base + r * R3)];
             Dft<T, R2>::run(a);
             sm[L::at(base)] = a[0];
-            const cx<T> w = tw[R1 * d3];
+            const cx<T> w = tw2[d3];            // compact table tw2[d] = W_N^(R1*d): adjacent lanes, adjacent cells
             cx<T> wk = w;
 #pragma unroll
             for (int k = 1; k < R2; ++k) {

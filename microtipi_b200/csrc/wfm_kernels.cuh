@@ -228,18 +228,24 @@ __global__ void k_fill_uniform(T* __restrict__ out, uint64_t seed, uint64_t firs
 // Pupil strip: rho, phi, psi and the mask/support flags gathered into the compact [N][pitch] layout
 // of the active columns, so that a column tile reads them as contiguous, independent loads.
 // ================================================================================================
+// Strip cells are TILE-MAJOR: the C columns of a pipeline column tile are adjacent, then ky, then the
+// tile: cell(ky, xi) = ((xi / C) * N + ky) * C + xi % C.  A column item then reads / writes one
+// contiguous 16*C*(lanes/C)-byte run per warp access instead of touching one cache line per row
+// (ncu, profiles/r01d_*: the 171-column pass cost as many L1 wavefronts as the 512-row pass).
+WFM_DEVI size_t strip_cell(int ky, int xi, int N, int C) { return ((size_t)(xi / C) * N + ky) * C + (xi % C); }
 struct Strip {
-    const double* rho; const double* phi; const double* psi;   // [N][pitch]
+    const double* rho; const double* phi; const double* psi;   // [pitch/C][N][C]
     const uint8_t* flags;                                        // bit 0: maskPupil, bit 1: support
 };
 __global__ void k_pack_strip(double* __restrict__ s_rho, double* __restrict__ s_phi, double* __restrict__ s_psi,
                              uint8_t* __restrict__ s_flags, const double* __restrict__ rho,
                              const double* __restrict__ phi, const double* __restrict__ psi,
                              const uint8_t* __restrict__ mask, const uint8_t* __restrict__ support,
-                             const int* __restrict__ act_x, int N, int nax, int pitch) {
+                             const int* __restrict__ act_x, int N, int nax, int pitch, int C) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= N * pitch) return;
-    const int ky = cell / pitch, xi = cell % pitch;
+    const int tile = cell / (N * C), rem = cell % (N * C);
+    const int ky = rem / C, xi = tile * C + rem % C;
     double r = 0.0, f = 0.0, p = 0.0;
     uint8_t fl = 0;
     if (xi < nax) {
@@ -298,7 +304,8 @@ template <typename T, int N> struct PipeCfg {
     static constexpr int ROWLEN = RowLayout<T, N>::LEN;
     static constexpr int COLLEN = ColL::pad_c(N - 1) + 1;
     static constexpr int CELLS = C * (ROWLEN > COLLEN ? ROWLEN : COLLEN);
-    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N) + sizeof(int) * (size_t)N;
+    static constexpr int TW2 = 16;                      // stage-2 base twiddles (R3 <= 16 entries)
+    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N + TW2) + sizeof(int) * (size_t)N;
     // resident CTAs per SM the register allocation is tuned for: 1024 threads (64 registers each)
     static constexpr int BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
     static constexpr int BY_SMEM = (int)((220 * 1024) / SMEM) < 1 ? 1 : (int)((220 * 1024) / SMEM);
@@ -421,14 +428,13 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
     const int c = threadIdx.x % C, t = threadIdx.x / C;
-    const int xi = sub * C + c;                        // xi < pitch: strip cells of padding columns are zero
     const double s = defoc_scale_dev(a.g.z0 + pl, a.g.nz_global, a.g.dz);
     double rho[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r)
-            rho[u * P::R1 + r] = __ldg(&a.st.rho[(size_t)((t + TT * u) + P::S1 * r) * a.pitch + xi]);
+            rho[u * P::R1 + r] = __ldg(&a.st.rho[((size_t)sub * N + (t + TT * u) + P::S1 * r) * C + c]);
     cx<T> v[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u) {
@@ -437,7 +443,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
             const int e = u * P::R1 + r;
             cx<T> val = mkc<T>((T)0, (T)0);
             if (rho[e] != 0.0) {
-                const size_t cell = (size_t)((t + TT * u) + P::S1 * r) * a.pitch + xi;
+                const size_t cell = ((size_t)sub * N + (t + TT * u) + P::S1 * r) * C + c;
                 const double ph = __dadd_rn(__ldg(&a.st.phi[cell]), __dmul_rn(s, __ldg(&a.st.psi[cell])));
                 double sn, cs;
                 WFM_SINCOS(ph, &sn, &cs);
@@ -446,13 +452,13 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
             v[e] = val;
         }
     }
-    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, 0);
+    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + N, 0);
     pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
-    cx<T>* dst = a.T1 + (size_t)(pl % ring) * N * a.pitch + xi;
+    cx<T>* dst = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)sub * N * C + c;
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
-        for (int r = 0; r < P::RL; ++r) __stcg(&dst[(size_t)((t + TT * u) + P::SL * r) * a.pitch], v[u * P::RL + r]);
+        for (int r = 0; r < P::RL; ++r) __stcg(&dst[(size_t)((t + TT * u) + P::SL * r) * C], v[u * P::RL + r]);
 }
 
 // B-item: ROWS_PER_ITEM rows of plane pl (each TT-thread group walks KR of them): FFT along x
@@ -467,19 +473,22 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
     constexpr int C = Cfg::C, TT = P::T, E = P::E;
     const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
     const T norm = (T)a.g.psf_norm;
-    int xis[E];
+    int xis[E];                                        // strip offset of column x (without the ky term) or -1
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
-        for (int r = 0; r < P::R1; ++r) xis[u * P::R1 + r] = invx_s[(t + TT * u) + P::S1 * r];
+        for (int r = 0; r < P::R1; ++r) {
+            const int xi = invx_s[(t + TT * u) + P::S1 * r];
+            xis[u * P::R1 + r] = xi >= 0 ? (xi / C) * N * C + xi % C : -1;
+        }
 #pragma unroll 1
     for (int kk = 0; kk < Cfg::KR; ++kk) {
         const int ky = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;     // N % ROWS_PER_ITEM == 0
-        const cx<T>* src = a.T1 + ((size_t)(pl % ring) * N + ky) * a.pitch;
+        const cx<T>* src = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)ky * C;
         cx<T> v[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = (xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
-        fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
+        fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
         const size_t base = (size_t)pl * N * N + (size_t)N * ky;
 #pragma unroll
         for (int u = 0; u < E / P::RL; ++u)
@@ -502,8 +511,10 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     using Cfg = PipeCfg<T, N>;
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
-    int* invx_s = reinterpret_cast<int*>(tw_s + N);
+    cx<T>* tw2_s = tw_s + N;
+    int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
+    if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
     __shared__ unsigned s_queue[4];
     PipeQueue qu;
     const int P = a.g.nzl;
@@ -558,11 +569,14 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
     constexpr int C = Cfg::C, TT = P::T, E = P::E;
     const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
     pipe_wait(dep);                                    // ring slot free? (rarely taken: probed at claim time)
-    int xis[E];
+    int xis[E];                                        // strip offset of column kx (without the y term) or -1
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
-        for (int r = 0; r < P::RL; ++r) xis[u * P::RL + r] = invx_s[(t + TT * u) + P::SL * r];
+        for (int r = 0; r < P::RL; ++r) {
+            const int xi = invx_s[(t + TT * u) + P::SL * r];
+            xis[u * P::RL + r] = xi >= 0 ? (xi / C) * N * C + xi % C : -1;
+        }
 #pragma unroll 1
     for (int kk = 0; kk < Cfg::KR; ++kk) {
         const int y = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;      // N % ROWS_PER_ITEM == 0
@@ -577,8 +591,8 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
                 const T qv = __ldcs(&a.q[base + x]);
                 v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
             }
-        fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, slot);
-        cx<T>* dst = a.T2 + ((size_t)(pl % ring) * N + y) * a.pitch;
+        fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
+        cx<T>* dst = a.T2 + (size_t)(pl % ring) * N * a.pitch + (size_t)y * C;
 #pragma unroll
         for (int e = 0; e < E; ++e)
             if (xis[e] >= 0) __stcg(&dst[xis[e]], v[e]);
@@ -598,14 +612,15 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
     const int c = threadIdx.x % C, t = threadIdx.x / C;
     const int xi = sub * C + c;
     const bool colvalid = xi < a.nax;
-    const cx<T>* src = a.T2 + (size_t)(pl % ring) * N * a.pitch + xi;
+    const size_t tbase = (size_t)sub * N * C + c;      // this thread's column inside the tile-major strip
+    const cx<T>* src = a.T2 + (size_t)(pl % ring) * N * a.pitch + tbase;
     cx<T> v[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r) {
             const int y = (t + TT * u) + P::S1 * r;
-            v[u * P::R1 + r] = colvalid ? __ldcg(&src[(size_t)y * a.pitch]) : mkc<T>((T)0, (T)0);
+            v[u * P::R1 + r] = colvalid ? __ldcg(&src[(size_t)y * C]) : mkc<T>((T)0, (T)0);
         }
     // the flags of this thread's output cells: independent loads, in flight during the transform
     unsigned fl = 0;
@@ -613,8 +628,8 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
         for (int r = 0; r < P::RL; ++r)
-            fl |= (unsigned)__ldg(&a.st.flags[(size_t)((t + TT * u) + P::SL * r) * a.pitch + xi]) << (2 * (u * P::RL + r));
-    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, 0);
+            fl |= (unsigned)__ldg(&a.st.flags[tbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
+    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + N, 0);
     const int iz = a.g.z0 + pl;
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
     const bool mod_plane = (a.Gm != nullptr) && (!a.last_plane_only || iz == a.g.nz_global - 1);
@@ -627,7 +642,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
             const int e = u * P::RL + r;
             const unsigned f = (fl >> (2 * e)) & want;
             if (!f) continue;
-            const size_t cell = (size_t)((t + TT * u) + P::SL * r) * a.pitch + xi;
+            const size_t cell = tbase + (size_t)((t + TT * u) + P::SL * r) * C;
             const double ph = __dadd_rn(__ldg(&a.st.phi[cell]), __dmul_rn(s, __ldg(&a.st.psi[cell])));
             const double rho = __ldg(&a.st.rho[cell]);
             double sn, cs;
@@ -643,8 +658,10 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     using Cfg = PipeCfg<T, N>;
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
-    int* invx_s = reinterpret_cast<int*>(tw_s + N);
+    cx<T>* tw2_s = tw_s + N;
+    int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
+    if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
     __shared__ unsigned s_queue[4];
     PipeQueue qu;
     const int P = a.g.nzl;
@@ -682,8 +699,9 @@ struct ReduceArgs {
     double dxy, lambda_ni, deltaX, deltaY;
     double* block_part;   // [nchunks][nblocks][glen]
     int glen;             // 3 + nphase + nmod
-    const int* cell_list; // [ncells] strip cells (ky*pitch + xi) that lie on the support
+    const int* cell_list; // [ncells] tile-major strip cells that lie on the support
     int ncells;
+    int ctile;            // columns per strip tile
 };
 
 #define WFM_RED_THREADS 256
@@ -701,8 +719,9 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     const int li = blockIdx.x * WFM_RED_THREADS + threadIdx.x;
     const bool in_range = li < a.ncells;
     const size_t cell = in_range ? (size_t)a.cell_list[li] : 0;
-    const int ky = in_range ? (int)(cell / a.pitch) : 0;
-    const int xi = in_range ? (int)(cell % a.pitch) : 0;
+    const int rem = (int)(cell % ((size_t)N * a.ctile));
+    const int ky = in_range ? rem / a.ctile : 0;
+    const int xi = in_range ? (int)(cell / ((size_t)N * a.ctile)) * a.ctile + rem % a.ctile : 0;
     const bool colvalid = in_range && xi < a.nax;
     const int kx = colvalid ? a.act_x[xi] : 0;
     const int in = kx + N * ky;
