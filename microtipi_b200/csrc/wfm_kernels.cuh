@@ -289,6 +289,14 @@ struct PipeCtl {
 #ifndef WFM_PIPE_C64
 #define WFM_PIPE_C64 4
 #endif
+// Row items double-buffer their global loads in registers: the next row's loads are issued before
+// the current row's transform, so a row group always has a row in flight (needs ~48 more registers).
+#ifndef WFM_ROW_PREFETCH
+#define WFM_ROW_PREFETCH 0
+#endif
+#ifndef WFM_PIPE_KR
+#define WFM_PIPE_KR 4
+#endif
 template <typename T, int N> struct PipeCfg {
     using P = Plan<N>;
     static constexpr int C = (N >= 256) ? (sizeof(T) == 8 ? WFM_PIPE_C64 : 8) : ColCfg<T, N>::C;   // columns per B-item == rows per A-item
@@ -297,7 +305,7 @@ template <typename T, int N> struct PipeCfg {
     static constexpr int THREADS = C * TT;
     // a row item gives every TT-thread group KR consecutive-in-time rows: the CTA-wide barrier and the
     // queue claim at the item boundary are paid once per C*KR rows
-    static constexpr int KR = ((N / C) % 4 == 0 && N >= 256) ? 4 : 1;
+    static constexpr int KR = ((N / C) % WFM_PIPE_KR == 0 && N >= 256) ? WFM_PIPE_KR : 1;
     static constexpr int ROWS_PER_ITEM = C * KR;
     static constexpr int SH = ilog2_c(P::S1);
     using ColL = ColLayout<C, SH>;
@@ -309,7 +317,11 @@ template <typename T, int N> struct PipeCfg {
     // resident CTAs per SM the register allocation is tuned for: 1024 threads (64 registers each)
     static constexpr int BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
     static constexpr int BY_SMEM = (int)((220 * 1024) / SMEM) < 1 ? 1 : (int)((220 * 1024) / SMEM);
+#ifdef WFM_PIPE_MINB
+    static constexpr int MINB = WFM_PIPE_MINB;
+#else
     static constexpr int MINB = BY_THREADS < BY_SMEM ? BY_THREADS : BY_SMEM;
+#endif
 };
 
 struct PipeItem { int type; int plane; int sub; };   // type 0 = A, 1 = B, -1 = done
@@ -481,13 +493,31 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
             const int xi = invx_s[(t + TT * u) + P::S1 * r];
             xis[u * P::R1 + r] = xi >= 0 ? (xi / C) * N * C + xi % C : -1;
         }
+#if WFM_ROW_PREFETCH
+    cx<T> nv[E];
+    {
+        const cx<T>* src0 = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)(sub * Cfg::ROWS_PER_ITEM + slot) * C;
+#pragma unroll
+        for (int e = 0; e < E; ++e) nv[e] = (xis[e] >= 0) ? __ldcg(&src0[xis[e]]) : mkc<T>((T)0, (T)0);
+    }
+#endif
 #pragma unroll 1
     for (int kk = 0; kk < Cfg::KR; ++kk) {
         const int ky = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;     // N % ROWS_PER_ITEM == 0
         const cx<T>* src = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)ky * C;
         cx<T> v[E];
+#if WFM_ROW_PREFETCH
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = nv[e];
+        if (kk + 1 < Cfg::KR) {
+            const cx<T>* nsrc = src + (size_t)C * C;
+#pragma unroll
+            for (int e = 0; e < E; ++e) nv[e] = (xis[e] >= 0) ? __ldcg(&nsrc[xis[e]]) : mkc<T>((T)0, (T)0);
+        }
+#else
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = (xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
+#endif
         fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
         const size_t base = (size_t)pl * N * N + (size_t)N * ky;
 #pragma unroll
@@ -577,11 +607,41 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
             const int xi = invx_s[(t + TT * u) + P::SL * r];
             xis[u * P::RL + r] = xi >= 0 ? (xi / C) * N * C + xi % C : -1;
         }
+#if WFM_ROW_PREFETCH
+    cx<T> nc[E];
+    T nq[E];
+    {
+        const size_t base0 = (size_t)pl * N * N + (size_t)N * (sub * Cfg::ROWS_PER_ITEM + slot);
+#pragma unroll
+        for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+            for (int r = 0; r < P::R1; ++r) {
+                const int x = (t + TT * u) + P::S1 * r;
+                nc[u * P::R1 + r] = __ldcs(&a.cpx[base0 + x]);
+                nq[u * P::R1 + r] = __ldcs(&a.q[base0 + x]);
+            }
+    }
+#endif
 #pragma unroll 1
     for (int kk = 0; kk < Cfg::KR; ++kk) {
         const int y = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;      // N % ROWS_PER_ITEM == 0
         const size_t base = (size_t)pl * N * N + (size_t)N * y;
         cx<T> v[E];
+#if WFM_ROW_PREFETCH
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = mkc<T>(nc[e].x * nq[e], nc[e].y * nq[e]);
+        if (kk + 1 < Cfg::KR) {                        // next row in flight during this row's transform
+            const size_t nb = base + (size_t)N * C;
+#pragma unroll
+            for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+                for (int r = 0; r < P::R1; ++r) {
+                    const int x = (t + TT * u) + P::S1 * r;
+                    nc[u * P::R1 + r] = __ldcs(&a.cpx[nb + x]);
+                    nq[u * P::R1 + r] = __ldcs(&a.q[nb + x]);
+                }
+        }
+#else
 #pragma unroll
         for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
@@ -591,6 +651,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
                 const T qv = __ldcs(&a.q[base + x]);
                 v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
             }
+#endif
         fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
         cx<T>* dst = a.T2 + (size_t)(pl % ring) * N * a.pitch + (size_t)y * C;
 #pragma unroll
