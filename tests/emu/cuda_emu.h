@@ -287,6 +287,10 @@ static inline double atomicAdd(double* addr, double v) {
     return o;
 }
 static inline unsigned atomicAdd(unsigned* addr, unsigned v) { return __atomic_fetch_add(addr, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicCAS(unsigned* addr, unsigned cmp, unsigned val) {
+    __atomic_compare_exchange_n(addr, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+}
 static inline int atomicAdd(int* addr, int v) { return __atomic_fetch_add(addr, v, __ATOMIC_SEQ_CST); }
 
 // polling back-off of the pipeline kernels: let the producer CTA's OS thread run
