@@ -326,42 +326,66 @@ template <typename T, int N> struct PipeCfg {
 
 struct PipeItem { int type; int plane; int sub; };   // type 0 = A, 1 = B, -1 = all work done, -2 = nothing claimed yet
 
-// Ready-first scheduling.  Items are claimed with compare-and-swap ONLY when they can run:
-//   B(p, .) when all A-items of plane p are finished (cntA[p] == nA)  -- preferred: it drains the ring;
-//   A(p, .) when the ring slot of plane p is free (p < ring or cntB[p - ring] == nB).
-// A CTA therefore never holds an item it has to wait for: no dependency stall inside an item and no
-// deadlock whatever the number of resident CTAs.  (The first revision used one interleaved queue
-// with a fixed lag; throughput kept rising with the lag up to a 72 MB ring, profiles/r01f_*.)
-WFM_DEVI bool pipe_try_claim(const PipeCtl& c, int P, PipeItem& out) {
+// Ready-first scheduling with wait-free claims.  Thread 0 peeks at the heads of the two queues:
+//   B(p, .) is runnable when all A-items of plane p are finished (cntA[p] == nA) -- preferred, it
+//           drains the ring;
+//   A(p, .) is runnable when the ring slot of plane p is free (p < ring or cntB[p - ring] == nB);
+// and claims from the chosen queue with atomicAdd (a compare-and-swap claim serialises: one success
+// per L2 round trip with ~600 CTAs racing -- measured 40x slower).  Between the peek and the add
+// another CTA may have taken the peeked item, so the item obtained can belong to the next plane and
+// not be runnable yet; `ready` is then false and the item waits (pipe_wait) before touching the
+// ring.  Deadlock freedom: dependencies point to strictly lower rank (rank A(p) = 2p, B(p) = 2p+1,
+// A(p) <- B(p-ring), B(p) <- A(p)); the first adder after a peek always obtains the peeked, runnable
+// item, so at every plane boundary at least one CTA is not stuck and drains the lower ranks.
+// (The first revision used one interleaved queue with a fixed lag; throughput kept rising with the
+// lag up to a 72 MB ring, profiles/r01f_*.)
+WFM_DEVI bool pipe_b_ready(const PipeCtl& c, int plane) {
+    return !(c.roles & 1) || *(volatile unsigned*)&c.cntA[plane] >= (unsigned)c.nA;
+}
+WFM_DEVI bool pipe_a_ready(const PipeCtl& c, int plane) {
+    return plane < c.ring || !(c.roles & 2) || *(volatile unsigned*)&c.cntB[plane - c.ring] >= (unsigned)c.nB;
+}
+WFM_DEVI bool pipe_try_claim(const PipeCtl& c, int P, PipeItem& out, bool& ready) {
     const unsigned totA = (unsigned)P * c.nA, totB = (unsigned)P * c.nB;
-    for (int attempt = 0; attempt < 4; ++attempt) {
-        const unsigned ib = *(volatile unsigned*)c.qB;
-        const unsigned ia = *(volatile unsigned*)c.qA;
-        if (ib >= totB && ia >= totA) { out.type = -1; out.plane = 0; out.sub = 0; return true; }
-        if (ib < totB) {
-            const int pb = (int)(ib / c.nB);
-            if (*(volatile unsigned*)&c.cntA[pb] >= (unsigned)c.nA) {
-                if (atomicCAS(c.qB, ib, ib + 1u) == ib) {
-                    __threadfence();                       // acquire: the A-items' ring stores are visible
-                    out.type = 1; out.plane = pb; out.sub = (int)(ib % c.nB);
-                    return true;
-                }
-                continue;
-            }
-        }
-        if (ia < totA) {
-            const int pa = (int)(ia / c.nA);
-            if (pa < c.ring || *(volatile unsigned*)&c.cntB[pa - c.ring] >= (unsigned)c.nB) {
-                if (atomicCAS(c.qA, ia, ia + 1u) == ia) {
-                    __threadfence();                       // acquire: the slot's previous readers are done
-                    out.type = 0; out.plane = pa; out.sub = (int)(ia % c.nA);
-                    return true;
-                }
-                continue;
-            }
+    const unsigned ib = *(volatile unsigned*)c.qB;
+    const unsigned ia = *(volatile unsigned*)c.qA;
+    ready = true;
+    if (ib < totB && pipe_b_ready(c, (int)(ib / c.nB))) {
+        const unsigned idx = atomicAdd(c.qB, 1u);
+        if (idx < totB) {
+            out.type = 1; out.plane = (int)(idx / c.nB); out.sub = (int)(idx % c.nB);
+            ready = pipe_b_ready(c, out.plane);
+            if (ready) __threadfence();                    // acquire: the A-items' ring stores are visible
+            return true;
         }
     }
+    if (ia < totA && pipe_a_ready(c, (int)(ia / c.nA))) {
+        const unsigned idx = atomicAdd(c.qA, 1u);
+        if (idx < totA) {
+            out.type = 0; out.plane = (int)(idx / c.nA); out.sub = (int)(idx % c.nA);
+            ready = pipe_a_ready(c, out.plane);
+            if (ready) __threadfence();                    // acquire: the slot's previous readers are done
+            return true;
+        }
+    }
+    if (*(volatile unsigned*)c.qB >= totB && *(volatile unsigned*)c.qA >= totA) {
+        out.type = -1; out.plane = 0; out.sub = 0;
+        return true;
+    }
     return false;
+}
+
+// thread 0 polls a counter (L2, volatile) until it reaches `target`; everybody then passes a barrier
+WFM_DEVI void pipe_wait(const unsigned* cnt, unsigned target, unsigned* err) {
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while (*(volatile const unsigned*)cnt < target) {
+            if (++spins > (1u << 22)) { *(volatile unsigned*)err = 1u; break; }   // ~seconds: never a hang
+            WFM_SPIN_PAUSE();
+        }
+        __threadfence();
+    }
+    __syncthreads();
 }
 
 // CTA barrier (all stores of the item issued), then thread 0 fences at GPU scope and publishes --
@@ -375,35 +399,40 @@ WFM_DEVI void pipe_signal(unsigned* cnt) {
 // processed (the claim latency is off the critical path); if nothing is runnable at that moment the
 // CTA claims at the top of its next iteration instead, polling with back-off.
 struct PipeQueue {
-    int* s;     // shared: two slots of {type, plane, sub}
+    int* s;     // shared: two slots of {type, plane, sub, ready}
     int cur;
-    WFM_DEVI void put(int slot, const PipeItem& it) { s[3 * slot] = it.type; s[3 * slot + 1] = it.plane; s[3 * slot + 2] = it.sub; }
+    WFM_DEVI void put(int slot, const PipeItem& it, bool ready) {
+        s[4 * slot] = it.type; s[4 * slot + 1] = it.plane; s[4 * slot + 2] = it.sub; s[4 * slot + 3] = ready ? 1 : 0;
+    }
     WFM_DEVI void claim_blocking(int slot, const PipeCtl& c, int P) {
         PipeItem it;
+        bool ready = true;
         unsigned spins = 0;
-        while (!pipe_try_claim(c, P, it)) {
+        while (!pipe_try_claim(c, P, it, ready)) {
             if (++spins > (1u << 22)) { *(volatile unsigned*)c.err = 1u; it.type = -1; it.plane = 0; it.sub = 0; break; }   // ~seconds: never a hang
             WFM_SPIN_PAUSE();
         }
-        put(slot, it);
+        put(slot, it, ready);
     }
-    WFM_DEVI void init(int* smem6, const PipeCtl& c, int P) {
-        s = smem6; cur = 0;
+    WFM_DEVI void init(int* smem8, const PipeCtl& c, int P) {
+        s = smem8; cur = 0;
         if (threadIdx.x == 0) claim_blocking(0, c, P);
         __syncthreads();
     }
-    WFM_DEVI PipeItem take(const PipeCtl& c, int P) {
-        if (s[3 * cur] == -2) {                           // the early claim found nothing runnable
+    WFM_DEVI PipeItem take(const PipeCtl& c, int P, bool& ready) {
+        if (s[4 * cur] == -2) {                           // the early claim found nothing runnable
             __syncthreads();
             if (threadIdx.x == 0) claim_blocking(cur, c, P);
             __syncthreads();
         }
         PipeItem it;
-        it.type = s[3 * cur]; it.plane = s[3 * cur + 1]; it.sub = s[3 * cur + 2];
+        it.type = s[4 * cur]; it.plane = s[4 * cur + 1]; it.sub = s[4 * cur + 2];
+        ready = s[4 * cur + 3] != 0;
         if (threadIdx.x == 0 && it.type >= 0) {
             PipeItem nx;
-            if (!pipe_try_claim(c, P, nx)) { nx.type = -2; nx.plane = 0; nx.sub = 0; }
-            put(cur ^ 1, nx);
+            bool nr = true;
+            if (!pipe_try_claim(c, P, nx, nr)) { nx.type = -2; nx.plane = 0; nx.sub = 0; }
+            put(cur ^ 1, nx, nr);
         }
         cur ^= 1;
         return it;
@@ -542,17 +571,20 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
-    __shared__ int s_queue[6];
+    __shared__ int s_queue[8];
     PipeQueue qu;
     const int P = a.g.nzl;
     qu.init(s_queue, ctl, P);
     for (;;) {
-        const PipeItem it = qu.take(ctl, P);
+        bool ready;
+        const PipeItem it = qu.take(ctl, P, ready);
         if (it.type < 0) break;
         if (it.type == 0) {
+            if (!ready) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
             if (ctl.roles & 1) psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
+            if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
             if (ctl.roles & 2) psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s);
             pipe_signal(&ctl.cntB[it.plane]);
         }
@@ -711,17 +743,20 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
-    __shared__ int s_queue[6];
+    __shared__ int s_queue[8];
     PipeQueue qu;
     const int P = a.g.nzl;
     qu.init(s_queue, ctl, P);
     for (;;) {
-        const PipeItem it = qu.take(ctl, P);
+        bool ready;
+        const PipeItem it = qu.take(ctl, P, ready);
         if (it.type < 0) break;
         if (it.type == 0) {
+            if (!ready) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
             if (ctl.roles & 1) jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s);
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
+            if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
             if (ctl.roles & 2) jac_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
             pipe_signal(&ctl.cntB[it.plane]);
         }
