@@ -256,33 +256,37 @@ Strip strip_of(const wfm_model* h) {
 // ---- pipeline control ---------------------------------------------------------------------------------
 // Ring / lag sizing: LAG ~ 1.5x the planes whose A-items are in flight at once, RING = 2*LAG + 2, with the
 // ring kept within ~48 MB so that it stays L2-resident (126 MB L2 shared with the streaming traffic).
-struct PipePlan { int ring, nA, nB, grid; };
+struct PipePlan { int ring, lag, nA, nB, grid; };
 
-// Ring sizing: with ready-first scheduling the ring only has to cover the A-items in flight; it is
-// kept within ~48 MB so that it stays L2-resident (126 MB L2 shared with the streaming traffic).
 PipePlan plan_pipeline(const wfm_model* h, int nA, int nB, size_t plane_bytes, int ctas_per_sm) {
     PipePlan p;
     p.nA = nA; p.nB = nB;
     const int nctas = h->num_sms * ctas_per_sm;
-    size_t budget = 48u << 20;
+    // Every CTA holds two claimed items (current + prefetched), so ~2*nctas consecutive queue entries are in
+    // flight; B(p) must be queued at least that far behind A(p) or its CTA stalls on cntA[p].  Measured at
+    // 512^2 fp64: ms/step 1.83, 1.37, 1.12, 1.01, 0.97, 0.95, 0.96 for lag 5, 8, 12, 16, 20, 24, 32.
+    int lag = (4 * nctas + (nA + nB) - 1) / (nA + nB) + 8;
+    if (lag < 2) lag = 2;
+    size_t budget = 80u << 20;                 // ring = 2*lag+2 planes, kept L2-resident (126 MB L2)
     if (const char* e = getenv("WFM_PIPE_RING_MB")) { int v = atoi(e); if (v > 0) budget = (size_t)v << 20; }
-    int ring = (int)(budget / plane_bytes);
-    if (const char* e = getenv("WFM_PIPE_RING")) { int v = atoi(e); if (v >= 1) ring = v; }
-    if (ring < 2) ring = 2;
+    if (const char* e = getenv("WFM_PIPE_LAG")) { int v = atoi(e); if (v >= 1) lag = v; }
+    while (lag > 2 && (size_t)(2 * lag + 2) * plane_bytes > budget) --lag;
+    int ring = 2 * lag + 2;
     if (ring > h->nzl) ring = h->nzl;
-    p.ring = ring;
+    if (lag >= ring) lag = ring > 1 ? ring - 1 : 1;
+    p.ring = ring; p.lag = lag;
     const long items = (long)h->nzl * (nA + nB);
     p.grid = (int)(items < nctas ? items : nctas);
     return p;
 }
 
 int prepare_ctl(wfm_model* h, const PipePlan& pp, PipeCtl& ctl, int roles) {
-    const size_t words = 4 + 2 * (size_t)h->nzl;
+    const size_t words = 2 + 2 * (size_t)h->nzl;
     WFM_CK(h, h->ctl.ensure(sizeof(unsigned) * words));
     WFM_CK(h, cudaMemsetAsync(h->ctl.p, 0, sizeof(unsigned) * words, h->stream));
     unsigned* base = (unsigned*)h->ctl.p;
-    ctl.qA = base; ctl.err = base + 1; ctl.qB = base + 2; ctl.cntA = base + 4; ctl.cntB = base + 4 + h->nzl;
-    ctl.ring = pp.ring; ctl.nA = pp.nA; ctl.nB = pp.nB; ctl.roles = roles;
+    ctl.queue = base; ctl.err = base + 1; ctl.cntA = base + 2; ctl.cntB = base + 2 + h->nzl;
+    ctl.ring = pp.ring; ctl.lag = pp.lag; ctl.nA = pp.nA; ctl.nB = pp.nB; ctl.roles = roles;
     return WFM_OK;
 }
 

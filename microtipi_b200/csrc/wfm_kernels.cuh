@@ -274,12 +274,12 @@ __global__ void k_pack_strip(double* __restrict__ s_rho, double* __restrict__ s_
 // ring (RING planes) that stays L2-resident instead of making an HBM round trip.
 // ================================================================================================
 struct PipeCtl {
-    unsigned* qA;      // [1] next A item (plane-major: item = plane*nA + sub)
-    unsigned* qB;      // [1] next B item
-    unsigned* err;     // [1] set when the scheduler gives up waiting (never in a correct run)
-    unsigned* cntA;    // [nzl] finished A-items per plane
-    unsigned* cntB;    // [nzl] finished B-items per plane
+    unsigned* queue;   // [1] next item
+    unsigned* err;     // [1] set when a dependency wait times out
+    unsigned* cntA;    // [nzl] published A-items per plane
+    unsigned* cntB;    // [nzl] finished  B-items per plane
     int ring;          // planes in the intermediate ring
+    int lag;           // B(p - lag) is queued next to A(p)
     int nA, nB;        // items per plane
     int roles;         // bit 0: run A items, bit 1: run B items (both set in production)
 };
@@ -324,55 +324,27 @@ template <typename T, int N> struct PipeCfg {
 #endif
 };
 
-struct PipeItem { int type; int plane; int sub; };   // type 0 = A, 1 = B, -1 = all work done, -2 = nothing claimed yet
+struct PipeItem { int type; int plane; int sub; };   // type 0 = A, 1 = B, -1 = done
 
-// Ready-first scheduling with wait-free claims.  Thread 0 peeks at the heads of the two queues:
-//   B(p, .) is runnable when all A-items of plane p are finished (cntA[p] == nA) -- preferred, it
-//           drains the ring;
-//   A(p, .) is runnable when the ring slot of plane p is free (p < ring or cntB[p - ring] == nB);
-// and claims from the chosen queue with atomicAdd (a compare-and-swap claim serialises: one success
-// per L2 round trip with ~600 CTAs racing -- measured 40x slower).  Between the peek and the add
-// another CTA may have taken the peeked item, so the item obtained can belong to the next plane and
-// not be runnable yet; `ready` is then false and the item waits (pipe_wait) before touching the
-// ring.  Deadlock freedom: dependencies point to strictly lower rank (rank A(p) = 2p, B(p) = 2p+1,
-// A(p) <- B(p-ring), B(p) <- A(p)); the first adder after a peek always obtains the peeked, runnable
-// item, so at every plane boundary at least one CTA is not stuck and drains the lower ranks.
-// (The first revision used one interleaved queue with a fixed lag; throughput kept rising with the
-// lag up to a 72 MB ring, profiles/r01f_*.)
-WFM_DEVI bool pipe_b_ready(const PipeCtl& c, int plane) {
-    return !(c.roles & 1) || *(volatile unsigned*)&c.cntA[plane] >= (unsigned)c.nA;
-}
-WFM_DEVI bool pipe_a_ready(const PipeCtl& c, int plane) {
-    return plane < c.ring || !(c.roles & 2) || *(volatile unsigned*)&c.cntB[plane - c.ring] >= (unsigned)c.nB;
-}
-WFM_DEVI bool pipe_try_claim(const PipeCtl& c, int P, PipeItem& out, bool& ready) {
-    const unsigned totA = (unsigned)P * c.nA, totB = (unsigned)P * c.nB;
-    const unsigned ib = *(volatile unsigned*)c.qB;
-    const unsigned ia = *(volatile unsigned*)c.qA;
-    ready = true;
-    if (ib < totB && pipe_b_ready(c, (int)(ib / c.nB))) {
-        const unsigned idx = atomicAdd(c.qB, 1u);
-        if (idx < totB) {
-            out.type = 1; out.plane = (int)(idx / c.nB); out.sub = (int)(idx % c.nB);
-            ready = pipe_b_ready(c, out.plane);
-            if (ready) __threadfence();                    // acquire: the A-items' ring stores are visible
-            return true;
-        }
+WFM_DEVI PipeItem pipe_decode(unsigned idx, int P, const PipeCtl& c) {
+    PipeItem it;
+    const int lag = c.lag < P ? c.lag : P;
+    const unsigned headA = (unsigned)lag * c.nA;
+    const unsigned per = (unsigned)(c.nA + c.nB);
+    const unsigned mid = (unsigned)(P - lag) * per;
+    if (idx < headA) { it.type = 0; it.plane = (int)(idx / c.nA); it.sub = (int)(idx % c.nA); return it; }
+    unsigned r = idx - headA;
+    if (r < mid) {
+        const int ph = (int)(r / per);
+        const int w = (int)(r % per);
+        if (w < c.nB) { it.type = 1; it.plane = ph; it.sub = w; }
+        else { it.type = 0; it.plane = lag + ph; it.sub = w - c.nB; }
+        return it;
     }
-    if (ia < totA && pipe_a_ready(c, (int)(ia / c.nA))) {
-        const unsigned idx = atomicAdd(c.qA, 1u);
-        if (idx < totA) {
-            out.type = 0; out.plane = (int)(idx / c.nA); out.sub = (int)(idx % c.nA);
-            ready = pipe_a_ready(c, out.plane);
-            if (ready) __threadfence();                    // acquire: the slot's previous readers are done
-            return true;
-        }
-    }
-    if (*(volatile unsigned*)c.qB >= totB && *(volatile unsigned*)c.qA >= totA) {
-        out.type = -1; out.plane = 0; out.sub = 0;
-        return true;
-    }
-    return false;
+    r -= mid;
+    if (r < (unsigned)lag * c.nB) { it.type = 1; it.plane = (P - lag) + (int)(r / c.nB); it.sub = (int)(r % c.nB); return it; }
+    it.type = -1; it.plane = 0; it.sub = 0;
+    return it;
 }
 
 // thread 0 polls a counter (L2, volatile) until it reaches `target`; everybody then passes a barrier
@@ -387,7 +359,6 @@ WFM_DEVI void pipe_wait(const unsigned* cnt, unsigned target, unsigned* err) {
     }
     __syncthreads();
 }
-
 // CTA barrier (all stores of the item issued), then thread 0 fences at GPU scope and publishes --
 // the arrive half of a cooperative-groups grid barrier.
 WFM_DEVI void pipe_signal(unsigned* cnt) {
@@ -395,49 +366,50 @@ WFM_DEVI void pipe_signal(unsigned* cnt) {
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(cnt, 1u); }
 }
 
-// Work-item queue of a persistent CTA.  Thread 0 tries to claim item i+1 while item i is being
-// processed (the claim latency is off the critical path); if nothing is runnable at that moment the
-// CTA claims at the top of its next iteration instead, polling with back-off.
+// Work-item queue of a persistent CTA.  Thread 0 claims item i+1 while item i is being processed
+// and probes that item's dependency counter once (acquire): in steady state the dependency is
+// already met, so neither the atomic nor the L2 poll is on the critical path.  The claim becomes
+// visible to the CTA through the barriers every item executes.
 struct PipeQueue {
-    int* s;     // shared: two slots of {type, plane, sub, ready}
+    unsigned* s;   // shared: s[0..1] item index, s[2..3] dependency already satisfied
     int cur;
-    WFM_DEVI void put(int slot, const PipeItem& it, bool ready) {
-        s[4 * slot] = it.type; s[4 * slot + 1] = it.plane; s[4 * slot + 2] = it.sub; s[4 * slot + 3] = ready ? 1 : 0;
-    }
-    WFM_DEVI void claim_blocking(int slot, const PipeCtl& c, int P) {
-        PipeItem it;
-        bool ready = true;
-        unsigned spins = 0;
-        while (!pipe_try_claim(c, P, it, ready)) {
-            if (++spins > (1u << 22)) { *(volatile unsigned*)c.err = 1u; it.type = -1; it.plane = 0; it.sub = 0; break; }   // ~seconds: never a hang
-            WFM_SPIN_PAUSE();
+    WFM_DEVI static bool probe(const PipeItem& it, const PipeCtl& c) {
+        const unsigned* cnt; unsigned target;
+        if (it.type == 0) {
+            if (it.plane < c.ring || !(c.roles & 2)) return true;
+            cnt = &c.cntB[it.plane - c.ring]; target = (unsigned)c.nB;
+        } else {
+            if (!(c.roles & 1)) return true;
+            cnt = &c.cntA[it.plane]; target = (unsigned)c.nA;
         }
-        put(slot, it, ready);
+        const bool ok = *(volatile const unsigned*)cnt >= target;
+        if (ok) __threadfence();
+        return ok;
     }
-    WFM_DEVI void init(int* smem8, const PipeCtl& c, int P) {
-        s = smem8; cur = 0;
-        if (threadIdx.x == 0) claim_blocking(0, c, P);
+    WFM_DEVI void claim(int slot, const PipeCtl& c, int P) {
+        const unsigned idx = atomicAdd(c.queue, 1u);
+        const PipeItem it = pipe_decode(idx, P, c);
+        s[slot] = idx;
+        s[2 + slot] = (it.type < 0 || probe(it, c)) ? 1u : 0u;
+    }
+    WFM_DEVI void init(unsigned* smem4, const PipeCtl& c, int P) {
+        s = smem4; cur = 0;
+        if (threadIdx.x == 0) claim(0, c, P);
         __syncthreads();
     }
+    // returns the current item; `ready` tells whether its dependency was already observed as met
     WFM_DEVI PipeItem take(const PipeCtl& c, int P, bool& ready) {
-        if (s[4 * cur] == -2) {                           // the early claim found nothing runnable
-            __syncthreads();
-            if (threadIdx.x == 0) claim_blocking(cur, c, P);
-            __syncthreads();
-        }
-        PipeItem it;
-        it.type = s[4 * cur]; it.plane = s[4 * cur + 1]; it.sub = s[4 * cur + 2];
-        ready = s[4 * cur + 3] != 0;
-        if (threadIdx.x == 0 && it.type >= 0) {
-            PipeItem nx;
-            bool nr = true;
-            if (!pipe_try_claim(c, P, nx, nr)) { nx.type = -2; nx.plane = 0; nx.sub = 0; }
-            put(cur ^ 1, nx, nr);
-        }
+        const PipeItem it = pipe_decode(s[cur], P, c);
+        ready = s[2 + cur] != 0u;
+        if (threadIdx.x == 0 && it.type >= 0) claim(cur ^ 1, c, P);
         cur ^= 1;
         return it;
     }
 };
+
+// What an item must wait for before it may touch the ring slot (NULL counter: nothing).
+struct PipeDep { const unsigned* cnt; unsigned target; unsigned* err; };
+WFM_DEVI void pipe_wait(const PipeDep& d) { if (d.cnt) pipe_wait(d.cnt, d.target, d.err); }
 
 // ================================================================================================
 // computePsf()  WFM:280-350 (fp32: 209-278)
@@ -462,7 +434,8 @@ template <typename T> struct PsfArgs {
 // A-item: active columns xi0 .. xi0+C-1 of plane pl.  A = rho*exp(i(phi + defoc_scale*psi)) is
 // synthesised in the load (WFM:311-316; sincos only where rho != 0, quirk Q6), then FFT along y.
 template <typename T, int N>
-WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s) {
+WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+                            const PipeDep& dep) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
@@ -492,6 +465,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
         }
     }
     fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + N, 0);
+    pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
     cx<T>* dst = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)sub * N * C + c;
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
@@ -571,7 +545,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
-    __shared__ int s_queue[8];
+    __shared__ unsigned s_queue[4];
     PipeQueue qu;
     const int P = a.g.nzl;
     qu.init(s_queue, ctl, P);
@@ -580,12 +554,17 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
         const PipeItem it = qu.take(ctl, P, ready);
         if (it.type < 0) break;
         if (it.type == 0) {
-            if (!ready) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
-            if (ctl.roles & 1) psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+            if (ctl.roles & 1) {
+                PipeDep dep;
+                dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
+                psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, dep);
+            }
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
-            if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-            if (ctl.roles & 2) psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s);
+            if (ctl.roles & 2) {
+                if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
+                psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s);
+            }
             pipe_signal(&ctl.cntB[it.plane]);
         }
     }
@@ -613,12 +592,13 @@ template <typename T> struct JacArgs {
 // fused into the streaming load (WFM:907-914), FFT along x, keep the active kx only.
 template <typename T, int N>
 WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
-                            const int* invx_s) {
+                            const int* invx_s, const PipeDep& dep) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
     using Cfg = PipeCfg<T, N>;
     constexpr int C = Cfg::C, TT = P::T, E = P::E;
     const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
+    pipe_wait(dep);                                    // ring slot free? (rarely taken: probed at claim time)
     int xis[E];                                        // strip offset of column kx (without the y term) or -1
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
@@ -743,7 +723,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
-    __shared__ int s_queue[8];
+    __shared__ unsigned s_queue[4];
     PipeQueue qu;
     const int P = a.g.nzl;
     qu.init(s_queue, ctl, P);
@@ -752,12 +732,17 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
         const PipeItem it = qu.take(ctl, P, ready);
         if (it.type < 0) break;
         if (it.type == 0) {
-            if (!ready) pipe_wait(&ctl.cntB[it.plane - ctl.ring], ctl.nB, ctl.err);
-            if (ctl.roles & 1) jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s);
+            if (ctl.roles & 1) {
+                PipeDep dep;
+                dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
+                jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, dep);
+            }
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
-            if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-            if (ctl.roles & 2) jac_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+            if (ctl.roles & 2) {
+                if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
+                jac_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+            }
             pipe_signal(&ctl.cntB[it.plane]);
         }
     }
