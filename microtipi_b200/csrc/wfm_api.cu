@@ -59,7 +59,8 @@ struct wfm_model {
     std::vector<uint8_t> h_map, h_zsup, h_esc;
     bool activity_dirty = true;
     int nax = 0, nay = 0, pitch = 0, ctile = 1;
-    DevBuf act_x, inv_x, act_y, inv_y, cell_list;
+    DevBuf act_x, inv_x, act_y, inv_y, cell_list, in_list, Zs;
+    bool basis_packed = false;
     DevBuf s_rho, s_phi, s_psi, s_flags;          // pupil strip [N][pitch]
     bool strip_dirty = true;
     int ncells = 0;
@@ -72,6 +73,7 @@ struct wfm_model {
     DevBuf scratch, Gj, Gm, ctl, block_part, grad, qdev;
     int num_sms = 148;
     unsigned long pipe_checks = 0;
+    bool ctl_dirty = true;
     int modulus_mode = WFM_MODULUS_INTENDED;
     std::string err;
     // optional per-kernel CUDA-event timing (wfm_set_profiling)
@@ -206,16 +208,20 @@ int rebuild_activity(wfm_model* h) {
     WFM_CK(h, h->inv_x.ensure(sizeof(int) * N));
     WFM_CK(h, h->inv_y.ensure(sizeof(int) * N));
     WFM_CK(h, h->support.ensure(npix));
-    std::vector<int> cells;                       // support cells of the compact strip [N][pitch]
+    std::vector<int> cells, ins;                  // support cells of the compact strip and their pixel indices
     for (int tile = 0; tile * C < h->nax; ++tile)          // tile-major order == memory order of the strip
         for (int ky = 0; ky < N; ++ky)
             for (int c = 0; c < C && tile * C + c < h->nax; ++c)
-                if (sup[ax[tile * C + c] + N * ky]) cells.push_back((tile * N + ky) * C + c);
+                if (sup[ax[tile * C + c] + N * ky]) { cells.push_back((tile * N + ky) * C + c); ins.push_back(ax[tile * C + c] + N * ky); }
     h->ncells = (int)cells.size();
     WFM_CK(h, h->cell_list.ensure(sizeof(int) * (cells.size() + 1)));
+    WFM_CK(h, h->in_list.ensure(sizeof(int) * (cells.size() + 1)));
+    h->basis_packed = false;
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     if (!cells.empty())
         WFM_CK(h, cudaMemcpy(h->cell_list.p, cells.data(), sizeof(int) * cells.size(), cudaMemcpyHostToDevice));
+    if (!ins.empty())
+        WFM_CK(h, cudaMemcpy(h->in_list.p, ins.data(), sizeof(int) * ins.size(), cudaMemcpyHostToDevice));
     WFM_CK(h, cudaMemcpy(h->act_x.p, ax.data(), sizeof(int) * ax.size(), cudaMemcpyHostToDevice));
     WFM_CK(h, cudaMemcpy(h->act_y.p, ay.data(), sizeof(int) * ay.size(), cudaMemcpyHostToDevice));
     WFM_CK(h, cudaMemcpy(h->inv_x.p, ix.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
@@ -281,11 +287,14 @@ PipePlan plan_pipeline(const wfm_model* h, int nA, int nB, size_t plane_bytes, i
 }
 
 int prepare_ctl(wfm_model* h, const PipePlan& pp, PipeCtl& ctl, int roles) {
-    const size_t words = 2 + 2 * (size_t)h->nzl;
-    WFM_CK(h, h->ctl.ensure(sizeof(unsigned) * words));
-    WFM_CK(h, cudaMemsetAsync(h->ctl.p, 0, sizeof(unsigned) * words, h->stream));
+    const size_t words = 4 + 2 * (size_t)h->nzl;
+    if (h->ctl.bytes < sizeof(unsigned) * words || h->ctl_dirty) {      // the kernels leave the block clean
+        WFM_CK(h, h->ctl.ensure(sizeof(unsigned) * words));
+        WFM_CK(h, cudaMemsetAsync(h->ctl.p, 0, sizeof(unsigned) * words, h->stream));
+        h->ctl_dirty = false;
+    }
     unsigned* base = (unsigned*)h->ctl.p;
-    ctl.queue = base; ctl.err = base + 1; ctl.cntA = base + 2; ctl.cntB = base + 2 + h->nzl;
+    ctl.queue = base; ctl.err = base + 1; ctl.done = base + 2; ctl.cntA = base + 4; ctl.cntB = base + 4 + h->nzl;
     ctl.ring = pp.ring; ctl.lag = pp.lag; ctl.nA = pp.nA; ctl.nB = pp.nB; ctl.roles = roles;
     return WFM_OK;
 }
@@ -355,15 +364,22 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     }
     {
         KernelSpan span(h, WFM_K_JAC_REDUCE);
+        if (!h->basis_packed && h->nzern > 0 && h->ncells > 0) {
+            WFM_CK(h, h->Zs.ensure(sizeof(double) * (size_t)h->nzern * h->ncells));
+            auto kpk = &k_pack_basis;
+            WFM_LAUNCH(kpk, dim3((h->ncells + 255) / 256), dim3(256), 0, h->stream, (double*)h->Zs.p,
+                       (const double*)h->Z.p, (const int*)h->in_list.p, h->ncells, h->nzern, h->npix());
+            WFM_CK_LAUNCH(h, "k_pack_basis");
+            h->basis_packed = true;
+        }
         ReduceArgs r;
-        r.g = a.g; r.Gj = a.Gj; r.Gm = a.Gm; r.pitch = h->pitch; r.nax = h->nax;
-        r.act_x = (const int*)h->act_x.p; r.Z = (const double*)h->Z.p; r.psi = (const double*)h->psi.p;
-        r.mask = (const uint8_t*)h->mask.p; r.support = (const uint8_t*)h->support.p;
+        r.g = a.g; r.Gj = a.Gj; r.Gm = a.Gm; r.pitch = h->pitch;
+        r.Zs = (const double*)h->Zs.p; r.psi = (const double*)h->psi.p; r.flags = (const uint8_t*)h->s_flags.p;
+        r.cell_list = (const int*)h->cell_list.p; r.in_list = (const int*)h->in_list.p; r.ncells = h->ncells;
         r.nphase = h->nphase; r.nmod = h->nmod; r.phase_off = h->radial ? 1 : 3;
         r.kinds = kinds; r.last_plane_only = a.last_plane_only;
         r.dxy = h->dxy; r.lambda_ni = h->lambda_ni; r.deltaX = h->deltaX; r.deltaY = h->deltaY;
         r.glen = h->glen();
-        r.cell_list = (const int*)h->cell_list.p; r.ncells = h->ncells; r.ctile = h->ctile;
         const int nblocks = h->ncells > 0 ? (h->ncells + WFM_RED_THREADS - 1) / WFM_RED_THREADS : 1;
         const int nchunks = (h->nzl + WFM_RED_PLANES - 1) / WFM_RED_PLANES;
         WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * nchunks * r.glen));
@@ -433,7 +449,7 @@ int check_pipeline(wfm_model* h) {
     h->pipe_checks = 0;
     unsigned flag = 0;
     WFM_CK(h, cudaMemcpy(&flag, (unsigned*)h->ctl.p + 1, sizeof(unsigned), cudaMemcpyDeviceToHost));
-    if (flag) return h->fail(WFM_ERR_INTERNAL, "pipeline dependency wait timed out");
+    if (flag) { h->ctl_dirty = true; return h->fail(WFM_ERR_INTERNAL, "pipeline dependency wait timed out"); }
     return WFM_OK;
 }                 // WFM:1970-1974
 
@@ -498,7 +514,7 @@ int wfm_destroy(wfm_model* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->Z, &h->rho, &h->phi, &h->psi, &h->mask, &h->map, &h->support, &h->act_x, &h->inv_x,
-                      &h->act_y, &h->inv_y, &h->cell_list, &h->s_rho, &h->s_phi, &h->s_psi, &h->s_flags, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gj, &h->Gm, &h->ctl, &h->block_part,
+                      &h->act_y, &h->inv_y, &h->cell_list, &h->in_list, &h->Zs, &h->s_rho, &h->s_phi, &h->s_psi, &h->s_flags, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gj, &h->Gm, &h->ctl, &h->block_part,
                       &h->grad, &h->qdev})
         b->release();
     drain_spans(h);
@@ -550,7 +566,7 @@ int wfm_set_basis(wfm_model* h, const double* Z, int nzern, int radial) {
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     WFM_CK(h, h->Z.ensure(8 * npix * nzern));
     WFM_CK(h, cudaMemcpy(h->Z.p, Z, 8 * npix * nzern, cudaMemcpyHostToDevice));
-    h->nzern = nzern; h->radial = radial ? 1 : 0;
+    h->nzern = nzern; h->radial = radial ? 1 : 0; h->basis_packed = false;
     h->h_zsup.assign(npix, 0);
     for (int k = 0; k < nzern; ++k)
         for (size_t i = 0; i < npix; ++i)
@@ -632,7 +648,7 @@ int wfm_build_basis(wfm_model* h, int nzern, int radial) {
     WFM_CK_LAUNCH(h, "zernike basis kernels");
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     dmodes.release(); partial.release();
-    h->nzern = nzern; h->radial = radial ? 1 : 0;
+    h->nzern = nzern; h->radial = radial ? 1 : 0; h->basis_packed = false;
     h->h_zsup.assign(npix, 0);
     for (int y = 0; y < N; ++y)
         for (int x = 0; x < N; ++x) {

@@ -276,6 +276,7 @@ __global__ void k_pack_strip(double* __restrict__ s_rho, double* __restrict__ s_
 struct PipeCtl {
     unsigned* queue;   // [1] next item
     unsigned* err;     // [1] set when a dependency wait times out
+    unsigned* done;    // [1] CTAs that have left the work loop (the last one clears the counters)
     unsigned* cntA;    // [nzl] published A-items per plane
     unsigned* cntB;    // [nzl] finished  B-items per plane
     int ring;          // planes in the intermediate ring
@@ -364,6 +365,21 @@ WFM_DEVI void pipe_wait(const unsigned* cnt, unsigned target, unsigned* err) {
 WFM_DEVI void pipe_signal(unsigned* cnt) {
     __syncthreads();
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(cnt, 1u); }
+}
+
+// Self-cleaning control block: the last CTA to leave the work loop zeroes the queue and the per-plane
+// counters, so the next launch needs no memset (every other CTA has already stopped touching them).
+WFM_DEVI void pipe_finish(const PipeCtl& c, int P) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(c.done, 1u) == gridDim.x - 1) {
+            for (int p = 0; p < P; ++p) { c.cntA[p] = 0u; c.cntB[p] = 0u; }
+            *c.queue = 0u;
+            *c.done = 0u;
+            __threadfence();
+        }
+    }
 }
 
 // Work-item queue of a persistent CTA.  Thread 0 claims item i+1 while item i is being processed
@@ -568,6 +584,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             pipe_signal(&ctl.cntB[it.plane]);
         }
     }
+    pipe_finish(ctl, P);
 }
 
 // ================================================================================================
@@ -746,48 +763,54 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             pipe_signal(&ctl.cntB[it.plane]);
         }
     }
+    pipe_finish(ctl, P);
 }
 
 // ---- contraction of the per-plane integrands with the basis: warp-then-block reductions --------
+// The basis is gathered once (per basis / support change) into the order of the support-cell list,
+// so that the reduction reads it as contiguous rows: Zs[k][li] = Z[k][in_list[li]].
+__global__ void k_pack_basis(double* __restrict__ Zs, const double* __restrict__ Z, const int* __restrict__ in_list,
+                             int ncells, int nzern, int npix) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= ncells) return;
+    const int in = in_list[li];
+    for (int k = 0; k < nzern; ++k) Zs[(size_t)k * ncells + li] = Z[(size_t)k * npix + in];
+}
+
 struct ReduceArgs {
     Geom g;
-    const double* Gj; const double* Gm; int pitch; int nax;
-    const int* act_x;
-    const double* Z; const double* psi; const uint8_t* mask; const uint8_t* support;
+    const double* Gj; const double* Gm; int pitch;
+    const double* Zs;        // [nzern][ncells] basis in cell-list order
+    const double* psi;
+    const uint8_t* flags;    // strip flags (bit 0 maskPupil, bit 1 support)
+    const int* cell_list;    // [ncells] tile-major strip cells that lie on the support
+    const int* in_list;      // [ncells] their pixel index kx + N*ky
+    int ncells;
     int nphase, nmod, phase_off;
     unsigned kinds;
     int last_plane_only;
     double dxy, lambda_ni, deltaX, deltaY;
-    double* block_part;   // [nchunks][nblocks][glen]
-    int glen;             // 3 + nphase + nmod
-    const int* cell_list; // [ncells] tile-major strip cells that lie on the support
-    int ncells;
-    int ctile;            // columns per strip tile
+    double* block_part;      // [nchunks][nblocks][glen]
+    int glen;                // 3 + nphase + nmod
 };
 
 #define WFM_RED_THREADS 256
 #define WFM_RED_CHUNK 8
 #define WFM_RED_PLANES 16   // planes summed by one CTA (grid.y = ceil(nzl / WFM_RED_PLANES))
 
-// One thread per support cell (ky, xi) of the compact pupil strip and per chunk of WFM_RED_PLANES planes.
-// Sums the planes of the chunk in fixed order (gP = sum jin, gD = sum defoc*jin, gM = sum J), then
-// forms the glen dot products WFM_RED_CHUNK at a time: shuffle-reduce inside each warp, then across
-// the warps of the block through shared memory.
+// One thread per support cell and per chunk of WFM_RED_PLANES planes.  Sums the planes of the chunk
+// in fixed order (gP = sum jin, gD = sum defoc*jin, gM = sum J), then forms the glen dot products
+// WFM_RED_CHUNK at a time: shuffle-reduce inside each warp, then across the warps of the block
+// through shared memory.
 __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     __shared__ double red[WFM_RED_THREADS / 32][WFM_RED_CHUNK];
     const int N = a.g.N;
     const size_t img = (size_t)N * a.pitch;
     const int li = blockIdx.x * WFM_RED_THREADS + threadIdx.x;
-    const bool in_range = li < a.ncells;
-    const size_t cell = in_range ? (size_t)a.cell_list[li] : 0;
-    const int rem = (int)(cell % ((size_t)N * a.ctile));
-    const int ky = in_range ? rem / a.ctile : 0;
-    const int xi = in_range ? (int)(cell / ((size_t)N * a.ctile)) * a.ctile + rem % a.ctile : 0;
-    const bool colvalid = in_range && xi < a.nax;
-    const int kx = colvalid ? a.act_x[xi] : 0;
-    const int in = kx + N * ky;
-    const bool sup = colvalid && a.support[in];
-    const bool m = sup && a.mask[in];
+    const bool sup = li < a.ncells;                    // every listed cell lies on the support
+    const size_t cell = sup ? (size_t)a.cell_list[li] : 0;
+    const int in = sup ? a.in_list[li] : 0;
+    const bool m = sup && (a.flags[cell] & 1u);
     const int p0 = blockIdx.y * WFM_RED_PLANES;
     const int p1 = (p0 + WFM_RED_PLANES < a.g.nzl) ? p0 + WFM_RED_PLANES : a.g.nzl;
     double gP = 0.0, gD = 0.0, gM = 0.0;
@@ -808,10 +831,9 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     if (m && (a.kinds & 1u)) {
         const double scale = 1.0 / ((double)N * a.dxy);
         wD = gD * (1.0 / a.psi[in]);
-        rx = (double)kappa_dev(kx, N) * scale - a.deltaX;
-        ry = (double)kappa_dev(ky, N) * scale - a.deltaY;
+        rx = (double)kappa_dev(in % N, N) * scale - a.deltaX;
+        ry = (double)kappa_dev(in / N, N) * scale - a.deltaY;
     }
-    const int npix = N * N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* out = a.block_part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * a.glen;
     for (int j0 = 0; j0 < a.glen; j0 += WFM_RED_CHUNK) {
@@ -824,9 +846,9 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
                 if (j < 3) {
                     if (a.kinds & 1u) val = (j == 0) ? wD * a.lambda_ni : (j == 1 ? wD * rx : wD * ry);
                 } else if (j < 3 + a.nphase) {
-                    if ((a.kinds & 2u) && m) val = gP * a.Z[(size_t)(j - 3 + a.phase_off) * npix + in];
+                    if ((a.kinds & 2u) && m) val = gP * a.Zs[(size_t)(j - 3 + a.phase_off) * a.ncells + li];
                 } else {
-                    if (a.kinds & 4u) val = gM * a.Z[(size_t)(j - 3 - a.nphase) * npix + in];
+                    if (a.kinds & 4u) val = gM * a.Zs[(size_t)(j - 3 - a.nphase) * a.ncells + li];
                 }
             }
             acc[jj] = val;
