@@ -179,9 +179,13 @@ template <int TT> struct RowSync {
 //       95 % busy with 2/3 of its wavefronts spent on per-leg twiddle loads; profiles/r01a_*.)
 // S   : barrier scope (CtaSync / RowSync); every thread inside that scope must call this together.  The caller
 // must place a barrier between the end of one call and the start of the next one that reuses sm.
-template <typename T, class P, class L, class S>
+struct NoHook { WFM_DEVI void operator()() const {} };
+
+// Hook: callable run once by every thread right after the first exchange barrier (used by the
+// pipelines to claim the next work item while two thirds of the transform are still ahead).
+template <typename T, class P, class L, class S, class Hook = NoHook>
 WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* tw, const cx<T>* tw2,
-                          const int sync_id) {
+                          const int sync_id, const Hook& hook = Hook()) {
     constexpr int E = P::E, R1 = P::R1, R2 = P::R2, R3 = P::R3, TT = P::T, S1 = P::S1;
     // stage 1: radix R1 over legs of stride S1, twiddle W_N^(b*k1), scatter to cell k1*S1 + b
 #pragma unroll
@@ -201,6 +205,7 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
         }
     }
     S::sync(sync_id);
+    hook();
     if constexpr (P::THREE) {
         // stage 2: inside block k1, radix R2 over legs of stride R3, twiddle W_N^(R1*d3*k2)
 #pragma unroll

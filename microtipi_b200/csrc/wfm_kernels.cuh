@@ -382,13 +382,16 @@ WFM_DEVI void pipe_finish(const PipeCtl& c, int P) {
     }
 }
 
-// Work-item queue of a persistent CTA.  Thread 0 claims item i+1 while item i is being processed
-// and probes that item's dependency counter once (acquire): in steady state the dependency is
-// already met, so neither the atomic nor the L2 poll is on the critical path.  The claim becomes
-// visible to the CTA through the barriers every item executes.
+// Work-item queue of a persistent CTA.  Thread 0 claims item i+1 LATE in item i (start of the last
+// row of a row item / after the first stage of a column item): the atomic's latency is still hidden
+// behind the rest of the item, but a CTA holds two claims only for a fraction of the item, so the
+// window of claimed-but-unstarted queue entries -- which sets the lag B(p) must trail A(p) by, hence
+// the ring size -- is ~1.3 items per CTA instead of 2.  At claim time thread 0 also probes the
+// item's dependency counter once (acquire): in steady state it is already met.
 struct PipeQueue {
     unsigned* s;   // shared: s[0..1] item index, s[2..3] dependency already satisfied
     int cur;
+    bool pre;      // (thread 0) next item already claimed during this item
     WFM_DEVI static bool probe(const PipeItem& it, const PipeCtl& c) {
         const unsigned* cnt; unsigned target;
         if (it.type == 0) {
@@ -409,22 +412,31 @@ struct PipeQueue {
         s[2 + slot] = (it.type < 0 || probe(it, c)) ? 1u : 0u;
     }
     WFM_DEVI void init(unsigned* smem4, const PipeCtl& c, int P) {
-        s = smem4; cur = 0;
+        s = smem4; cur = 0; pre = false;
         if (threadIdx.x == 0) claim(0, c, P);
         __syncthreads();
     }
-    // returns the current item; `ready` tells whether its dependency was already observed as met
+    // the current item; `ready` tells whether its dependency was already observed as met
     WFM_DEVI PipeItem take(const PipeCtl& c, int P, bool& ready) {
-        const PipeItem it = pipe_decode(s[cur], P, c);
+        pre = false;
         ready = s[2 + cur] != 0u;
-        if (threadIdx.x == 0 && it.type >= 0) claim(cur ^ 1, c, P);
-        cur ^= 1;
-        return it;
+        return pipe_decode(s[cur], P, c);
     }
+    // claim the next item (thread 0, once per item; called from inside the item and again, as a
+    // no-op, before the item is published)
+    WFM_DEVI void prefetch(const PipeCtl& c, int P) {
+        if (threadIdx.x == 0 && !pre) { claim(cur ^ 1, c, P); pre = true; }
+    }
+    WFM_DEVI void advance() { cur ^= 1; }
 };
 
 // What an item must wait for before it may touch the ring slot (NULL counter: nothing).
 struct PipeDep { const unsigned* cnt; unsigned target; unsigned* err; };
+// hook for fft_inplace: claim the next item after the first stage of a column item
+struct PipePrefetchHook {
+    PipeQueue& qu; const PipeCtl& ctl; int P;
+    WFM_DEVI void operator()() const { qu.prefetch(ctl, P); }
+};
 WFM_DEVI void pipe_wait(const PipeDep& d) { if (d.cnt) pipe_wait(d.cnt, d.target, d.err); }
 
 // ================================================================================================
@@ -451,7 +463,7 @@ template <typename T> struct PsfArgs {
 // synthesised in the load (WFM:311-316; sincos only where rho != 0, quirk Q6), then FFT along y.
 template <typename T, int N>
 WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
-                            const PipeDep& dep) {
+                            const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
@@ -480,7 +492,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
             v[e] = val;
         }
     }
-    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + N, 0);
+    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + N, 0, PipePrefetchHook{qu, ctl, a.g.nzl});
     pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
     cx<T>* dst = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)sub * N * C + c;
 #pragma unroll
@@ -494,7 +506,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
 // (WFM:323-328) as full contiguous rows.  No CTA-wide barrier inside.
 template <typename T, int N>
 WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
-                            const int* invx_s) {
+                            const int* invx_s, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
     using Cfg = PipeCfg<T, N>;
@@ -519,6 +531,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
 #endif
 #pragma unroll 1
     for (int kk = 0; kk < Cfg::KR; ++kk) {
+        if (kk == Cfg::KR - 1) qu.prefetch(ctl, a.g.nzl);             // claim the next item behind the last row
         const int ky = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;     // N % ROWS_PER_ITEM == 0
         const cx<T>* src = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)ky * C;
         cx<T> v[E];
@@ -573,16 +586,19 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, dep);
+                psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, dep, qu, ctl);
             }
+            qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s);
+                psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, qu, ctl);
             }
+            qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntB[it.plane]);
         }
+        qu.advance();
     }
     pipe_finish(ctl, P);
 }
@@ -609,7 +625,7 @@ template <typename T> struct JacArgs {
 // fused into the streaming load (WFM:907-914), FFT along x, keep the active kx only.
 template <typename T, int N>
 WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
-                            const int* invx_s, const PipeDep& dep) {
+                            const int* invx_s, const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
     using Cfg = PipeCfg<T, N>;
@@ -641,6 +657,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 #endif
 #pragma unroll 1
     for (int kk = 0; kk < Cfg::KR; ++kk) {
+        if (kk == Cfg::KR - 1) qu.prefetch(ctl, a.g.nzl);             // claim the next item behind the last row
         const int y = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;      // N % ROWS_PER_ITEM == 0
         const size_t base = (size_t)pl * N * N + (size_t)N * y;
         cx<T> v[E];
@@ -683,7 +700,8 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 //   jin = rho*(B_re sin ph + B_im cos ph)   on maskPupil   (WFM:925-928, 1253)
 //   J   = B_re cos ph - B_im sin ph         on the support (WFM:607-611)
 template <typename T, int N>
-WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s) {
+WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+                            PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
@@ -707,7 +725,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 #pragma unroll
         for (int r = 0; r < P::RL; ++r)
             fl |= (unsigned)__ldg(&a.st.flags[tbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
-    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + N, 0);
+    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + N, 0, PipePrefetchHook{qu, ctl, a.g.nzl});
     const int iz = a.g.z0 + pl;
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
     const bool mod_plane = (a.Gm != nullptr) && (!a.last_plane_only || iz == a.g.nz_global - 1);
@@ -752,16 +770,19 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, dep);
+                jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, dep, qu, ctl);
             }
+            qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                jac_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s);
+                jac_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, qu, ctl);
             }
+            qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntB[it.plane]);
         }
+        qu.advance();
     }
     pipe_finish(ctl, P);
 }
