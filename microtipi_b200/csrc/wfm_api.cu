@@ -268,12 +268,12 @@ PipePlan plan_pipeline(const wfm_model* h, int nA, int nB, size_t plane_bytes, i
     PipePlan p;
     p.nA = nA; p.nB = nB;
     const int nctas = h->num_sms * ctas_per_sm;
-    // Every CTA holds two claimed items (current + prefetched), so ~2*nctas consecutive queue entries are in
-    // flight; B(p) must be queued at least that far behind A(p) or its CTA stalls on cntA[p].  Measured at
-    // 512^2 fp64: ms/step 1.83, 1.37, 1.12, 1.01, 0.97, 0.95, 0.96 for lag 5, 8, 12, 16, 20, 24, 32.
-    int lag = (4 * nctas + (nA + nB) - 1) / (nA + nB) + 8;
+    // A CTA holds its current item plus, for the last part of it, the next one: ~1.3*nctas consecutive queue
+    // entries are in flight, and B(p) must be queued about twice that far behind A(p) or its CTA stalls on
+    // cntA[p].  Measured at 512^2 fp64 (ms/step): lag 8: 1.14, 12: 1.00, 16: 0.949, 20: 0.940, 26: 0.963.
+    int lag = (13 * nctas / 5 + (nA + nB) - 1) / (nA + nB);
     if (lag < 2) lag = 2;
-    size_t budget = 80u << 20;                 // ring = 2*lag+2 planes, kept L2-resident (126 MB L2)
+    size_t budget = 64u << 20;                 // ring = 2*lag+2 planes, meant to stay L2-resident (126 MB L2)
     if (const char* e = getenv("WFM_PIPE_RING_MB")) { int v = atoi(e); if (v > 0) budget = (size_t)v << 20; }
     if (const char* e = getenv("WFM_PIPE_LAG")) { int v = atoi(e); if (v >= 1) lag = v; }
     while (lag > 2 && (size_t)(2 * lag + 2) * plane_bytes > budget) --lag;
