@@ -464,7 +464,6 @@ template <typename T> struct PsfArgs {
 template <typename T, int N>
 WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
                             const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
-    const unsigned long long pol = ring_policy();
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
@@ -499,7 +498,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
-        for (int r = 0; r < P::RL; ++r) ring_store(&dst[(size_t)((t + TT * u) + P::SL * r) * C], v[u * P::RL + r], pol);
+        for (int r = 0; r < P::RL; ++r) __stcg(&dst[(size_t)((t + TT * u) + P::SL * r) * C], v[u * P::RL + r]);
 }
 
 // B-item: ROWS_PER_ITEM rows of plane pl (each TT-thread group walks KR of them): FFT along x
@@ -508,7 +507,6 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
 template <typename T, int N>
 WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
                             const int* invx_s, PipeQueue& qu, const PipeCtl& ctl) {
-    const unsigned long long pol = ring_policy();
     using P = Plan<N>;
     using L = RowLayout<T, N>;
     using Cfg = PipeCfg<T, N>;
@@ -528,7 +526,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
     {
         const cx<T>* src0 = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)(sub * Cfg::ROWS_PER_ITEM + slot) * C;
 #pragma unroll
-        for (int e = 0; e < E; ++e) nv[e] = (xis[e] >= 0) ? ring_load(&src0[xis[e]], pol) : mkc<T>((T)0, (T)0);
+        for (int e = 0; e < E; ++e) nv[e] = (xis[e] >= 0) ? __ldcg(&src0[xis[e]]) : mkc<T>((T)0, (T)0);
     }
 #endif
 #pragma unroll 1
@@ -543,11 +541,11 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
         if (kk + 1 < Cfg::KR) {
             const cx<T>* nsrc = src + (size_t)C * C;
 #pragma unroll
-            for (int e = 0; e < E; ++e) nv[e] = (xis[e] >= 0) ? ring_load(&nsrc[xis[e]], pol) : mkc<T>((T)0, (T)0);
+            for (int e = 0; e < E; ++e) nv[e] = (xis[e] >= 0) ? __ldcg(&nsrc[xis[e]]) : mkc<T>((T)0, (T)0);
         }
 #else
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = (xis[e] >= 0) ? ring_load(&src[xis[e]], pol) : mkc<T>((T)0, (T)0);
+        for (int e = 0; e < E; ++e) v[e] = (xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
 #endif
         fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
         const size_t base = (size_t)pl * N * N + (size_t)N * ky;
@@ -628,7 +626,6 @@ template <typename T> struct JacArgs {
 template <typename T, int N>
 WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
                             const int* invx_s, const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
-    const unsigned long long pol = ring_policy();
     using P = Plan<N>;
     using L = RowLayout<T, N>;
     using Cfg = PipeCfg<T, N>;
@@ -693,7 +690,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
         cx<T>* dst = a.T2 + (size_t)(pl % ring) * N * a.pitch + (size_t)y * C;
 #pragma unroll
         for (int e = 0; e < E; ++e)
-            if (xis[e] >= 0) ring_store(&dst[xis[e]], v[e], pol);
+            if (xis[e] >= 0) __stcg(&dst[xis[e]], v[e]);
         if (kk + 1 < Cfg::KR) RowSync<TT>::sync(slot);
     }
 }
@@ -705,7 +702,6 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 template <typename T, int N>
 WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
                             PipeQueue& qu, const PipeCtl& ctl) {
-    const unsigned long long pol = ring_policy();
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
@@ -720,7 +716,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 #pragma unroll
         for (int r = 0; r < P::R1; ++r) {
             const int y = (t + TT * u) + P::S1 * r;
-            v[u * P::R1 + r] = colvalid ? ring_load(&src[(size_t)y * C], pol) : mkc<T>((T)0, (T)0);
+            v[u * P::R1 + r] = colvalid ? __ldcg(&src[(size_t)y * C]) : mkc<T>((T)0, (T)0);
         }
     // the flags of this thread's output cells: independent loads, in flight during the transform
     unsigned fl = 0;

@@ -297,12 +297,6 @@ static inline int atomicAdd(int* addr, int v) { return __atomic_fetch_add(addr, 
 #include <chrono>
 #define WFM_SPIN_PAUSE() std::this_thread::sleep_for(std::chrono::microseconds(50))
 
-namespace wfm {
-static inline unsigned long long ring_policy() { return 0; }
-template <class V> static inline V ring_load(const V* p, unsigned long long) { return *p; }
-template <class V> static inline void ring_store(V* p, V v, unsigned long long) { *p = v; }
-}  // namespace wfm
-
 // dynamic shared memory of the running CTA
 #define WFM_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::cur()->smem)
 
