@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="Nx = Ny")
+    ap.add_argument("--nxy", "--n", dest="n", type=int, default=512, help="Nx = Ny (use --nxy under torchrun)")
     ap.add_argument("--nz", type=int, default=256, help="z-planes per GPU")
     ap.add_argument("--single", action="store_true", help="optional fp32 mode (not the headline)")
     ap.add_argument("--kinds", type=int, default=2, help="Jacobian bits: 1 defocus, 2 phase, 4 modulus")
