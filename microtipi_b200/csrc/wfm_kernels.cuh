@@ -298,6 +298,10 @@ struct PipeCtl {
 #ifndef WFM_PIPE_KR
 #define WFM_PIPE_KR 4
 #endif
+// Row items of the Jacobian bulk-prefetch their next row of conj(a) and q into L2 (TMA prefetch).
+#ifndef WFM_L2_PREFETCH
+#define WFM_L2_PREFETCH 1
+#endif
 template <typename T, int N> struct PipeCfg {
     using P = Plan<N>;
     static constexpr int C = (N >= 256) ? (sizeof(T) == 8 ? WFM_PIPE_C64 : 8) : ColCfg<T, N>::C;   // columns per B-item == rows per A-item
@@ -660,6 +664,12 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
         if (kk == Cfg::KR - 1) qu.prefetch(ctl, a.g.nzl);             // claim the next item behind the last row
         const int y = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;      // N % ROWS_PER_ITEM == 0
         const size_t base = (size_t)pl * N * N + (size_t)N * y;
+#if WFM_L2_PREFETCH
+        if (t == 0 && kk + 1 < Cfg::KR) {              // this group's next row: DRAM -> L2 while this row is transformed
+            wfm_prefetch_l2(&a.cpx[base + (size_t)N * C], (unsigned)(N * sizeof(cx<T>)));
+            wfm_prefetch_l2(&a.q[base + (size_t)N * C], (unsigned)(N * sizeof(T)));
+        }
+#endif
         cx<T> v[E];
 #if WFM_ROW_PREFETCH
 #pragma unroll

@@ -22,6 +22,12 @@ inline std::atomic<unsigned long long>& launch_counter() {
 
 #define WFM_SPIN_PAUSE() __nanosleep(40)
 
+// TMA bulk prefetch of a contiguous global range into L2 (no registers, no shared memory, one
+// instruction per row): bytes must be a multiple of 16, the address 16-byte aligned.
+__device__ __forceinline__ void wfm_prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 
 #define WFM_LAUNCH(kfn, grid, block, smem, stream, ...)                    \
     do {                                                                   \

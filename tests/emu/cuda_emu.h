@@ -297,6 +297,8 @@ static inline int atomicAdd(int* addr, int v) { return __atomic_fetch_add(addr, 
 #include <chrono>
 #define WFM_SPIN_PAUSE() std::this_thread::sleep_for(std::chrono::microseconds(50))
 
+static inline void wfm_prefetch_l2(const void*, unsigned) {}
+
 // dynamic shared memory of the running CTA
 #define WFM_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::cur()->smem)
 
