@@ -339,7 +339,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     rc = pack_strip(h); if (rc) return rc;
     const int nA = N / Cfg::ROWS_PER_ITEM, nB = h->pitch / Cfg::C;
     const size_t plane_bytes = sizeof(cx<T>) * (size_t)N * h->pitch;
-    const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, Cfg::MINB);
+    const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, Cfg::MINB_JAC);
     WFM_CK(h, h->scratch.ensure(plane_bytes * pp.ring));
     const size_t img = (size_t)N * h->pitch;
     WFM_CK(h, h->Gj.ensure(sizeof(double) * img * h->nzl));
@@ -401,10 +401,13 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     return WFM_OK;
 }
 
-#ifdef WFM_ONLY_512   /* quick experiment builds: instantiate the headline size only */
+#ifdef WFM_ONLY_512
+#define WFM_ONLY_N 512
+#endif
+#ifdef WFM_ONLY_N   /* quick experiment builds: instantiate one size only */
 #define WFM_DISPATCH_N(FN, h, ...)                                                     \
     switch ((h)->N) {                                                                  \
-        case 512: return FN<T, 512>(h, ##__VA_ARGS__);                                 \
+        case WFM_ONLY_N: return FN<T, WFM_ONLY_N>(h, ##__VA_ARGS__);                   \
         default: return (h)->fail(WFM_ERR_UNSUPPORTED, "unsupported N=%d", (h)->N);    \
     }
 #else

@@ -327,6 +327,13 @@ template <typename T, int N> struct PipeCfg {
 #else
     static constexpr int MINB = BY_THREADS < BY_SMEM ? BY_THREADS : BY_SMEM;
 #endif
+    // The Jacobian pipeline spills at 64 registers (hoisted strip offsets + pointwise part); it is
+    // faster with ~85 registers and three quarters of the CTAs (measured 0.410 vs 0.432 ms at 512^2).
+#ifdef WFM_PIPE_MINB_JAC
+    static constexpr int MINB_JAC = WFM_PIPE_MINB_JAC;
+#else
+    static constexpr int MINB_JAC = (sizeof(T) == 8 && MINB >= 4) ? (3 * MINB) / 4 : MINB;
+#endif
 };
 
 struct PipeItem { int type; int plane; int sub; };   // type 0 = A, 1 = B, -1 = done
@@ -760,7 +767,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 }
 
 template <typename T, int N>
-__global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k_jac_pipeline(JacArgs<T> a, PipeCtl ctl) {
+__global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB_JAC) k_jac_pipeline(JacArgs<T> a, PipeCtl ctl) {
     using Cfg = PipeCfg<T, N>;
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
