@@ -577,3 +577,34 @@ def synthetic_q(Nx, Ny, Nz, seed=42, z0=0, nz_local=None, single=False):
     nzl = Nz - z0 if nz_local is None else nz_local
     q = splitmix64_uniform(seed, z0 * Nx * Ny, nzl * Nx * Ny).reshape(nzl, Ny, Nx)
     return q.astype(np.float32) if single else q
+
+
+# ----------------------------------------------------------------------------
+# BASELINE config 3: structured q from a synthetic bead volume
+# ----------------------------------------------------------------------------
+def bead_problem(shape, psf_true, noise_sigma_rel=0.01, seed=7, radius_px=2.5):
+    """(O, data): spectrum of a solid sphere of `radius_px` centred at voxel 0 and the noisy data
+    obj (*) psf_true + N(0, noise_sigma_rel*max) (periodic 3-D FFT convolution)."""
+    nz, ny, nx = shape
+    zz, yy, xx = np.meshgrid(np.arange(nz) - nz // 2, np.arange(ny) - ny // 2, np.arange(nx) - nx // 2, indexing="ij")
+    obj = ((zz ** 2 + yy ** 2 + xx ** 2) <= radius_px ** 2).astype(np.float64)
+    obj = np.roll(obj, (-(nz // 2), -(ny // 2), -(nx // 2)), axis=(0, 1, 2))      # centred at voxel 0 like the PSF
+    O = sfft.fftn(obj)
+    data = sfft.ifftn(O * sfft.fftn(np.asarray(psf_true, dtype=np.float64))).real
+    rng = np.random.default_rng(seed)
+    return O, data + rng.normal(0.0, noise_sigma_rel * float(np.abs(data).max()), data.shape)
+
+
+def bead_cost_and_q(psf, O, data):
+    """cost = 1/2 ||h (*) obj - data||^2 and q = d cost / d h = corr(obj, h (*) obj - data)."""
+    resid = sfft.ifftn(O * sfft.fftn(np.asarray(psf, dtype=np.float64))).real - data
+    return 0.5 * float(np.sum(resid * resid)), sfft.ifftn(np.conj(O) * sfft.fftn(resid)).real
+
+
+def bead_gradient_q(psf, psf_true, noise_sigma_rel=0.01, seed=7, radius_px=2.5):
+    """q = d/dh 1/2 ||h (*) obj - data||^2 for the synthetic bead volume of SURVEY 8d2 (ii)
+    (restating the role of TiPi's WeightedConvolutionCost at PSF_Estimation.java:147-157,206 with
+    unit weights; TiPi's source is not in the reference tree, so this is only a realistic *input*
+    for the Jacobians, not a parity claim on the cost function)."""
+    O, data = bead_problem(psf.shape, psf_true, noise_sigma_rel, seed, radius_px)
+    return bead_cost_and_q(psf, O, data)[1]

@@ -215,3 +215,44 @@ def test_full_size_properties_512x512x256(lib):
     assert o.rel_l2(got[3:13], want_p) <= 1e-12
     assert o.rel_l2(got[13:], want_m) <= 1e-12
     m.close()
+
+
+def test_config3_bead_volume_gradient(lib):
+    """BASELINE config 3 at reduced size: q comes from an FFT-convolution data term on a synthetic bead
+    (structured, strongly correlated with the PSF) instead of white noise."""
+    N, Nz = 128, 16
+    ref, m = make_pair(N, Nz, lib)
+    truth = o.WideFieldModelOracle((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"])
+    truth.setPhase(o.synthetic_alpha(10, seed=4321))
+    truth.setModulus(BETA4)
+    q = o.bead_gradient_q(ref.getPsf(), truth.getPsf())
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+    for a, b in zip(m.apply_J_all(q), (ref.apply_J_defocus(q), ref.apply_J_phase(q), ref.apply_J_modulus(q))):
+        assert o.rel_l2(a, b) <= 1e-12
+    m.close()
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_config5_independent_models(lib, single):
+    """BASELINE config 5 (batched PSF estimation over independent 256x256 bead PSFs) as a parity case:
+    several models with parameter seeds 1234+b live side by side (distinct handles are independent)."""
+    N, Nz, B = 256, 8, 3
+    t = tol(single)
+    models, refs = [], []
+    for b in range(B):
+        ref = o.WideFieldModelOracle((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], single=single)
+        m = WideFieldModel((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, single, lib=lib,
+                           basis=oracle_basis(N))
+        alpha = o.synthetic_alpha(10, seed=1234 + b)
+        for mm in (ref, m):
+            mm.setPhase(alpha)
+            mm.setModulus(BETA4)
+        models.append(m); refs.append(ref)
+    for m in models:                                   # all PSFs first, then all Jacobians: handles interleave
+        m.computePsf()
+    for b, (m, ref) in enumerate(zip(models, refs)):
+        q = o.synthetic_q(N, N, Nz, seed=42 + b, single=single)
+        assert o.rel_l2(m.getPsf(), ref.getPsf()) <= t
+        assert o.rel_l2(m.apply_J_phase(q).data, ref.apply_J_phase(q)) <= (20 * t if single else t)
+    for m in models:
+        m.close()

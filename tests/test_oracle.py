@@ -182,3 +182,22 @@ def test_splitmix_counter_based():
     z = np.uint64(0)
     u = o.splitmix64_uniform(0, 0, 1)[0]
     assert u == 2.0 * ((0xE220A8397B1DCDAF >> 11) / 2 ** 53) - 1.0
+
+
+def test_blind_deconvolution_inner_loop_chain_rule():
+    # config 3: d/d alpha of the data term 1/2||h(alpha)(*)obj - data||^2 == apply_J_phase(dcost/dh)
+    m = make(32, 8)
+    truth = make(32, 8)
+    truth.setPhase(o.synthetic_alpha(10, seed=4321))
+    O, data = o.bead_problem((8, 32, 32), truth.getPsf())
+    a0 = m.alpha.copy()
+    _, q = o.bead_cost_and_q(m.getPsf(), O, data)
+    g = m.apply_J_phase(q)
+    for k in (1, 6):
+        h = 1e-6
+        ap, am = a0.copy(), a0.copy()
+        ap[k] += h
+        am[k] -= h
+        m.setPhase(ap); cp, _ = o.bead_cost_and_q(m.getPsf(), O, data)
+        m.setPhase(am); cm, _ = o.bead_cost_and_q(m.getPsf(), O, data)
+        assert abs((cp - cm) / (2 * h) - g[k]) <= 5e-6 * np.abs(g).max()
