@@ -76,6 +76,24 @@ class ShardedWideFieldModel:
             self._dist.all_reduce(grad_tensor, op=self._dist.ReduceOp.SUM, group=self.group)
         return grad_tensor
 
+    def gatherPsfDevice(self):
+        """NCCL all-gather of the PSF slabs on the device: returns a CUDA tensor (Nz, Ny, Nx) holding the
+        whole stack on every rank.  Bandwidth-heavy (8*Npix*Nz bytes), therefore off the hot path."""
+        import torch
+        local = self.model.devicePsfTensor()
+        self.model.synchronize()
+        if self.world == 1:
+            return local
+        nz = self.model.Nz
+        out = torch.empty((nz, self.model.Ny, self.model.Nx), dtype=local.dtype, device=local.device)
+        bounds = [slab_bounds(nz, self.world, r) for r in range(self.world)]
+        if len({b[1] for b in bounds}) == 1:
+            self._dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        else:
+            parts = [out[z0:z0 + n] for z0, n in bounds]
+            self._dist.all_gather(parts, local.contiguous(), group=self.group)
+        return out
+
     # ---- optional PSF gather ------------------------------------------------------------------------
     def getPsf(self, gather=False):
         local = self.model.getPsf()

@@ -316,6 +316,17 @@ class WideFieldModel(MicroscopeModel):
         self.PState = 1
         return p.value
 
+    def devicePsfTensor(self):
+        """Zero-copy torch view (nz_local, Ny, Nx) of the device-resident PSF slab (plumbing for NCCL)."""
+        import torch
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.nz_local, self.Ny, self.Nx), "typestr": "<f4" if self.single else "<f8",
+                                      "data": (self.devicePsfPointer(), False), "version": 2}
+        return torch.as_tensor(v, device="cuda")
+
     def fillUniform(self, dev_ptr, seed, first_index, count, single=None):
         prec = capi.WFM_F32 if (self.single if single is None else single) else capi.WFM_F64
         self._call("wfm_fill_uniform", C.c_void_p(dev_ptr), prec, int(seed), int(first_index), int(count))
