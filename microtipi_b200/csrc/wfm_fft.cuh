@@ -108,7 +108,11 @@ template <> struct Plan<32> : PlanBase<32, 8, 8, 4, 1> {};
 template <> struct Plan<64> : PlanBase<64, 8, 8, 8, 1> {};
 template <> struct Plan<128> : PlanBase<128, 8, 8, 4, 4> {};
 template <> struct Plan<256> : PlanBase<256, 8, 8, 8, 4> {};
+#ifdef WFM_PLAN512_E16   /* experiment: one warp per transform (T = 32), 16 values per thread */
+template <> struct Plan<512> : PlanBase<512, 16, 16, 8, 4> {};
+#else
 template <> struct Plan<512> : PlanBase<512, 8, 8, 8, 8> {};
+#endif
 template <> struct Plan<1024> : PlanBase<1024, 16, 16, 8, 8> {};
 template <> struct Plan<2048> : PlanBase<2048, 16, 16, 16, 8> {};
 
@@ -118,7 +122,11 @@ template <> struct RowPad<32, 16> { static constexpr int PA = 3, PB = 4; };
 template <> struct RowPad<64, 16> { static constexpr int PA = 3, PB = 0; };
 template <> struct RowPad<128, 16> { static constexpr int PA = 0, PB = 4; };
 template <> struct RowPad<256, 16> { static constexpr int PA = 3, PB = 6; };
+#ifdef WFM_PLAN512_E16
+template <> struct RowPad<512, 16> { static constexpr int PA = 3, PB = 6; };
+#else
 template <> struct RowPad<512, 16> { static constexpr int PA = 0, PB = 6; };
+#endif
 template <> struct RowPad<1024, 16> { static constexpr int PA = 0, PB = 6; };
 template <> struct RowPad<2048, 16> { static constexpr int PA = 0, PB = 7; };
 template <> struct RowPad<32, 8> { static constexpr int PA = 3, PB = 4; };
