@@ -113,9 +113,11 @@ def cpu_reference_planes_per_s(N, nz_global, planes, threads, repeats=1):
     ref = o.WideFieldModelOracle((N, N, 2), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"])
     ref.setPhase(o.synthetic_alpha(10))
     rho, phi, psi, mask, Z = ref.rho, ref.phi, ref.psi, ref.maskPupil, ref.Z
-    q = o.synthetic_q(N, N, nz_global, nz_local=planes)
+    nzq = min(planes, nz_global)
+    q = o.synthetic_q(N, N, nz_global, nz_local=nzq)
 
-    def task(iz):
+    def task(i):
+        iz = i % nzq                                                # the sample may wrap around the stack
         c, p = o.compute_psf(rho, phi, psi, nz_global, P["dz"], z0=iz, nz_local=1)
         return o.apply_J_phase(q[iz:iz + 1], c, rho, phi, psi, mask, Z, 10, nz_global, P["dz"], z0=iz)
 
@@ -136,7 +138,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    planes = args.cpu_planes or max(cores, 16)
+    planes = args.cpu_planes or max(8 * cores, 64)             # ~0.25 s per step on 16 cores
     times, total = [], 0
     for _ in range(args.warmup):
         cpu_reference_planes_per_s(args.n, args.nz * args.gpus, min(planes, cores), cores)
@@ -346,7 +348,7 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            planes = args.cpu_planes or max(2 * cores, 32)
+            planes = args.cpu_planes or max(128 * cores, 512)      # a few seconds of wall time = tens of core-seconds
             v, dt = cpu_reference_planes_per_s(N, nzg, planes, cores)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"{planes} of the {nzg} planes ({N}x{N} fp64), one task per plane on "
