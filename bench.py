@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval-fg", action="store_true", help="skip the config-3 inner-loop timing (wfm_eval_fg)")
     return ap.parse_args()
 
 
@@ -281,8 +282,9 @@ def run_b200(args):
     def e2e_step(i):
         a = np.ascontiguousarray(alpha + 1e-3 * (i % 7))
         assert lib.wfm_set_phase(h, a.ctypes.data_as(C.c_void_p), 10) == 0
-        assert lib.wfm_get_psf(h, hp) == 0                         # computePsf + D2H of the PSF slab
+        assert lib.wfm_get_psf_async(h, hp) == 0                   # computePsf + D2H of the PSF slab (2nd stream)
         assert lib.wfm_apply_j_phase(h, hq, gout, 10) == 0         # H2D of q + Jacobian + D2H of the gradient
+        assert lib.wfm_wait_transfers(h) == 0                      # the PSF slab has landed in host memory
         if world > 1:
             g = torch.tensor(list(gout), dtype=torch.float64, device=dev)
             dist.all_reduce(g)
@@ -303,6 +305,35 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     lib.wfm_host_free(hq)
     lib.wfm_host_free(hp)
+
+    # ---- config 3: the blind-deconvolution inner loop with the data term on the device (row f1) ------
+    # one evaluation = setParam(x) -> computePsf -> FFT-convolution cost + gradient -> apply_J_phase; only x
+    # goes to the device, the cost and the gradient come back (PSF_Estimation.java:202-217).
+    eval_fg = None
+    if world == 1 and not single and not args.no_eval_fg:
+        from microtipi_b200 import WeightedConvolutionCost, DoubleShapedVectorSpace
+        f = WeightedConvolutionCost.build(DoubleShapedVectorSpace(N, N, nzl), device=local)
+        obj = np.zeros((nzl, N, N))
+        for dz_ in range(-2, 3):
+            for dy_ in range(-2, 3):
+                for dx_ in range(-2, 3):
+                    if dz_ * dz_ + dy_ * dy_ + dx_ * dx_ <= 6.25:
+                        obj[dz_ % nzl, dy_ % N, dx_ % N] = 1.0     # solid sphere, radius 2.5 px, centred at voxel 0
+        f.setPSF(obj)
+        del obj
+        f.setData(np.random.default_rng(7).random((nzl, N, N)) * 1e-6)
+        nf = max(3, min(args.steps, 10))
+        f.evalFG(m, m.PHASE, alpha)
+        fence()
+        t0 = time.perf_counter()
+        for i in range(nf):
+            cost, gfg = f.evalFG(m, m.PHASE, alpha + 1e-3 * (i % 7))
+        fg_ms = (time.perf_counter() - t0) * 1e3 / nf
+        assert np.isfinite(cost) and np.all(np.isfinite(gfg))
+        eval_fg = {"ms_per_eval": fg_ms, "value": nzg / (fg_ms * 1e-3), "unit": UNIT, "steps": nf,
+                   "h2d_bytes_per_step": 80, "d2h_bytes_per_step": 88,
+                   "note": "wfm_eval_fg: PSF + 3-D FFT convolution cost/gradient (12 volume sweeps) + Jacobian, host wall clock"}
+        f.close()
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -346,6 +377,8 @@ def run_b200(args):
                               "note": "whole step: 6*s*Npix bytes per plane over the step time (per GPU)"},
             "kernel_ms_per_step": {k: round(v, 5) for k, v in per.items()},
         }
+        if eval_fg:
+            out["eval_fg"] = eval_fg
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             planes = args.cpu_planes or max(128 * cores, 512)      # a few seconds of wall time = tens of core-seconds

@@ -149,6 +149,12 @@ WFM_API int wfm_psf_state(const wfm_model* h);
  * slab to host memory (double or float according to the handle's precision). */
 WFM_API int wfm_get_psf(wfm_model* h, void* out_host);
 WFM_API int wfm_get_cpx_psf(wfm_model* h, void* out_host);
+/* getPsf() with the device->host copy queued on the handle's second stream: returns at once, so that the copy
+ * overlaps the host->device copy of the next q (PCIe is full duplex).  out_host must be pinned
+ * (wfm_host_alloc) and stay valid until wfm_wait_transfers() returns; the next computePsf() is ordered
+ * after the copy.  wfm_wait_transfers blocks until every queued read-back has landed. */
+WFM_API int wfm_get_psf_async(wfm_model* h, void* out_host);
+WFM_API int wfm_wait_transfers(wfm_model* h);
 /* Device-resident views of the same arrays (valid until the next setter / destroy). */
 WFM_API int wfm_device_psf(wfm_model* h, void** dev_ptr);
 WFM_API int wfm_device_cpx_psf(wfm_model* h, void** dev_ptr);
@@ -172,6 +178,32 @@ WFM_API int wfm_apply_j_all(wfm_model* h, const void* q_host, double* out_defocu
  * one sum-allreduce across ranks.  Asynchronous on the handle's stream. */
 WFM_API int wfm_apply_jacobian_dev(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev);
 WFM_API int wfm_grad_length(const wfm_model* h);
+
+/* ---- "next" row f1: the FFT-convolution data term on the device ------------------------ */
+/* TiPi mitiv.conv.WeightedConvolutionCost as PSF_Estimation drives it (PSF_Estimation.java:147-150,157,206):
+ * the OBJECT is the kernel of the operator, the microscope PSF h is the variable,
+ *     cost = alpha/2 * sum w * (obj (*) h - y)^2,   grad = alpha * corr(obj, w * (obj (*) h - y))
+ * (periodic 3-D convolution at the data shape, offset {0,0,0}).  TiPi's source is not in the reference tree:
+ * these semantics are restated, parity unpinned.  fp64, nx == ny, nx and nz powers of two in [32, 2048]. */
+typedef struct wfm_conv wfm_conv;
+WFM_API int wfm_conv_create(wfm_conv** out, int nx, int ny, int nz, int precision, int device);
+WFM_API int wfm_conv_destroy(wfm_conv* c);
+WFM_API const char* wfm_conv_last_error(const wfm_conv* c);
+WFM_API int wfm_conv_set_stream(wfm_conv* c, void* cuda_stream);
+WFM_API int wfm_conv_set_object(wfm_conv* c, const void* obj_host);     /* fdata.setPSF(obj, off)   :148 */
+WFM_API int wfm_conv_set_data(wfm_conv* c, const void* data_host);      /* fdata.setData(data)      :149 */
+WFM_API int wfm_conv_set_weights(wfm_conv* c, const void* w_host);      /* fdata.setWeights(w,true) :150; NULL = 1 */
+/* fdata.computeCostAndGradient(alpha, psf, gcost, clr) :157,206 -- host buffers (synchronous) ... */
+WFM_API int wfm_conv_cost_and_gradient(wfm_conv* c, double alpha, const void* h_host, void* grad_host, int clr,
+                                       double* cost);
+/* ... and device-resident (asynchronous on the handle's stream; cost_dev may be NULL). */
+WFM_API int wfm_conv_cost_and_gradient_dev(wfm_conv* c, double alpha, const void* h_dev, void* grad_dev, int clr,
+                                           double* cost_dev);
+/* One COMPUTE_FG step of PSF_Estimation.fitPSF (PSF_Estimation.java:202-217) entirely on the device:
+ * setParam(x) -> computePsf() -> computeCostAndGradient(alpha, psf, gcost, true) -> apply_Jacobian(gcost, space).
+ * Only x (n doubles) crosses to the device; the cost and the n gradient doubles come back. */
+WFM_API int wfm_eval_fg(wfm_model* h, wfm_conv* c, int param, const double* x, int n, double alpha, double* cost,
+                        double* grad_out);
 
 /* ---- utilities ---------------------------------------------------------------------- */
 

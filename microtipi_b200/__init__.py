@@ -8,4 +8,6 @@ from ._capi import load_library, LIB_PATH  # noqa: F401
 from .wide_field_model import (DoubleShapedVector, DoubleShapedVectorSpace, MicroscopeModel, Shape,  # noqa: F401
                                WideFieldModel)
 
+from .convolution_cost import WeightedConvolutionCost  # noqa: F401,E402
+
 __version__ = "0.1"

@@ -61,9 +61,21 @@ SIGNATURES = {
     "wfm_apply_j_defocus": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "wfm_apply_j_modulus": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "wfm_apply_jacobian": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
+    "wfm_get_psf_async": (C.c_int, [_vp, _vp]),
+    "wfm_wait_transfers": (C.c_int, [_vp]),
     "wfm_apply_j_all": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "wfm_apply_jacobian_dev": (C.c_int, [_vp, C.c_uint, _vp, _vp]),
     "wfm_grad_length": (C.c_int, [_vp]),
+    "wfm_conv_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "wfm_conv_destroy": (C.c_int, [_vp]),
+    "wfm_conv_last_error": (C.c_char_p, [_vp]),
+    "wfm_conv_set_stream": (C.c_int, [_vp, _vp]),
+    "wfm_conv_set_object": (C.c_int, [_vp, _vp]),
+    "wfm_conv_set_data": (C.c_int, [_vp, _vp]),
+    "wfm_conv_set_weights": (C.c_int, [_vp, _vp]),
+    "wfm_conv_cost_and_gradient": (C.c_int, [_vp, C.c_double, _vp, _vp, C.c_int, _dp]),
+    "wfm_conv_cost_and_gradient_dev": (C.c_int, [_vp, C.c_double, _vp, _vp, C.c_int, _vp]),
+    "wfm_eval_fg": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_double, _dp, _vp]),
     "wfm_fill_uniform": (C.c_int, [_vp, _vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]),
     "wfm_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "wfm_host_free": (C.c_int, [_vp]),

@@ -43,6 +43,10 @@ struct wfm_model {
     int precision = WFM_F64;
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // second stream for wfm_get_psf_async: the D2H of the PSF runs beside the H2D of q (full-duplex PCIe)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_copied = nullptr;
+    bool copy_pending = false;
     // optics (WFM:161-166)
     bool have_optics = false;
     double NA = 0, lambda = 0, ni = 0, lambda_ni = 0, radius = 0, deltaX = 0, deltaY = 0;
@@ -324,6 +328,7 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
     a.T1 = (cx<T>*)h->scratch.p; a.cpx = (cx<T>*)h->cpx.p; a.psf = (T*)h->psf.p;
     PipeCtl ctl;
     rc = prepare_ctl(h, pp, ctl, pipe_roles()); if (rc) return rc;
+    if (h->copy_pending) WFM_CK(h, cudaStreamWaitEvent(h->stream, h->ev_copied, 0));   // psf is still being read out
     KernelSpan span(h, WFM_K_PSF);
     WFM_LAUNCH(kfn, dim3(pp.grid), dim3(Cfg::THREADS), Cfg::SMEM, h->stream, a, ctl);
     WFM_CK_LAUNCH(h, "k_psf_pipeline");
@@ -522,6 +527,9 @@ int wfm_destroy(wfm_model* h) {
         b->release();
     drain_spans(h);
     for (cudaEvent_t e : h->free_events) cudaEventDestroy(e);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+    if (h->ev_copied) cudaEventDestroy(h->ev_copied);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return WFM_OK;
@@ -776,6 +784,33 @@ int wfm_get_psf(wfm_model* h, void* out) {
     return copy_out(h, out, h->psf.p, (size_t)h->npix() * h->nzl * h->esz());
 }
 
+// getPsf() whose device->host copy runs on the handle's second stream: returns once the copy is queued.
+// `out` must stay valid (and should be pinned, wfm_host_alloc) until wfm_wait_transfers() returns.  The next
+// computePsf() on this handle is ordered after the copy, so the slab is never overwritten while it is read.
+int wfm_get_psf_async(wfm_model* h, void* out) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
+    int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1800-1802
+    if (!h->copy_stream) {
+        WFM_CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        WFM_CK(h, cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+        WFM_CK(h, cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+    }
+    WFM_CK(h, cudaEventRecord(h->ev_ready, h->stream));
+    WFM_CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
+    WFM_CK(h, cudaMemcpyAsync(out, h->psf.p, (size_t)h->npix() * h->nzl * h->esz(), cudaMemcpyDeviceToHost, h->copy_stream));
+    WFM_CK(h, cudaEventRecord(h->ev_copied, h->copy_stream));
+    h->copy_pending = true;
+    return WFM_OK;
+}
+
+int wfm_wait_transfers(wfm_model* h) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->copy_stream) WFM_CK(h, cudaStreamSynchronize(h->copy_stream));
+    h->copy_pending = false;
+    return check_pipeline(h);
+}
+
 int wfm_get_cpx_psf(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
     int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1857-1859
@@ -950,3 +985,5 @@ const char* wfm_version(void) {
 }
 
 }  // extern "C"
+
+#include "wfm_conv_api.inl"

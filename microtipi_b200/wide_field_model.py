@@ -516,6 +516,15 @@ class WideFieldModel(MicroscopeModel):
         self.psf = out
         return out
 
+    def getPsfAsync(self, out_ptr):
+        """getPsf() into a pinned host buffer (raw address) without waiting for the copy: it runs on the
+        handle's second stream beside the next host->device transfer.  Pair with waitTransfers()."""
+        self._call("wfm_get_psf_async", C.c_void_p(out_ptr))
+        self.PState = 1
+
+    def waitTransfers(self):
+        self._call("wfm_wait_transfers")
+
     def get_cpxPsf(self):                                                  # WFM:1856-1861
         if self.PState < 1:
             self.computePsf()

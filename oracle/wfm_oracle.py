@@ -601,6 +601,22 @@ def bead_cost_and_q(psf, O, data):
     return 0.5 * float(np.sum(resid * resid)), sfft.ifftn(np.conj(O) * sfft.fftn(resid)).real
 
 
+def weighted_convolution_cost(h, obj, data, weights=None, alpha=1.0):
+    """TiPi mitiv.conv.WeightedConvolutionCost as PSF_Estimation drives it (PSF_Estimation.java:147-150
+    build / setPSF(obj, off={0,0,0}) / setData / setWeights, :157,206 computeCostAndGradient(alpha, psf,
+    gcost, clr)): the OBJECT is the kernel of the operator and the PSF h is the variable,
+        cost = alpha/2 * sum w * (obj (*) h - data)^2,    grad = alpha * corr(obj, w * (obj (*) h - data))
+    with a periodic 3-D convolution at the data shape.  TiPi's source is not in the reference tree
+    (un-vendored, un-pinned): restated semantics, PARITY UNPINNED; pinned only by the finite-difference
+    known-answer test in tests/test_oracle.py.  Arrays are numpy (nz, ny, nx) = reference flat order."""
+    h = np.asarray(h, dtype=np.float64)
+    O = sfft.fftn(np.asarray(obj, dtype=np.float64))
+    r = sfft.ifftn(O * sfft.fftn(h)).real - np.asarray(data, dtype=np.float64)
+    wr = r if weights is None else np.asarray(weights, dtype=np.float64) * r
+    cost = 0.5 * alpha * float(np.sum(wr * r))
+    return cost, alpha * sfft.ifftn(np.conj(O) * sfft.fftn(wr)).real
+
+
 def bead_gradient_q(psf, psf_true, noise_sigma_rel=0.01, seed=7, radius_px=2.5):
     """q = d/dh 1/2 ||h (*) obj - data||^2 for the synthetic bead volume of SURVEY 8d2 (ii)
     (restating the role of TiPi's WeightedConvolutionCost at PSF_Estimation.java:147-157,206 with

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build", "libwfm_emu.so")
 SRCS = [os.path.join(ROOT, "microtipi_b200", "csrc", "wfm_api.cu")]
 DEPS = SRCS + [os.path.join(ROOT, "microtipi_b200", "csrc", f) for f in
-               ("wfm_kernels.cuh", "wfm_fft.cuh", "wfm_platform.cuh")] + [
+               ("wfm_kernels.cuh", "wfm_fft.cuh", "wfm_platform.cuh", "wfm_conv.cuh", "wfm_conv_api.inl")] + [
     os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "include", "wfm_b200.h")]
 
 

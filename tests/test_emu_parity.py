@@ -134,3 +134,60 @@ def test_fill_uniform_matches_oracle_generator(lib):
     m.fillUniform(buf.ctypes.data, seed=42, first_index=12345, count=n)   # emulated "device" memory is host memory
     np.testing.assert_array_equal(buf, o.splitmix64_uniform(42, 12345, n))
     m.close()
+
+
+def test_convolution_data_term_matches_oracle(lib):
+    # row f1 (TiPi WeightedConvolutionCost as PSF_Estimation.java:147-157 drives it): 3-D FFT convolution cost
+    # and gradient through the same kernel sources, with weights, alpha and the clr flag
+    from microtipi_b200 import WeightedConvolutionCost, DoubleShapedVectorSpace
+    rng = np.random.default_rng(11)
+    N, Nz = 32, 32
+    shp = (Nz, N, N)
+    obj, h, y = rng.normal(size=shp), rng.normal(size=shp), rng.normal(size=shp)
+    w = rng.uniform(0.0, 2.0, size=shp)
+    f = WeightedConvolutionCost.build(DoubleShapedVectorSpace(N, N, Nz), lib=lib)
+    f.setPSF(obj, (0, 0, 0)); f.setData(y); f.setWeights(w, True)
+    g = np.zeros(h.size)
+    c = f.computeCostAndGradient(0.7, h, g, True)
+    c_ref, g_ref = o.weighted_convolution_cost(h, obj, y, w, 0.7)
+    assert abs(c - c_ref) <= 1e-12 * abs(c_ref)
+    assert o.rel_l2(g, g_ref) <= 1e-12
+    c2 = f.computeCostAndGradient(0.7, h, g, False)                 # clr = false accumulates
+    assert c2 == c and o.rel_l2(g, 2 * g_ref) <= 1e-12
+    f.setWeights(None)
+    c3 = f.computeCostAndGradient(1.0, h, g, True)
+    c3_ref, g3_ref = o.weighted_convolution_cost(h, obj, y)
+    assert abs(c3 - c3_ref) <= 1e-12 * abs(c3_ref) and o.rel_l2(g, g3_ref) <= 1e-12
+    with pytest.raises(ValueError):
+        f.setPSF(obj, (1, 0, 0))
+    with pytest.raises(ValueError):
+        WeightedConvolutionCost.build(DoubleShapedVectorSpace(32, 64, 32), lib=lib)
+    f.close()
+
+
+def test_eval_fg_one_call_inner_loop(lib):
+    # wfm_eval_fg == setParam -> computePsf -> computeCostAndGradient -> apply_Jacobian (PSF_Estimation.java:202-217)
+    from microtipi_b200 import WeightedConvolutionCost, DoubleShapedVectorSpace
+    N, Nz = 32, 32
+    ref, m = make_pair(N, Nz, lib)
+    truth = o.WideFieldModelOracle((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"])
+    truth.setModulus([1.0, 0.1, -0.05, 0.02]); truth.setPhase(o.synthetic_alpha(10, seed=4321))
+    zz, yy, xx = np.meshgrid(*(np.arange(n) - n // 2 for n in (Nz, N, N)), indexing="ij")
+    obj = np.roll(((zz ** 2 + yy ** 2 + xx ** 2) <= 2.5 ** 2).astype(np.float64), (-(Nz // 2), -(N // 2), -(N // 2)), (0, 1, 2))
+    _, data = o.bead_problem((Nz, N, N), truth.getPsf())
+    f = WeightedConvolutionCost.build(DoubleShapedVectorSpace(N, N, Nz), lib=lib)
+    f.setPSF(obj); f.setData(data)
+    x = o.synthetic_alpha(10) + 0.01
+    cost, g = f.evalFG(m, m.PHASE, x)
+    ref.setPhase(x)
+    c_ref, q_ref = o.weighted_convolution_cost(ref.getPsf(), obj, data)
+    g_ref = ref.apply_J_phase(q_ref)
+    assert abs(cost - c_ref) <= 1e-11 * abs(c_ref)
+    assert o.rel_l2(g, g_ref) <= 1e-10          # conditioning of the chain (residual is a difference of near-equal volumes)
+    d = np.array([P["ni"] / P["lam"], 1e4, -1e4])
+    cost, g = f.evalFG(m, m.DEFOCUS, d)
+    ref.setDefocus(d)
+    c_ref, q_ref = o.weighted_convolution_cost(ref.getPsf(), obj, data)
+    assert abs(cost - c_ref) <= 1e-11 * abs(c_ref)
+    assert o.rel_l2(g, ref.apply_J_defocus(q_ref)) <= 1e-10
+    f.close(); m.close()

@@ -256,3 +256,78 @@ def test_config5_independent_models(lib, single):
         assert o.rel_l2(m.apply_J_phase(q).data, ref.apply_J_phase(q)) <= (20 * t if single else t)
     for m in models:
         m.close()
+
+
+def _bead_object(N, Nz, radius_px=2.5):
+    zz, yy, xx = np.meshgrid(*(np.arange(n) - n // 2 for n in (Nz, N, N)), indexing="ij")
+    obj = ((zz ** 2 + yy ** 2 + xx ** 2) <= radius_px ** 2).astype(np.float64)
+    return np.roll(obj, (-(Nz // 2), -(N // 2), -(N // 2)), axis=(0, 1, 2))
+
+
+@pytest.mark.parametrize("N,Nz", [(32, 32), (64, 128), (128, 64), (256, 32)])
+def test_convolution_data_term_matches_oracle(lib, N, Nz):
+    """Row f1: TiPi WeightedConvolutionCost as PSF_Estimation.java:147-157,206 drives it (restated, unpinned)."""
+    from microtipi_b200 import WeightedConvolutionCost, DoubleShapedVectorSpace
+    rng = np.random.default_rng(11)
+    shp = (Nz, N, N)
+    obj, h, y = rng.normal(size=shp), rng.normal(size=shp), rng.normal(size=shp)
+    w = rng.uniform(0.0, 2.0, size=shp)
+    f = WeightedConvolutionCost.build(DoubleShapedVectorSpace(N, N, Nz), lib=lib)
+    f.setPSF(obj, (0, 0, 0)); f.setData(y); f.setWeights(w, True)
+    g = np.zeros(h.size)
+    c = f.computeCostAndGradient(0.7, h, g, True)
+    c_ref, g_ref = o.weighted_convolution_cost(h, obj, y, w, 0.7)
+    assert abs(c - c_ref) <= 1e-12 * abs(c_ref)
+    assert o.rel_l2(g, g_ref) <= 1e-12
+    c2 = f.computeCostAndGradient(0.7, h, g, False)
+    assert c2 == c and o.rel_l2(g, 2 * g_ref) <= 1e-12
+    f.setWeights(None)
+    c3 = f.computeCostAndGradient(1.0, h, g, True)
+    c3_ref, g3_ref = o.weighted_convolution_cost(h, obj, y)
+    assert abs(c3 - c3_ref) <= 1e-12 * abs(c3_ref) and o.rel_l2(g, g3_ref) <= 1e-12
+    f.close()
+
+
+def test_eval_fg_inner_loop_matches_oracle_chain(lib):
+    """BASELINE config 3 (reduced): one COMPUTE_FG evaluation of PSF_Estimation.fitPSF entirely on the device."""
+    from microtipi_b200 import WeightedConvolutionCost, DoubleShapedVectorSpace
+    N, Nz = 128, 32
+    ref, m = make_pair(N, Nz, lib)
+    truth = o.WideFieldModelOracle((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"])
+    truth.setModulus(BETA4); truth.setPhase(o.synthetic_alpha(10, seed=4321))
+    obj = _bead_object(N, Nz)
+    _, data = o.bead_problem((Nz, N, N), truth.getPsf())
+    f = WeightedConvolutionCost.build(DoubleShapedVectorSpace(N, N, Nz), lib=lib)
+    f.setPSF(obj); f.setData(data)
+    for flag, x, refset, refj in (
+            (m.PHASE, o.synthetic_alpha(10) + 0.01, ref.setPhase, ref.apply_J_phase),
+            (m.DEFOCUS, np.array([P["ni"] / P["lam"], 1e4, -1e4]), ref.setDefocus, ref.apply_J_defocus),
+            (m.MODULUS, np.array([1.0, 0.12, -0.04, 0.03]), ref.setModulus, ref.apply_J_modulus)):
+        cost, g = f.evalFG(m, flag, x)
+        refset(x)
+        c_ref, q_ref = o.weighted_convolution_cost(ref.getPsf(), obj, data)
+        assert abs(cost - c_ref) <= 1e-11 * abs(c_ref)
+        assert o.rel_l2(g, refj(q_ref)) <= 1e-10
+    f.close(); m.close()
+
+
+def test_async_psf_readback_overlaps_and_orders(lib):
+    """wfm_get_psf_async + wfm_wait_transfers: same bytes as getPsf(); the next computePsf is ordered after the copy."""
+    N, Nz = 256, 32
+    ref, m = make_pair(N, Nz, lib)
+    nbytes = N * N * Nz * 8
+    hp = C.c_void_p()
+    assert lib.wfm_host_alloc(C.byref(hp), nbytes) == 0
+    out = np.frombuffer((C.c_char * nbytes).from_address(hp.value), dtype=np.float64)
+    q = o.synthetic_q(N, N, Nz)
+    m.getPsfAsync(hp.value)
+    g = m.apply_J_phase(q).data                 # H2D of q + Jacobian while the PSF is read back
+    a2 = o.synthetic_alpha(10) * 0.5
+    m.setPhase(a2); m.computePsf()              # must not overwrite the slab before the copy has finished
+    m.waitTransfers()
+    assert o.rel_l2(out, ref.getPsf()) <= 1e-12
+    assert o.rel_l2(g, ref.apply_J_phase(q)) <= 1e-12
+    ref.setPhase(a2)
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+    lib.wfm_host_free(hp)
+    m.close()

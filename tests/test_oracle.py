@@ -201,3 +201,32 @@ def test_blind_deconvolution_inner_loop_chain_rule():
         m.setPhase(ap); cp, _ = o.bead_cost_and_q(m.getPsf(), O, data)
         m.setPhase(am); cm, _ = o.bead_cost_and_q(m.getPsf(), O, data)
         assert abs((cp - cm) / (2 * h) - g[k]) <= 5e-6 * np.abs(g).max()
+
+
+def test_weighted_convolution_cost_gradient_is_exact():
+    # row f1: cost(h) = alpha/2 sum w (obj (*) h - y)^2 ; grad checked by central differences (the cost is
+    # quadratic in h, so central differences are exact up to rounding) and against the unweighted bead helper
+    rng = np.random.default_rng(5)
+    shp = (4, 8, 8)
+    obj, h, y = rng.normal(size=shp), rng.normal(size=shp), rng.normal(size=shp)
+    w = rng.uniform(0.0, 2.0, size=shp)
+    c0, g = o.weighted_convolution_cost(h, obj, y, w, alpha=0.7)
+    for idx in [(0, 0, 0), (3, 7, 1), (2, 4, 5)]:
+        e = np.zeros(shp); e[idx] = 1e-3
+        cp, _ = o.weighted_convolution_cost(h + e, obj, y, w, alpha=0.7)
+        cm, _ = o.weighted_convolution_cost(h - e, obj, y, w, alpha=0.7)
+        assert abs((cp - cm) / 2e-3 - g[idx]) <= 1e-9 * np.abs(g).max()
+    c1, g1 = o.weighted_convolution_cost(h, obj, y)
+    c2, g2 = o.bead_cost_and_q(h, sfft_fftn(obj), y)
+    assert abs(c1 - c2) <= 1e-12 * abs(c2) and o.rel_l2(g1, g2) <= 1e-13
+    # direct (non-FFT) periodic convolution at one voxel
+    k = (1, 2, 3)
+    direct = sum(obj[a, b, c] * h[(k[0] - a) % 4, (k[1] - b) % 8, (k[2] - c) % 8]
+                 for a in range(4) for b in range(8) for c in range(8))
+    conv = np.fft.ifftn(np.fft.fftn(obj) * np.fft.fftn(h)).real
+    assert abs(direct - conv[k]) <= 1e-12 * abs(direct)
+
+
+def sfft_fftn(a):
+    import scipy.fft
+    return scipy.fft.fftn(a)
