@@ -63,6 +63,7 @@ struct wfm_model {
     std::vector<uint8_t> h_map, h_zsup, h_esc;
     bool activity_dirty = true;
     int nax = 0, nay = 0, pitch = 0, ctile = 1;
+    bool narrow = false;                          // support inside [0,N/4) u [3N/4,N) on both axes ("narrow" kernels)
     DevBuf act_x, inv_x, act_y, inv_y, cell_list, in_list, Zs;
     bool basis_packed = false;
     DevBuf s_rho, s_phi, s_psi, s_flags;          // pupil strip [N][pitch]
@@ -204,6 +205,9 @@ int rebuild_activity(wfm_model* h) {
     if (ax.empty()) { ix[0] = 0; ax.push_back(0); }
     if (ay.empty()) { iy[0] = 0; ay.push_back(0); }
     h->nax = (int)ax.size(); h->nay = (int)ay.size();
+    h->narrow = getenv("WFM_NO_NARROW") == nullptr;
+    for (int x : ax) if (x >= N / 4 && x < N - N / 4) h->narrow = false;
+    for (int y : ay) if (y >= N / 4 && y < N - N / 4) h->narrow = false;
     const int C = h->precision == WFM_F64 ? col_tile<double>(N) : col_tile<float>(N);
     h->pitch = (h->nax + C - 1) / C * C;
     h->ctile = C;
@@ -248,7 +252,7 @@ int pack_strip(wfm_model* h) {
     WFM_CK(h, h->s_psi.ensure(8 * cells)); WFM_CK(h, h->s_flags.ensure(cells));
     KernelSpan span(h, WFM_K_SETTERS);
     auto kfn = &k_pack_strip;
-    WFM_LAUNCH(kfn, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, h->stream, (double*)h->s_rho.p,
+    WFM_LAUNCH_PDL(kfn, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, h->stream, (double*)h->s_rho.p,
                (double*)h->s_phi.p, (double*)h->s_psi.p, (uint8_t*)h->s_flags.p, (const double*)h->rho.p,
                (const double*)h->phi.p, (const double*)h->psi.p, (const uint8_t*)h->mask.p,
                (const uint8_t*)h->support.p, (const int*)h->act_x.p, h->N, h->nax, h->pitch, h->ctile);
@@ -312,7 +316,10 @@ int pipe_roles() {
 // ---- computePsf ---------------------------------------------------------------------------------
 template <typename T, int N> int launch_psf(wfm_model* h) {
     using Cfg = PipeCfg<T, N>;
-    auto kfn = &k_psf_pipeline<T, N>;
+    auto kfn = &k_psf_pipeline<T, N, false>;
+    if constexpr (Plan<N>::R1 == 8) {
+        if (h->narrow) kfn = &k_psf_pipeline<T, N, true>;       // legs 2..5 of the first stages are zero: pruned kernels
+    }
     int rc = set_smem(h, kfn, Cfg::SMEM); if (rc) return rc;
     rc = pack_strip(h); if (rc) return rc;
     const int nA = h->pitch / Cfg::C, nB = N / Cfg::ROWS_PER_ITEM;
@@ -330,7 +337,7 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
     rc = prepare_ctl(h, pp, ctl, pipe_roles()); if (rc) return rc;
     if (h->copy_pending) WFM_CK(h, cudaStreamWaitEvent(h->stream, h->ev_copied, 0));   // psf is still being read out
     KernelSpan span(h, WFM_K_PSF);
-    WFM_LAUNCH(kfn, dim3(pp.grid), dim3(Cfg::THREADS), Cfg::SMEM, h->stream, a, ctl);
+    WFM_LAUNCH_PDL(kfn, dim3(pp.grid), dim3(Cfg::THREADS), Cfg::SMEM, h->stream, a, ctl);
     WFM_CK_LAUNCH(h, "k_psf_pipeline");
     h->pipe_checks++;
     return WFM_OK;
@@ -339,7 +346,10 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
 // ---- apply_J_* ------------------------------------------------------------------------------------
 template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev) {
     using Cfg = PipeCfg<T, N>;
-    auto kfn = &k_jac_pipeline<T, N>;
+    auto kfn = &k_jac_pipeline<T, N, false>;
+    if constexpr (Plan<N>::RL >= 4) {
+        if (h->narrow) kfn = &k_jac_pipeline<T, N, true>;       // outputs outside the legs that can hit the support are skipped
+    }
     int rc = set_smem(h, kfn, Cfg::SMEM); if (rc) return rc;
     rc = pack_strip(h); if (rc) return rc;
     const int nA = N / Cfg::ROWS_PER_ITEM, nB = h->pitch / Cfg::C;
@@ -363,7 +373,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         PipeCtl ctl;
         rc = prepare_ctl(h, pp, ctl, pipe_roles()); if (rc) return rc;
         KernelSpan span(h, WFM_K_JAC);
-        WFM_LAUNCH(kfn, dim3(pp.grid), dim3(Cfg::THREADS), Cfg::SMEM, h->stream, a, ctl);
+        WFM_LAUNCH_PDL(kfn, dim3(pp.grid), dim3(Cfg::THREADS), Cfg::SMEM, h->stream, a, ctl);
         WFM_CK_LAUNCH(h, "k_jac_pipeline");
         h->pipe_checks++;
     }
@@ -390,7 +400,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * nchunks * r.glen));
         r.block_part = (double*)h->block_part.p;
         auto kred = &k_jac_reduce;
-        WFM_LAUNCH(kred, dim3(nblocks, nchunks), dim3(WFM_RED_THREADS), 0, h->stream, r);
+        WFM_LAUNCH_PDL(kred, dim3(nblocks, nchunks), dim3(WFM_RED_THREADS), 0, h->stream, r);
         WFM_CK_LAUNCH(h, "k_jac_reduce");
         double nbeta = 0.0;
         if (h->nmod > 0) {
@@ -399,7 +409,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
             nbeta = 1.0 / std::sqrt(s);                                        // WFM:435
         }
         auto kfin = &k_jac_final;
-        WFM_LAUNCH(kfin, dim3(r.glen), dim3(WFM_FINAL_THREADS), 0, h->stream, (const double*)r.block_part,
+        WFM_LAUNCH_PDL(kfin, dim3(r.glen), dim3(WFM_FINAL_THREADS), 0, h->stream, (const double*)r.block_part,
                    nblocks * nchunks, r.glen, h->nphase, a.g.psf_norm, h->beta, nbeta, kinds, grad_dev);
         WFM_CK_LAUNCH(h, "k_jac_final");
     }

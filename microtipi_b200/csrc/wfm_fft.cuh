@@ -91,6 +91,27 @@ template <typename T, int R> struct Dft {
     }
 };
 
+// Radix-8 DFT whose inputs 2..5 are structurally zero (the pupil occupies the legs {0, 1, 6, 7} of the first
+// stage when it fits the central half of the frequency axis, see PipeCfg / "narrow" kernels):
+//   v[k] = a0 + i^k a6 + W8^k a1 + W8^-k a7 = p[k mod 4] + c_k (a1 + a7) - i s_k (a1 - a7)
+// 32 additions + 4 multiplications instead of 48 + 8.
+template <typename T> WFM_DEVI void dft8_in0167(cx<T> (&v)[8]) {
+    const T h = (T)0.70710678118654752440084436210484903928;
+    const cx<T> a0 = v[0], a1 = v[1], a6 = v[6], a7 = v[7];
+    const cx<T> p0 = cadd(a0, a6), p2 = csub(a0, a6);
+    const cx<T> p1 = mkc<T>(a0.x - a6.y, a0.y + a6.x);     // a0 + i a6
+    const cx<T> p3 = mkc<T>(a0.x + a6.y, a0.y - a6.x);     // a0 - i a6
+    const cx<T> S = cadd(a1, a7), D = csub(a1, a7);
+    const cx<T> U = mkc<T>(h * S.x, h * S.y);               // h S
+    const cx<T> V = mkc<T>(h * D.y, -(h * D.x));            // -i h D
+    const cx<T> W = mkc<T>(D.y, -D.x);                      // -i D
+    const cx<T> A = cadd(U, V), B = csub(V, U);
+    v[0] = cadd(p0, S); v[4] = csub(p0, S);
+    v[2] = cadd(p2, W); v[6] = csub(p2, W);
+    v[1] = cadd(p1, A); v[5] = csub(p1, A);
+    v[3] = cadd(p3, B); v[7] = csub(p3, B);
+}
+
 // ---- plans ---------------------------------------------------------------------------------
 template <int N_, int E_, int R1_, int R2_, int R3_> struct PlanBase {
     static constexpr int N = N_, E = E_, R1 = R1_, R2 = R2_, R3 = R3_;
@@ -191,9 +212,12 @@ struct NoHook { WFM_DEVI void operator()() const {} };
 
 // Hook: callable run once by every thread right after the first exchange barrier (used by the
 // pipelines to claim the next work item while two thirds of the transform are still ahead).
-template <typename T, class P, class L, class S, class Hook = NoHook>
+// SPARSE1: the caller guarantees that the stage-1 legs 2..5 of every butterfly are zero (R1 == 8 only); their
+// slots in v are ignored.
+template <typename T, class P, class L, class S, class Hook = NoHook, bool SPARSE1 = false>
 WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* tw, const cx<T>* tw2,
                           const int sync_id, const Hook& hook = Hook()) {
+    static_assert(!SPARSE1 || P::R1 == 8, "sparse first stage is a radix-8 special case");
     constexpr int E = P::E, R1 = P::R1, R2 = P::R2, R3 = P::R3, TT = P::T, S1 = P::S1;
     // stage 1: radix R1 over legs of stride S1, twiddle W_N^(b*k1), scatter to cell k1*S1 + b
 #pragma unroll
@@ -201,7 +225,8 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
         cx<T> a[R1];
 #pragma unroll
         for (int r = 0; r < R1; ++r) a[r] = v[u * R1 + r];
-        Dft<T, R1>::run(a);
+        if constexpr (SPARSE1) dft8_in0167<T>(reinterpret_cast<cx<T>(&)[8]>(a));
+        else Dft<T, R1>::run(a);
         const int b = t + TT * u;
         sm[L::at(b)] = a[0];
         const cx<T> w = tw[b];

@@ -116,6 +116,7 @@ __global__ void k_compute_defocus(double* __restrict__ psi, uint8_t* __restrict_
 __global__ void k_set_phase(double* __restrict__ phi, const double* __restrict__ Z,
                             const uint8_t* __restrict__ mask, Coefs alpha, int n, int off, int npix) {
     const int in = blockIdx.x * blockDim.x + threadIdx.x;
+    wfm_grid_dep_trigger();
     if (in >= npix) return;
     double acc = 0.0;
     if (mask[in]) {
@@ -243,6 +244,8 @@ __global__ void k_pack_strip(double* __restrict__ s_rho, double* __restrict__ s_
                              const uint8_t* __restrict__ mask, const uint8_t* __restrict__ support,
                              const int* __restrict__ act_x, int N, int nax, int pitch, int C) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    wfm_grid_dep_trigger();
+    wfm_grid_dep_wait();
     if (cell >= N * pitch) return;
     const int tile = cell / (N * C), rem = cell % (N * C);
     const int ky = rem / C, xi = tile * C + rem % C;
@@ -472,7 +475,13 @@ template <typename T> struct PsfArgs {
 
 // A-item: active columns xi0 .. xi0+C-1 of plane pl.  A = rho*exp(i(phi + defoc_scale*psi)) is
 // synthesised in the load (WFM:311-316; sincos only where rho != 0, quirk Q6), then FFT along y.
-template <typename T, int N>
+// NARROW: every active row and column lies in [0, N/4) u [3N/4, N) -- the first-stage legs 2..5 (of 8) of both
+// passes are structurally zero, so they are neither loaded nor transformed (fft_inplace SPARSE1).
+// The same holds for the outputs the Jacobian needs: only the last-stage legs r < R/4 or r >= R - R/4 can hit the
+// support, so the others are neither stored (row items) nor multiplied out (column items).
+template <int R, bool NARROW> WFM_DEVI constexpr bool leg_live(int r) { return !NARROW || r < R / 4 || r >= R - R / 4; }
+
+template <typename T, int N, bool NARROW>
 WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
                             const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
@@ -485,7 +494,8 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r)
-            rho[u * P::R1 + r] = __ldg(&a.st.rho[((size_t)sub * N + (t + TT * u) + P::S1 * r) * C + c]);
+            if (leg_live<P::R1, NARROW>(r))
+                rho[u * P::R1 + r] = __ldg(&a.st.rho[((size_t)sub * N + (t + TT * u) + P::S1 * r) * C + c]);
     cx<T> v[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u) {
@@ -493,17 +503,20 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
         for (int r = 0; r < P::R1; ++r) {
             const int e = u * P::R1 + r;
             cx<T> val = mkc<T>((T)0, (T)0);
-            if (rho[e] != 0.0) {
-                const size_t cell = ((size_t)sub * N + (t + TT * u) + P::S1 * r) * C + c;
-                const double ph = __dadd_rn(__ldg(&a.st.phi[cell]), __dmul_rn(s, __ldg(&a.st.psi[cell])));
-                double sn, cs;
-                WFM_SINCOS(ph, &sn, &cs);
-                val = mkc<T>((T)__dmul_rn(rho[e], cs), (T)__dmul_rn(rho[e], sn));
+            if (leg_live<P::R1, NARROW>(r)) {
+                if (rho[e] != 0.0) {
+                    const size_t cell = ((size_t)sub * N + (t + TT * u) + P::S1 * r) * C + c;
+                    const double ph = __dadd_rn(__ldg(&a.st.phi[cell]), __dmul_rn(s, __ldg(&a.st.psi[cell])));
+                    double sn, cs;
+                    WFM_SINCOS(ph, &sn, &cs);
+                    val = mkc<T>((T)__dmul_rn(rho[e], cs), (T)__dmul_rn(rho[e], sn));
+                }
             }
             v[e] = val;
         }
     }
-    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + N, 0, PipePrefetchHook{qu, ctl, a.g.nzl});
+    fft_inplace<T, P, L, CtaSync, PipePrefetchHook, NARROW>(v, cells + c, t, tw_s, tw_s + N, 0,
+                                                            PipePrefetchHook{qu, ctl, a.g.nzl});
     pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
     cx<T>* dst = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)sub * N * C + c;
 #pragma unroll
@@ -515,7 +528,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
 // B-item: ROWS_PER_ITEM rows of plane pl (each TT-thread group walks KR of them): FFT along x
 // (inactive columns are zero), then the fused streaming store of conj(a) and |a|^2*PSFnorm
 // (WFM:323-328) as full contiguous rows.  No CTA-wide barrier inside.
-template <typename T, int N>
+template <typename T, int N, bool NARROW>
 WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
                             const int* invx_s, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
@@ -529,6 +542,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r) {
+            if (!leg_live<P::R1, NARROW>(r)) { xis[u * P::R1 + r] = -1; continue; }
             const int xi = invx_s[(t + TT * u) + P::S1 * r];
             xis[u * P::R1 + r] = xi >= 0 ? (xi / C) * N * C + xi % C : -1;
         }
@@ -537,7 +551,8 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
     {
         const cx<T>* src0 = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)(sub * Cfg::ROWS_PER_ITEM + slot) * C;
 #pragma unroll
-        for (int e = 0; e < E; ++e) nv[e] = (xis[e] >= 0) ? __ldcg(&src0[xis[e]]) : mkc<T>((T)0, (T)0);
+        for (int e = 0; e < E; ++e)
+            if (leg_live<P::R1, NARROW>(e % P::R1)) nv[e] = (xis[e] >= 0) ? __ldcg(&src0[xis[e]]) : mkc<T>((T)0, (T)0);
     }
 #endif
 #pragma unroll 1
@@ -548,17 +563,19 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
         cx<T> v[E];
 #if WFM_ROW_PREFETCH
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = nv[e];
+        for (int e = 0; e < E; ++e) v[e] = leg_live<P::R1, NARROW>(e % P::R1) ? nv[e] : mkc<T>((T)0, (T)0);
         if (kk + 1 < Cfg::KR) {
             const cx<T>* nsrc = src + (size_t)C * C;
 #pragma unroll
-            for (int e = 0; e < E; ++e) nv[e] = (xis[e] >= 0) ? __ldcg(&nsrc[xis[e]]) : mkc<T>((T)0, (T)0);
+            for (int e = 0; e < E; ++e)
+                if (leg_live<P::R1, NARROW>(e % P::R1)) nv[e] = (xis[e] >= 0) ? __ldcg(&nsrc[xis[e]]) : mkc<T>((T)0, (T)0);
         }
 #else
 #pragma unroll
-        for (int e = 0; e < E; ++e) v[e] = (xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
+        for (int e = 0; e < E; ++e)
+            v[e] = (leg_live<P::R1, NARROW>(e % P::R1) && xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
 #endif
-        fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
+        fft_inplace<T, P, L, RowSync<TT>, NoHook, NARROW>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
         const size_t base = (size_t)pl * N * N + (size_t)N * ky;
 #pragma unroll
         for (int u = 0; u < E / P::RL; ++u)
@@ -576,7 +593,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
     }
 }
 
-template <typename T, int N>
+template <typename T, int N, bool NARROW>
 __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k_psf_pipeline(PsfArgs<T> a, PipeCtl ctl) {
     using Cfg = PipeCfg<T, N>;
     WFM_DYN_SMEM(cx<T>, cells);
@@ -585,6 +602,8 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
+    wfm_grid_dep_trigger();  // the next kernel's CTAs may take the place of ours as we exit
+    wfm_grid_dep_wait();     // the tables above are constants; everything below depends on the previous kernel
     __shared__ unsigned s_queue[4];
     PipeQueue qu;
     const int P = a.g.nzl;
@@ -597,14 +616,14 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                psf_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, dep, qu, ctl);
+                psf_cols_item<T, N, NARROW>(a, it.plane, it.sub, ctl.ring, cells, tw_s, dep, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                psf_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, qu, ctl);
+                psf_rows_item<T, N, NARROW>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntB[it.plane]);
@@ -634,7 +653,7 @@ template <typename T> struct JacArgs {
 
 // A-item: ROWS_PER_ITEM rows of plane pl (each TT-thread group walks KR of them).  Aq = conj(a)*q
 // fused into the streaming load (WFM:907-914), FFT along x, keep the active kx only.
-template <typename T, int N>
+template <typename T, int N, bool NARROW>
 WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
                             const int* invx_s, const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
@@ -648,6 +667,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
         for (int r = 0; r < P::RL; ++r) {
+            if (!leg_live<P::RL, NARROW>(r)) { xis[u * P::RL + r] = -1; continue; }
             const int xi = invx_s[(t + TT * u) + P::SL * r];
             xis[u * P::RL + r] = xi >= 0 ? (xi / C) * N * C + xi % C : -1;
         }
@@ -707,7 +727,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
         cx<T>* dst = a.T2 + (size_t)(pl % ring) * N * a.pitch + (size_t)y * C;
 #pragma unroll
         for (int e = 0; e < E; ++e)
-            if (xis[e] >= 0) __stcg(&dst[xis[e]], v[e]);
+            if (leg_live<P::RL, NARROW>(e % P::RL) && xis[e] >= 0) __stcg(&dst[xis[e]], v[e]);
         if (kk + 1 < Cfg::KR) RowSync<TT>::sync(slot);
     }
 }
@@ -716,7 +736,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 // shared by the three Jacobians, written per plane (summed over z by k_jac_reduce in fixed order):
 //   jin = rho*(B_re sin ph + B_im cos ph)   on maskPupil   (WFM:925-928, 1253)
 //   J   = B_re cos ph - B_im sin ph         on the support (WFM:607-611)
-template <typename T, int N>
+template <typename T, int N, bool NARROW>
 WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
                             PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
@@ -741,7 +761,8 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
         for (int r = 0; r < P::RL; ++r)
-            fl |= (unsigned)__ldg(&a.st.flags[tbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
+            if (leg_live<P::RL, NARROW>(r))
+                fl |= (unsigned)__ldg(&a.st.flags[tbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
     fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + N, 0, PipePrefetchHook{qu, ctl, a.g.nzl});
     const int iz = a.g.z0 + pl;
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
@@ -753,6 +774,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 #pragma unroll
         for (int r = 0; r < P::RL; ++r) {
             const int e = u * P::RL + r;
+            if (!leg_live<P::RL, NARROW>(r)) continue;
             const unsigned f = (fl >> (2 * e)) & want;
             if (!f) continue;
             const size_t cell = tbase + (size_t)((t + TT * u) + P::SL * r) * C;
@@ -766,7 +788,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
         }
 }
 
-template <typename T, int N>
+template <typename T, int N, bool NARROW>
 __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB_JAC) k_jac_pipeline(JacArgs<T> a, PipeCtl ctl) {
     using Cfg = PipeCfg<T, N>;
     WFM_DYN_SMEM(cx<T>, cells);
@@ -775,6 +797,8 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB_JA
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
+    wfm_grid_dep_trigger();  // the next kernel's CTAs may take the place of ours as we exit
+    wfm_grid_dep_wait();     // the tables above are constants; everything below depends on the previous kernel
     __shared__ unsigned s_queue[4];
     PipeQueue qu;
     const int P = a.g.nzl;
@@ -787,14 +811,14 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB_JA
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                jac_rows_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, dep, qu, ctl);
+                jac_rows_item<T, N, NARROW>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, dep, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                jac_cols_item<T, N>(a, it.plane, it.sub, ctl.ring, cells, tw_s, qu, ctl);
+                jac_cols_item<T, N, NARROW>(a, it.plane, it.sub, ctl.ring, cells, tw_s, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntB[it.plane]);
@@ -846,23 +870,34 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     const size_t img = (size_t)N * a.pitch;
     const int li = blockIdx.x * WFM_RED_THREADS + threadIdx.x;
     const bool sup = li < a.ncells;                    // every listed cell lies on the support
-    const size_t cell = sup ? (size_t)a.cell_list[li] : 0;
+    const size_t cell = sup ? (size_t)a.cell_list[li] : 0;      // (index lists: constant since the last basis change)
     const int in = sup ? a.in_list[li] : 0;
+    wfm_grid_dep_trigger();
+    wfm_grid_dep_wait();                               // Gj / Gm come from the pipeline kernel before us
     const bool m = sup && (a.flags[cell] & 1u);
     const int p0 = blockIdx.y * WFM_RED_PLANES;
     const int p1 = (p0 + WFM_RED_PLANES < a.g.nzl) ? p0 + WFM_RED_PLANES : a.g.nzl;
     double gP = 0.0, gD = 0.0, gM = 0.0;
     if (m) {
-#pragma unroll 4
-        for (int pl = p0; pl < p1; ++pl) {
-            const double jin = a.Gj[(size_t)pl * img + cell];
-            gP += jin;
-            gD += defoc_depth_dev(a.g.z0 + pl, a.g.nz_global, a.g.dz) * jin;
+        // all loads of the chunk in flight at once (the kernel is latency-bound: one DRAM round trip per thread
+        // instead of four; measured 41 -> 35 us per step at 512^2 x 256), then the fixed-order sums
+        double jin[WFM_RED_PLANES];
+#pragma unroll
+        for (int k = 0; k < WFM_RED_PLANES; ++k) jin[k] = (p0 + k < p1) ? __ldcs(&a.Gj[(size_t)(p0 + k) * img + cell]) : 0.0;
+#pragma unroll
+        for (int k = 0; k < WFM_RED_PLANES; ++k) {
+            gP += jin[k];
+            gD += defoc_depth_dev(a.g.z0 + p0 + k, a.g.nz_global, a.g.dz) * jin[k];
         }
     }
     if (sup && (a.kinds & 4u)) {
-        for (int pl = p0; pl < p1; ++pl)
-            if (!a.last_plane_only || a.g.z0 + pl == a.g.nz_global - 1) gM += a.Gm[(size_t)pl * img + cell];
+        double jm[WFM_RED_PLANES];
+#pragma unroll
+        for (int k = 0; k < WFM_RED_PLANES; ++k)
+            jm[k] = (p0 + k < p1 && (!a.last_plane_only || a.g.z0 + p0 + k == a.g.nz_global - 1))
+                        ? __ldcs(&a.Gm[(size_t)(p0 + k) * img + cell]) : 0.0;
+#pragma unroll
+        for (int k = 0; k < WFM_RED_PLANES; ++k) gM += jm[k];
     }
     // defocus weights: idef = 1/psi on maskPupil (WFM:1251); rx, ry of the prologue WFM:1040-1061
     double wD = 0.0, rx = 0.0, ry = 0.0;
@@ -926,6 +961,7 @@ __global__ void __launch_bounds__(WFM_FINAL_THREADS) k_jac_final(const double* _
     __shared__ double red[WFM_FINAL_THREADS / 32];
     const int j = blockIdx.x;
     double x = 0.0;
+    wfm_grid_dep_wait();
     for (int b = threadIdx.x; b < nblocks; b += WFM_FINAL_THREADS) x += block_part[(size_t)b * glen + j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);

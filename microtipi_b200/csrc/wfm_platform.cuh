@@ -8,6 +8,7 @@
 #ifndef WFM_EMU
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cstdlib>
 
 namespace wfm {
 inline std::atomic<unsigned long long>& launch_counter() {
@@ -28,6 +29,33 @@ __device__ __forceinline__ void wfm_prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with WFM_LAUNCH_PDL may become resident while its
+// predecessor on the stream is still draining; it must execute wfm_grid_dep_wait() before its first access
+// to anything the predecessor reads or writes (everything before that point -- twiddle tables into shared
+// memory, index set-up -- overlaps the predecessor's tail and the launch latency).
+__device__ __forceinline__ void wfm_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the next PDL kernel on the stream be scheduled as soon as this grid leaves room for it (it still blocks in
+// wfm_grid_dep_wait() until this grid has completed and its writes are visible).
+__device__ __forceinline__ void wfm_grid_dep_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+namespace wfm {
+template <class K, class... Args>
+inline void launch_pdl(K kfn, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool off = getenv("WFM_NO_PDL") != nullptr;       // experiment / debugging switch
+    cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, kfn, args...);
+}
+}  // namespace wfm
+#define WFM_LAUNCH_PDL(kfn, grid, block, smem, stream, ...)                \
+    do {                                                                   \
+        ::wfm::launch_counter()++;                                         \
+        ::wfm::launch_pdl(kfn, (grid), (block), (smem), (stream), __VA_ARGS__); \
+    } while (0)
 
 #define WFM_LAUNCH(kfn, grid, block, smem, stream, ...)                    \
     do {                                                                   \

@@ -301,6 +301,8 @@ static inline int atomicAdd(int* addr, int v) { return __atomic_fetch_add(addr, 
 #define WFM_SPIN_PAUSE() std::this_thread::sleep_for(std::chrono::microseconds(50))
 
 static inline void wfm_prefetch_l2(const void*, unsigned) {}
+static inline void wfm_grid_dep_wait() {}
+static inline void wfm_grid_dep_trigger() {}
 
 // dynamic shared memory of the running CTA
 #define WFM_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::cur()->smem)
@@ -309,3 +311,4 @@ static inline void wfm_prefetch_l2(const void*, unsigned) {}
 #define WFM_LAUNCH(kfn, grid, block, smem, stream, ...)                                   \
     do { emu::launch_counter()++; (void)(stream);                                          \
          emu::launch((grid), (block), (smem), [&]() { kfn(__VA_ARGS__); }); } while (0)
+#define WFM_LAUNCH_PDL WFM_LAUNCH

@@ -3,7 +3,7 @@ import re, subprocess, sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = os.path.join(ROOT, "microtipi_b200", "csrc", "wfm_api.cu")
 out = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-                      "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", src, "-o", "/tmp/_ptxas_report.so"],
+                      "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"] + os.environ.get("WFM_BUILD_FLAGS", "").split() + [src, "-o", "/tmp/_ptxas_report.so"],
                      capture_output=True, text=True).stderr
 pat = sys.argv[1] if len(sys.argv) > 1 else "pipeline"
 cur = None
