@@ -347,14 +347,18 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
 template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev) {
     using Cfg = PipeCfg<T, N>;
     auto kfn = &k_jac_pipeline<T, N, false>;
+    int ctas_per_sm = Cfg::template minb_jac<false>();
     if constexpr (Plan<N>::RL >= 4) {
-        if (h->narrow) kfn = &k_jac_pipeline<T, N, true>;       // outputs outside the legs that can hit the support are skipped
+        if (h->narrow) {                                        // outputs outside the legs that can hit the support are skipped
+            kfn = &k_jac_pipeline<T, N, true>;
+            ctas_per_sm = Cfg::template minb_jac<true>();
+        }
     }
     int rc = set_smem(h, kfn, Cfg::SMEM); if (rc) return rc;
     rc = pack_strip(h); if (rc) return rc;
     const int nA = N / Cfg::ROWS_PER_ITEM, nB = h->pitch / Cfg::C;
     const size_t plane_bytes = sizeof(cx<T>) * (size_t)N * h->pitch;
-    const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, Cfg::MINB_JAC);
+    const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, ctas_per_sm);
     WFM_CK(h, h->scratch.ensure(plane_bytes * pp.ring));
     const size_t img = (size_t)N * h->pitch;
     WFM_CK(h, h->Gj.ensure(sizeof(double) * img * h->nzl));

@@ -337,6 +337,13 @@ template <typename T, int N> struct PipeCfg {
 #else
     static constexpr int MINB_JAC = (sizeof(T) == 8 && MINB >= 4) ? (3 * MINB) / 4 : MINB;
 #endif
+    // The narrow Jacobian kernel (4 instead of 8 strip offsets and output predicates per thread) would fit 64
+    // registers with 8 bytes of spill, but the full CTA count measured slower (0.841 vs 0.832 ms/step, A/B/A/B).
+#ifdef WFM_PIPE_MINB_JAC_NARROW
+    template <bool NARROW> static constexpr int minb_jac() { return NARROW ? WFM_PIPE_MINB_JAC_NARROW : MINB_JAC; }
+#else
+    template <bool NARROW> static constexpr int minb_jac() { return MINB_JAC; }
+#endif
 };
 
 struct PipeItem { int type; int plane; int sub; };   // type 0 = A, 1 = B, -1 = done
@@ -789,7 +796,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 }
 
 template <typename T, int N, bool NARROW>
-__global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB_JAC) k_jac_pipeline(JacArgs<T> a, PipeCtl ctl) {
+__global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::template minb_jac<NARROW>()) k_jac_pipeline(JacArgs<T> a, PipeCtl ctl) {
     using Cfg = PipeCfg<T, N>;
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
