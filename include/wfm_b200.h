@@ -155,6 +155,14 @@ WFM_API int wfm_get_cpx_psf(wfm_model* h, void* out_host);
  * after the copy.  wfm_wait_transfers blocks until every queued read-back has landed. */
 WFM_API int wfm_get_psf_async(wfm_model* h, void* out_host);
 WFM_API int wfm_wait_transfers(wfm_model* h);
+/* "next" row f4.  ArrayUtils.roll(pupil.getPsf()) of BlindDeconvJob.java:100: the PSF with its origin moved from
+ * voxel (0,0,0) to the centre of the volume, out[(i + n/2) mod n] = in[i] on every axis; host copy and
+ * device-resident variant (whole stack on one handle).  getMtf() WFM:1807-1828 as intended (the reference loop
+ * never terminates, quirk Q8): the unnormalised 3-D DFT of the PSF, interleaved complex (2,Nx,Ny,Nz); fp64,
+ * Nz a power of two in [32, 2048]. */
+WFM_API int wfm_get_psf_rolled(wfm_model* h, void* out_host);
+WFM_API int wfm_roll_psf_dev(wfm_model* h, void* out_dev);
+WFM_API int wfm_get_mtf(wfm_model* h, void* out_host);
 /* Device-resident views of the same arrays (valid until the next setter / destroy). */
 WFM_API int wfm_device_psf(wfm_model* h, void** dev_ptr);
 WFM_API int wfm_device_cpx_psf(wfm_model* h, void** dev_ptr);

@@ -61,6 +61,9 @@ SIGNATURES = {
     "wfm_apply_j_defocus": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "wfm_apply_j_modulus": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "wfm_apply_jacobian": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
+    "wfm_get_psf_rolled": (C.c_int, [_vp, _vp]),
+    "wfm_roll_psf_dev": (C.c_int, [_vp, _vp]),
+    "wfm_get_mtf": (C.c_int, [_vp, _vp]),
     "wfm_get_psf_async": (C.c_int, [_vp, _vp]),
     "wfm_wait_transfers": (C.c_int, [_vp]),
     "wfm_apply_j_all": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),

@@ -825,6 +825,36 @@ int wfm_wait_transfers(wfm_model* h) {
     return check_pipeline(h);
 }
 
+// ArrayUtils.roll(pupil.getPsf()) (BlindDeconvJob.java:100) -- "next" row f4: the centred PSF, shifted on the device.
+int wfm_roll_psf_dev(wfm_model* h, void* out_dev) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!out_dev) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
+    if (h->z0 != 0 || h->nzl != h->nz_global)
+        return h->fail(WFM_ERR_UNSUPPORTED, "the rolled PSF needs the whole stack on one handle (z roll crosses slabs)");
+    int rc = compute_psf_impl(h); if (rc) return rc;
+    const size_t vox = (size_t)h->npix() * h->nzl;
+    const unsigned grid = (unsigned)((vox + 255) / 256);
+    if (h->precision == WFM_F64) {
+        auto kfn = &k_roll3<double>;
+        WFM_LAUNCH(kfn, dim3(grid), dim3(256), 0, h->stream, (double*)out_dev, (const double*)h->psf.p, h->N, h->N, h->nzl);
+    } else {
+        auto kfn = &k_roll3<float>;
+        WFM_LAUNCH(kfn, dim3(grid), dim3(256), 0, h->stream, (float*)out_dev, (const float*)h->psf.p, h->N, h->N, h->nzl);
+    }
+    WFM_CK_LAUNCH(h, "k_roll3");
+    return WFM_OK;
+}
+
+int wfm_get_psf_rolled(wfm_model* h, void* out) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
+    WFM_CK(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->npix() * h->nzl * h->esz();
+    WFM_CK(h, h->qdev.ensure(bytes));                    // reuse the q staging buffer
+    int rc = wfm_roll_psf_dev(h, h->qdev.p); if (rc) return rc;
+    return copy_out(h, out, h->qdev.p, bytes);
+}
+
 int wfm_get_cpx_psf(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
     int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1857-1859

@@ -94,7 +94,14 @@ ConvArgs<double> conv_args(wfm_conv* c) {
 
 extern "C" {
 
+static int conv_create_impl(wfm_conv** out, int nx, int ny, int nz, int precision, int device, bool lite);
+
 int wfm_conv_create(wfm_conv** out, int nx, int ny, int nz, int precision, int device) {
+    return conv_create_impl(out, nx, ny, nz, precision, device, false);
+}
+
+// lite: only the work volume and the twiddles (3-D transform helper of wfm_get_mtf)
+static int conv_create_impl(wfm_conv** out, int nx, int ny, int nz, int precision, int device, bool lite) {
     if (!out) { g_create_error = "out is NULL"; return WFM_ERR_INVALID_ARG; }
     *out = nullptr;
     if (nx != ny) { g_create_error = "Nx should equal Ny"; return WFM_ERR_INVALID_ARG; }
@@ -113,8 +120,8 @@ int wfm_conv_create(wfm_conv** out, int nx, int ny, int nz, int precision, int d
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(WFM_ERR_CUDA, "cudaStreamCreate failed");
     c->stream = c->own_stream;
     const size_t vox = c->vox();
-    if (c->V.ensure(16 * vox) || c->X.ensure(16 * vox) || c->y.ensure(8 * vox) || c->cost_dev.ensure(8) ||
-        c->cost_part.ensure(8 * ((size_t)ny * nz + 8)))
+    if (c->V.ensure(16 * vox) || c->cost_dev.ensure(8) || c->cost_part.ensure(8 * ((size_t)ny * nz + 8)) ||
+        (!lite && (c->X.ensure(16 * vox) || c->y.ensure(8 * vox))))
         return bail(WFM_ERR_NOMEM, "device allocation failed");
     if (conv_upload_twiddles(c, c->twx, nx) != WFM_OK || conv_upload_twiddles(c, c->twz, nz) != WFM_OK)
         return bail(WFM_ERR_CUDA, "twiddle upload failed");
@@ -280,6 +287,34 @@ int wfm_eval_fg(wfm_model* h, wfm_conv* c, int param, const double* x, int n, do
     const int len = (param == WFM_DEFOCUS) ? n : (param == WFM_PHASE ? h->nphase : h->nmod);
     memcpy(grad_out, g.data() + off, 8 * (size_t)len);
     return WFM_OK;
+}
+
+// getMtf() WFM:1807-1828 as intended: FFT3 of the PSF (DoubleFFT_3D.complexForward on the zero-imaginary copy).
+int wfm_get_mtf(wfm_model* h, void* out_host) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!out_host) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
+    if (h->precision != WFM_F64) return h->fail(WFM_ERR_UNSUPPORTED, "getMtf is fp64 only in this revision");
+    if (h->z0 != 0 || h->nzl != h->nz_global) return h->fail(WFM_ERR_UNSUPPORTED, "getMtf needs the whole stack on one handle");
+    if (!supported_n(h->nz_global)) return h->fail(WFM_ERR_UNSUPPORTED, "getMtf needs Nz to be a power of two in [32, 2048]");
+    int rc = compute_psf_impl(h); if (rc) return rc;
+    wfm_conv* c = nullptr;
+    rc = conv_create_impl(&c, h->N, h->N, h->nz_global, WFM_F64, h->device, true);
+    if (rc) return h->fail(rc, "%s", g_create_error.c_str());
+    c->stream = h->stream;
+    ConvArgs<double> a = conv_args(c);
+    a.real_in = (const double*)h->psf.p;
+    a.Xout = (double2*)c->V.p;
+    if (!(rc = conv_rows_n<CL_REAL, CS_CPLX>(c, a)) && !(rc = conv_cols_n<CS_CPLX>(c, a, 1)) &&
+        !(rc = conv_cols_n<CS_CPLX>(c, a, 2))) {
+        cudaError_t e = cudaMemcpyAsync(out_host, c->V.p, 16 * c->vox(), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = h->fail(WFM_ERR_CUDA, "MTF copy failed: %s", cudaGetErrorString(e));
+    } else {
+        h->fail(rc, "%s", c->err.c_str());
+    }
+    c->stream = c->own_stream;
+    wfm_conv_destroy(c);
+    return rc ? rc : check_pipeline(h);
 }
 
 }  // extern "C"

@@ -225,6 +225,18 @@ __global__ void k_fill_uniform(T* __restrict__ out, uint64_t seed, uint64_t firs
     out[i] = (T)__dsub_rn(__dmul_rn(2.0, u), 1.0);
 }
 
+// ArrayUtils.roll(psf) (BlindDeconvJob.java:100): the PSF is computed with its origin at voxel (0,0,0); callers
+// that want it centred shift every axis by half its length: out[(i + n/2) mod n] = in[i].
+template <typename T>
+__global__ void k_roll3(T* __restrict__ out, const T* __restrict__ in, int nx, int ny, int nz) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t vox = (size_t)nx * ny * nz;
+    if (i >= vox) return;
+    const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((size_t)nx * ny));
+    const int xo = (x + nx / 2) % nx, yo = (y + ny / 2) % ny, zo = (z + nz / 2) % nz;
+    out[xo + (size_t)nx * (yo + (size_t)ny * zo)] = in[i];
+}
+
 // ================================================================================================
 // Pupil strip: rho, phi, psi and the mask/support flags gathered into the compact [N][pitch] layout
 // of the active columns, so that a column tile reads them as contiguous, independent loads.

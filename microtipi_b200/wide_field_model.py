@@ -533,7 +533,19 @@ class WideFieldModel(MicroscopeModel):
         return out
 
     def getMtf(self):                                                      # WFM:1807-1828
-        raise NotImplementedError("getMtf never terminates in the reference (i=i++, WFM:1814); out of scope")
+        """The 3-D DFT of the PSF, shape (Nz, Ny, Nx, 2) -- what the reference's getMtf() is written to return
+        (its copy loop `i = i++` never terminates, quirk Q8; the intended result is implemented)."""
+        out = np.empty((self.nz_local, self.Ny, self.Nx, 2), dtype=np.float64)
+        self._call("wfm_get_mtf", out.ctypes.data_as(C.c_void_p))
+        self.PState = 1
+        return out
+
+    def getPsfRolled(self):
+        """ArrayUtils.roll(getPsf()) (BlindDeconvJob.java:100): the PSF centred in the volume."""
+        out = np.empty((self.nz_local, self.Ny, self.Nx), dtype=self._dtype())
+        self._call("wfm_get_psf_rolled", out.ctypes.data_as(C.c_void_p))
+        self.PState = 1
+        return out
 
     def getZernike(self, k=None):                                          # WFM:1834 / 1849
         Z = np.empty((self.Nzern, self._npix()))

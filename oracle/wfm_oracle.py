@@ -601,6 +601,21 @@ def bead_cost_and_q(psf, O, data):
     return 0.5 * float(np.sum(resid * resid)), sfft.ifftn(np.conj(O) * sfft.fftn(resid)).real
 
 
+def roll_psf(psf):
+    """ArrayUtils.roll(psf) as BlindDeconvJob.java:100 uses it: origin moved from voxel 0 to the centre of every
+    axis, out[(i + n/2) mod n] = in[i] (TiPi source unavailable: assumed, unambiguous for the even sizes used)."""
+    psf = np.asarray(psf)
+    return np.roll(psf, tuple(n // 2 for n in psf.shape), axis=tuple(range(psf.ndim)))
+
+
+def mtf(psf):
+    """getMtf() WFM:1807-1828 as intended (the reference's copy loop `i = i++` never terminates, quirk Q8):
+    DoubleFFT_3D.complexForward of the PSF with zero imaginary part = unnormalised 3-D DFT, returned
+    interleaved (..., 2) like the reference's (2,Nx,Ny,Nz) array."""
+    F = sfft.fftn(np.asarray(psf, dtype=np.float64))
+    return np.stack([F.real, F.imag], axis=-1)
+
+
 def weighted_convolution_cost(h, obj, data, weights=None, alpha=1.0):
     """TiPi mitiv.conv.WeightedConvolutionCost as PSF_Estimation drives it (PSF_Estimation.java:147-150
     build / setPSF(obj, off={0,0,0}) / setData / setWeights, :157,206 computeCostAndGradient(alpha, psf,

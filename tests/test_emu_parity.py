@@ -191,3 +191,36 @@ def test_eval_fg_one_call_inner_loop(lib):
     assert abs(cost - c_ref) <= 1e-11 * abs(c_ref)
     assert o.rel_l2(g, ref.apply_J_defocus(q_ref)) <= 1e-10
     f.close(); m.close()
+
+
+def test_rolled_psf_and_mtf(lib):
+    # row f4: ArrayUtils.roll(getPsf()) (BlindDeconvJob.java:100) and the intended getMtf() (WFM:1807-1828)
+    ref, m = make_pair(32, 32, lib)
+    psf = ref.getPsf()
+    np.testing.assert_array_equal(m.getPsfRolled(), o.roll_psf(m.getPsf()))
+    assert o.rel_l2(m.getPsfRolled(), o.roll_psf(psf)) <= 1e-12
+    assert o.rel_l2(m.getMtf(), o.mtf(psf)) <= 1e-12
+    assert abs(m.getMtf()[0, 0, 0, 0] - psf.sum()) <= 1e-12          # DC term = total energy (= sum rho^2)
+    m.close()
+    sl = WideFieldModel((32, 32, 32), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, False, lib=lib,
+                        z0=8, nz_local=8)
+    with pytest.raises(RuntimeError):
+        sl.getPsfRolled()                                           # z roll crosses slabs
+    sl.close()
+
+
+def test_wide_pupil_uses_generic_kernels(lib):
+    # pupil radius > N/4: the "narrow" (pruned first-stage) kernels must not be selected; both paths match the oracle
+    N, Nz = 64, 3
+    big = dict(P); big["dxy"] = 2.2 * P["dxy"]
+    ref = o.WideFieldModelOracle((N, N, Nz), 10, 4, big["NA"], big["lam"], big["ni"], big["dxy"], big["dz"])
+    m = WideFieldModel((N, N, Nz), 10, 4, big["NA"], big["lam"], big["ni"], big["dxy"], big["dz"], False, False, lib=lib,
+                       basis=lambda nz: o.compute_zernike(nz, N, N, big["NA"], big["lam"], big["dxy"]))
+    for mm in (ref, m):
+        mm.setPhase(o.synthetic_alpha(10)); mm.setModulus([1.0, 0.1, -0.05, 0.02])
+    assert m.activeExtent()[0] > N // 2
+    q = o.synthetic_q(N, N, Nz)
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+    assert o.rel_l2(m.apply_J_phase(q).data, ref.apply_J_phase(q)) <= 1e-12
+    assert o.rel_l2(m.apply_J_defocus(q).data, ref.apply_J_defocus(q)) <= 1e-12
+    m.close()

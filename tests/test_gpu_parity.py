@@ -331,3 +331,31 @@ def test_async_psf_readback_overlaps_and_orders(lib):
     assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
     lib.wfm_host_free(hp)
     m.close()
+
+
+@pytest.mark.parametrize("N,Nz", [(64, 32), (256, 64)])
+def test_rolled_psf_and_mtf(lib, N, Nz):
+    """Row f4: ArrayUtils.roll(getPsf()) (BlindDeconvJob.java:100) and the intended getMtf() (WFM:1807-1828)."""
+    ref, m = make_pair(N, Nz, lib)
+    psf = ref.getPsf()
+    np.testing.assert_array_equal(m.getPsfRolled(), o.roll_psf(m.getPsf()))
+    assert o.rel_l2(m.getPsfRolled(), o.roll_psf(psf)) <= 1e-12
+    assert o.rel_l2(m.getMtf(), o.mtf(psf)) <= 1e-12
+    m.close()
+
+
+def test_generic_kernels_when_the_pupil_is_wide(lib):
+    """A pupil wider than N/4 switches the pruned ("narrow") kernels off: both variants must agree with the oracle."""
+    N, Nz = 128, 8
+    big = dict(P); big["dxy"] = 2.2 * P["dxy"]                     # pupil radius 0.37 N > N/4
+    ref = o.WideFieldModelOracle((N, N, Nz), 10, 4, big["NA"], big["lam"], big["ni"], big["dxy"], big["dz"])
+    m = WideFieldModel((N, N, Nz), 10, 4, big["NA"], big["lam"], big["ni"], big["dxy"], big["dz"], False, False, lib=lib,
+                       basis=lambda nz: o.compute_zernike(nz, N, N, big["NA"], big["lam"], big["dxy"]))
+    for mm in (ref, m):
+        mm.setPhase(o.synthetic_alpha(10)); mm.setModulus(BETA4)
+    assert m.activeExtent()[0] > N // 2
+    q = o.synthetic_q(N, N, Nz)
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+    for a, b in zip(m.apply_J_all(q), (ref.apply_J_defocus(q), ref.apply_J_phase(q), ref.apply_J_modulus(q))):
+        assert o.rel_l2(a, b) <= 1e-12
+    m.close()
