@@ -250,6 +250,17 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
 #pragma unroll
             for (int r = 0; r < R2; ++r) a[r] = sm[L::at(base + r * R3)];
             Dft<T, R2>::run(a);
+#ifdef WFM_FAKE_NO_X2   /* timing experiment only (wrong results): what would the step cost without the second exchange? */
+            const cx<T> w = tw2[d3];
+            cx<T> wk = w;
+            v[u * R2] = a[0];
+#pragma unroll
+            for (int k = 1; k < R2; ++k) {
+                v[u * R2 + k] = cmul(a[k], wk);
+                if (k + 1 < R2) wk = cmul(wk, w);
+            }
+        }
+#else
             sm[L::at(base)] = a[0];
             const cx<T> w = tw2[d3];            // compact table tw2[d] = W_N^(R1*d): adjacent lanes, adjacent cells
             cx<T> wk = w;
@@ -260,6 +271,7 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
             }
         }
         S::sync(sync_id);
+#endif
         // stage 3: radix R3 over adjacent cells; butterfly b = k1 + R1*k2 -> X[b + (N/R3)*r]
 #pragma unroll
         for (int u = 0; u < E / R3; ++u) {
@@ -267,8 +279,14 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
             const int k1 = b % R1, k2 = b / R1;
             const int base = k1 * S1 + k2 * R3;
             cx<T> a[R3];
+#ifdef WFM_FAKE_NO_X2
+#pragma unroll
+            for (int r = 0; r < R3; ++r) a[r] = v[u * R3 + r];
+            (void)base;
+#else
 #pragma unroll
             for (int r = 0; r < R3; ++r) a[r] = sm[L::at(base + r)];
+#endif
             Dft<T, R3>::run(a);
 #pragma unroll
             for (int r = 0; r < R3; ++r) v[u * R3 + r] = a[r];

@@ -472,6 +472,24 @@ struct PipePrefetchHook {
 };
 WFM_DEVI void pipe_wait(const PipeDep& d) { if (d.cnt) pipe_wait(d.cnt, d.target, d.err); }
 
+// (slot, t) of a thread of a row item: which row transform of the CTA it belongs to and its index inside it.
+// With two warps per transform (TT = 64) and four transforms per CTA the two warps of a transform are w and
+// w + 4, i.e. they live on the same SM sub-partition (warp w is scheduled by sub-partition w % 4): the scheduler
+// that parks one of them at the exchange barrier is the one running its partner.
+#ifndef WFM_ROW_SAME_SMSP
+#define WFM_ROW_SAME_SMSP 0
+#endif
+template <int C, int TT> WFM_DEVI void row_thread_map(int& slot, int& t) {
+    if constexpr (WFM_ROW_SAME_SMSP && TT == 64 && C == 4) {
+        const int w = threadIdx.x >> 5;
+        slot = w & 3;
+        t = ((w >> 2) << 5) + (threadIdx.x & 31);
+    } else {
+        slot = threadIdx.x / TT;
+        t = threadIdx.x % TT;
+    }
+}
+
 // ================================================================================================
 // computePsf()  WFM:280-350 (fp32: 209-278)
 //
@@ -554,7 +572,8 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
     using L = RowLayout<T, N>;
     using Cfg = PipeCfg<T, N>;
     constexpr int C = Cfg::C, TT = P::T, E = P::E;
-    const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
+    int slot, t;
+    row_thread_map<C, TT>(slot, t);
     const T norm = (T)a.g.psf_norm;
     int xis[E];                                        // strip offset of column x (without the ky term) or -1
 #pragma unroll
@@ -679,7 +698,8 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
     using L = RowLayout<T, N>;
     using Cfg = PipeCfg<T, N>;
     constexpr int C = Cfg::C, TT = P::T, E = P::E;
-    const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
+    int slot, t;
+    row_thread_map<C, TT>(slot, t);
     pipe_wait(dep);                                    // ring slot free? (rarely taken: probed at claim time)
     int xis[E];                                        // strip offset of column kx (without the y term) or -1
 #pragma unroll
