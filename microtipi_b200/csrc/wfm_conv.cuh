@@ -9,13 +9,18 @@
 // TiPi's source is not in the reference tree (un-vendored, un-pinned): PARITY UNPINNED -- the
 // semantics above are the documented ones and are checked against the oracle and by finite differences.
 //
-// 3-D FFTs are separable passes over a complex work volume V[Nz][Ny][Nx]:
-//   x pass : rows, RowLayout, 4 rows per 256-thread CTA, named barrier per row (same engine as the PSF path)
-//   y pass : columns inside a plane, ColLayout tiles of CW adjacent x
-//   z pass : columns of the [Nz][Npix] matrix, ColLayout tiles of CW adjacent pixels
+// Every array here is real, so the transforms work on the HALF spectrum: the x pass reads a real row of Nx samples
+// as Nx/2 complex numbers z[j] = h[2j] + i h[2j+1], transforms them with the half-length plan and untangles the
+// result into the Nx/2+1 non-redundant coefficients (the mirror element comes through the row's shared cells).
+// The work volume is V[Nz][Ny][P] complex, P = Nx/2 + 8 (entries kx = 0..Nx/2, then zero padding up to a
+// multiple of the column tile), i.e. half the bytes of a complex volume on every later pass:
+//   x pass : rows (real <-> half spectrum), RowLayout, one transform per T-thread group
+//   y pass : columns inside a plane, ColLayout tiles of CW adjacent kx
+//   z pass : columns of the [Nz][Ny*P] matrix, ColLayout tiles of CW adjacent entries
 // Inverse transforms use IFFT(v) = conj(FFT(conj(v)))/Ntot; the conjugations, the spectral products
 // with X = FFT3(obj), the residual, the weights, the cost reduction and the final real part are all
-// fused into the load / store of the neighbouring passes, so one evaluation is 12 sweeps of the volume.
+// fused into the load / store of the neighbouring passes, so one evaluation is 12 sweeps of the half volume.
+// (k_conv_rows, the full complex x pass, is kept for wfm_get_mtf, which returns the whole spectrum.)
 #pragma once
 #include "wfm_kernels.cuh"
 
@@ -40,6 +45,8 @@ template <typename T> struct ConvArgs {
     T* grad;              // CS_GRAD destination
     double* cost_part;    // [gridDim.x] per-CTA partial sums of w r^2
     const cx<T>* tw;      // twiddles of this pass's length
+    const cx<T>* twn;     // r2c / c2r rows: W_Nx^k, k < Nx/2
+    T* resid;             // c2r CS_RESID destination: w * r as a real volume
     int nx, ny, nz;
     double inv_ntot, alpha;
     int clear_grad;       // CS_GRAD: 1 = overwrite, 0 = accumulate (TiPi's `clr` flag)
@@ -118,6 +125,133 @@ __global__ void __launch_bounds__(RowCfg<N>::THREADS) k_conv_rows(ConvArgs<T> a)
 #pragma unroll
             for (int r = 0; r < P::RL; ++r)
                 conv_store<T, STORE>(a, base + (t + TT * u) + P::SL * r, v[u * P::RL + r], cost_acc);
+    }
+    if constexpr (STORE == CS_RESID) conv_cost_reduce(cost_acc, &a.cost_part[blockIdx.x]);
+}
+
+// ---- x pass on real data -------------------------------------------------------------------------------
+__host__ __device__ constexpr int conv_pitch(int nx) { return nx / 2 + 8; }
+
+template <int M> struct ConvRowSmem {
+    template <typename T> static constexpr size_t bytes() {
+        return sizeof(cx<T>) * ((size_t)RowCfg<M>::RB * RowLayout<T, M>::LEN + 2 * (size_t)M + 16);
+    }
+};
+
+// real row -> half spectrum.  STORE: CS_CPLX (-> V) or CS_SPECTRUM (-> Xout)
+//   Z = FFT_M(z), z[j] = h[2j] + i h[2j+1];  H[k] = 1/2 [(Z[k] + conj Z[M-k]) - i W_N^k (Z[k] - conj Z[M-k])], k < M;
+//   H[M] = Re Z[0] - Im Z[0]
+template <typename T, int N, int STORE>
+__global__ void __launch_bounds__(RowCfg<N / 2>::THREADS) k_conv_rows_r2c(ConvArgs<T> a) {
+    constexpr int M = N / 2;
+    using P = Plan<M>;
+    using L = RowLayout<T, M>;
+    constexpr int RB = RowCfg<M>::RB, TT = P::T, E = P::E;
+    WFM_DYN_SMEM(cx<T>, cells);
+    cx<T>* tw_s = cells + RB * L::LEN;
+    cx<T>* twn_s = tw_s + M + 16;
+    for (int i = threadIdx.x; i < M; i += RowCfg<M>::THREADS) { tw_s[i] = a.tw[i]; twn_s[i] = a.twn[i]; }
+    if (threadIdx.x < P::R3) tw_s[M + threadIdx.x] = a.tw[P::R1 * threadIdx.x];
+    __syncthreads();
+    const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
+    const size_t nrows = (size_t)a.ny * a.nz;
+    const size_t row = (size_t)blockIdx.x * RB + slot;
+    const bool valid = row < nrows;
+    const cx<T>* src = reinterpret_cast<const cx<T>*>(a.real_in + (valid ? row : 0) * N);
+    cx<T> v[E];
+#pragma unroll
+    for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+        for (int r = 0; r < P::R1; ++r)
+            v[u * P::R1 + r] = valid ? src[(t + TT * u) + P::S1 * r] : mkc<T>((T)0, (T)0);
+    cx<T>* sm = cells + slot * L::LEN;
+    fft_inplace<T, P, L, RowSync<TT>>(v, sm, t, tw_s, tw_s + M, slot);
+    RowSync<TT>::sync(slot);                           // the last stage has read the cells: reuse them for the mirror
+#pragma unroll
+    for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+        for (int r = 0; r < P::RL; ++r) sm[L::at((t + TT * u) + P::SL * r)] = v[u * P::RL + r];
+    RowSync<TT>::sync(slot);
+    if (!valid) return;
+    cx<T>* out = (STORE == CS_SPECTRUM ? a.Xout : a.V) + row * (size_t)conv_pitch(N);
+#pragma unroll
+    for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+        for (int r = 0; r < P::RL; ++r) {
+            const int k = (t + TT * u) + P::SL * r;
+            const cx<T> Z = v[u * P::RL + r], Zm = sm[L::at((M - k) & (M - 1))], w = twn_s[k];
+            const T sx = Z.x + Zm.x, sy = Z.y - Zm.y;              // Z + conj(Zm)
+            const T dx = Z.x - Zm.x, dy = Z.y + Zm.y;              // Z - conj(Zm)
+            const T px = w.x * dy + w.y * dx, py = w.y * dy - w.x * dx;   // -i w (Z - conj Zm)
+            out[k] = mkc<T>((T)0.5 * (sx + px), (T)0.5 * (sy + py));
+            if (k == 0) out[M] = mkc<T>(Z.x - Z.y, (T)0);
+        }
+    for (int i = t; i < 7; i += TT) out[M + 1 + i] = mkc<T>((T)0, (T)0);   // padding up to the pitch
+}
+
+// half spectrum -> real row, fed with V = conj(G) (the inverse passes run forward transforms on conjugates):
+//   c[k] = (V[k] + conj V[M-k]) - i W_N^k (V[k] - conj V[M-k]);  w = FFT_M(c);  g[2j] = Re w[j], g[2j+1] = -Im w[j]
+// STORE: CS_RESID (r = g/Ntot - y; cost += w r^2; resid = w r) or CS_GRAD (grad = alpha g/Ntot)
+template <typename T, int N, int STORE>
+__global__ void __launch_bounds__(RowCfg<N / 2>::THREADS) k_conv_rows_c2r(ConvArgs<T> a) {
+    constexpr int M = N / 2;
+    using P = Plan<M>;
+    using L = RowLayout<T, M>;
+    constexpr int RB = RowCfg<M>::RB, TT = P::T, E = P::E;
+    WFM_DYN_SMEM(cx<T>, cells);
+    cx<T>* tw_s = cells + RB * L::LEN;
+    cx<T>* twn_s = tw_s + M + 16;
+    for (int i = threadIdx.x; i < M; i += RowCfg<M>::THREADS) { tw_s[i] = a.tw[i]; twn_s[i] = a.twn[i]; }
+    if (threadIdx.x < P::R3) tw_s[M + threadIdx.x] = a.tw[P::R1 * threadIdx.x];
+    __syncthreads();
+    const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
+    const size_t nrows = (size_t)a.ny * a.nz;
+    const size_t row = (size_t)blockIdx.x * RB + slot;
+    const bool valid = row < nrows;
+    const cx<T>* in = a.V + (valid ? row : 0) * (size_t)conv_pitch(N);
+    cx<T> v[E];
+#pragma unroll
+    for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+        for (int r = 0; r < P::R1; ++r) {
+            const int k = (t + TT * u) + P::S1 * r;
+            cx<T> c = mkc<T>((T)0, (T)0);
+            if (valid) {
+                const cx<T> V = in[k], Vm = in[M - k], w = twn_s[k];
+                const T sx = V.x + Vm.x, sy = V.y - Vm.y;
+                const T dx = V.x - Vm.x, dy = V.y + Vm.y;
+                c = mkc<T>(sx + (w.x * dy + w.y * dx), sy + (w.y * dy - w.x * dx));
+            }
+            v[u * P::R1 + r] = c;
+        }
+    fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, tw_s + M, slot);
+    double cost_acc = 0.0;
+    if (valid) {
+        const size_t base = row * N;
+#pragma unroll
+        for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+            for (int r = 0; r < P::RL; ++r) {
+                const int j = (t + TT * u) + P::SL * r;
+                const cx<T> wv = v[u * P::RL + r];
+                const double g0 = (double)wv.x * a.inv_ntot, g1 = -(double)wv.y * a.inv_ntot;
+                const size_t idx = base + 2 * (size_t)j;
+                if constexpr (STORE == CS_RESID) {
+                    const cx<T> yv = *reinterpret_cast<const cx<T>*>(a.y + idx);
+                    cx<T> wt = mkc<T>((T)1, (T)1);
+                    if (a.w) wt = *reinterpret_cast<const cx<T>*>(a.w + idx);
+                    const double r0 = g0 - (double)yv.x, r1 = g1 - (double)yv.y;
+                    cost_acc += (double)wt.x * r0 * r0 + (double)wt.y * r1 * r1;
+                    *reinterpret_cast<cx<T>*>(a.resid + idx) = mkc<T>((T)((double)wt.x * r0), (T)((double)wt.y * r1));
+                } else {
+                    cx<T> g = mkc<T>((T)(a.alpha * g0), (T)(a.alpha * g1));
+                    if (!a.clear_grad) {
+                        const cx<T> old = *reinterpret_cast<const cx<T>*>(a.grad + idx);
+                        g = mkc<T>(old.x + g.x, old.y + g.y);
+                    }
+                    *reinterpret_cast<cx<T>*>(a.grad + idx) = g;
+                }
+            }
     }
     if constexpr (STORE == CS_RESID) conv_cost_reduce(cost_acc, &a.cost_part[blockIdx.x]);
 }

@@ -7,10 +7,13 @@ struct wfm_conv {
     int precision = WFM_F64;
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    DevBuf V, X, y, w, hdev, gdev, cost_part, cost_dev, twx, twz;
+    DevBuf V, X, y, w, R, hdev, gdev, cost_part, cost_dev, twx, twz, twh, twn;
+    bool lite = false;                  // full complex work volume only (wfm_get_mtf)
     bool have_obj = false, have_data = false, have_w = false;
     std::string err;
     size_t vox() const { return (size_t)nx * ny * nz; }
+    int pitch() const { return conv_pitch(nx); }
+    size_t hvox() const { return (size_t)pitch() * ny * nz; }      // entries of the half-spectrum volume
     size_t esz() const { return precision == WFM_F64 ? 8 : 4; }
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -22,10 +25,12 @@ struct wfm_conv {
 
 namespace {
 
-int conv_upload_twiddles(wfm_conv* c, DevBuf& dst, int n) {
+// dst[m] = exp(-2 pi i m / period), m < n
+int conv_upload_twiddles(wfm_conv* c, DevBuf& dst, int n, int period = 0) {
+    if (period == 0) period = n;
     std::vector<double2> t(n);
     for (int m = 0; m < n; ++m) {
-        long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)n;
+        long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)period;
         t[m].x = (double)cosl(a); t[m].y = (double)(-sinl(a));
     }
     WFM_CK(c, dst.ensure(sizeof(double2) * n));
@@ -45,14 +50,41 @@ template <typename T, int N, int LOAD, int STORE> int conv_rows(wfm_conv* c, Con
     return WFM_OK;
 }
 
-// axis 1: columns inside each plane (length ny == nx == N); axis 2: columns along z (length nz)
-template <typename T, int LEN, int STORE> int conv_cols(wfm_conv* c, ConvArgs<T> a, int axis) {
+template <typename T, int N, int STORE> int conv_rows_r2c(wfm_conv* c, ConvArgs<T> a) {
+    constexpr int M = N / 2;
+    auto kfn = &k_conv_rows_r2c<T, N, STORE>;
+    const size_t smem = ConvRowSmem<M>::template bytes<T>();
+    if (smem > 48 * 1024) WFM_CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t nrows = (size_t)a.ny * a.nz;
+    const unsigned grid = (unsigned)((nrows + RowCfg<M>::RB - 1) / RowCfg<M>::RB);
+    a.tw = (const cx<T>*)c->twh.p; a.twn = (const cx<T>*)c->twn.p;
+    WFM_LAUNCH(kfn, dim3(grid), dim3(RowCfg<M>::THREADS), smem, c->stream, a);
+    WFM_CK_LAUNCH(c, "k_conv_rows_r2c");
+    return WFM_OK;
+}
+template <typename T, int N, int STORE> int conv_rows_c2r(wfm_conv* c, ConvArgs<T> a, int* nparts) {
+    constexpr int M = N / 2;
+    auto kfn = &k_conv_rows_c2r<T, N, STORE>;
+    const size_t smem = ConvRowSmem<M>::template bytes<T>();
+    if (smem > 48 * 1024) WFM_CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t nrows = (size_t)a.ny * a.nz;
+    const unsigned grid = (unsigned)((nrows + RowCfg<M>::RB - 1) / RowCfg<M>::RB);
+    if (nparts) *nparts = (int)grid;
+    a.tw = (const cx<T>*)c->twh.p; a.twn = (const cx<T>*)c->twn.p;
+    WFM_LAUNCH(kfn, dim3(grid), dim3(RowCfg<M>::THREADS), smem, c->stream, a);
+    WFM_CK_LAUNCH(c, "k_conv_rows_c2r");
+    return WFM_OK;
+}
+
+// axis 1: columns inside each plane (length ny == nx == N); axis 2: columns along z (length nz).  `pitch` = entries
+// per row of the volume (nx for the full complex volume, conv_pitch(nx) for the half spectrum).
+template <typename T, int LEN, int STORE> int conv_cols(wfm_conv* c, ConvArgs<T> a, int axis, int pitch) {
     using Cfg = ConvColCfg<T, LEN>;
     auto kfn = &k_conv_cols<T, LEN, STORE>;
     if (Cfg::SMEM > 48 * 1024) WFM_CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    const size_t npix = (size_t)a.nx * a.ny;
+    const size_t npix = (size_t)pitch * a.ny;
     size_t stride, outer_stride; int tiles_per_outer; size_t nouter;
-    if (axis == 1) { stride = a.nx; tiles_per_outer = a.nx / Cfg::CW; outer_stride = npix; nouter = a.nz; a.tw = (const cx<T>*)c->twx.p; }
+    if (axis == 1) { stride = pitch; tiles_per_outer = pitch / Cfg::CW; outer_stride = npix; nouter = a.nz; a.tw = (const cx<T>*)c->twx.p; }
     else { stride = npix; tiles_per_outer = (int)(npix / Cfg::CW); outer_stride = 0; nouter = 1; a.tw = (const cx<T>*)c->twz.p; }
     const unsigned grid = (unsigned)(nouter * tiles_per_outer);
     WFM_LAUNCH(kfn, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, c->stream, a, stride, tiles_per_outer, outer_stride);
@@ -75,8 +107,14 @@ template <typename T, int LEN, int STORE> int conv_cols(wfm_conv* c, ConvArgs<T>
 template <int LOAD, int STORE> int conv_rows_n(wfm_conv* c, const ConvArgs<double>& a) {
     WFM_CONV_SWITCH(c->nx, (conv_rows<double, L_, LOAD, STORE>(c, a)))
 }
-template <int STORE> int conv_cols_n(wfm_conv* c, const ConvArgs<double>& a, int axis) {
-    WFM_CONV_SWITCH(axis == 1 ? c->ny : c->nz, (conv_cols<double, L_, STORE>(c, a, axis)))
+template <int STORE> int conv_cols_n(wfm_conv* c, const ConvArgs<double>& a, int axis, int pitch) {
+    WFM_CONV_SWITCH(axis == 1 ? c->ny : c->nz, (conv_cols<double, L_, STORE>(c, a, axis, pitch)))
+}
+template <int STORE> int conv_r2c_n(wfm_conv* c, const ConvArgs<double>& a) {
+    WFM_CONV_SWITCH(c->nx, (conv_rows_r2c<double, L_, STORE>(c, a)))
+}
+template <int STORE> int conv_c2r_n(wfm_conv* c, const ConvArgs<double>& a, int* nparts) {
+    WFM_CONV_SWITCH(c->nx, (conv_rows_c2r<double, L_, STORE>(c, a, nparts)))
 }
 
 ConvArgs<double> conv_args(wfm_conv* c) {
@@ -114,16 +152,17 @@ static int conv_create_impl(wfm_conv** out, int nx, int ny, int nz, int precisio
     if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return WFM_ERR_INVALID_ARG; }
     wfm_conv* c = new (std::nothrow) wfm_conv();
     if (!c) { g_create_error = "out of host memory"; return WFM_ERR_NOMEM; }
-    c->nx = nx; c->ny = ny; c->nz = nz; c->precision = precision; c->device = device;
+    c->nx = nx; c->ny = ny; c->nz = nz; c->precision = precision; c->device = device; c->lite = lite;
     auto bail = [&](int code, const char* what) { g_create_error = what; wfm_conv_destroy(c); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(WFM_ERR_CUDA, "cudaSetDevice failed");
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(WFM_ERR_CUDA, "cudaStreamCreate failed");
     c->stream = c->own_stream;
     const size_t vox = c->vox();
-    if (c->V.ensure(16 * vox) || c->cost_dev.ensure(8) || c->cost_part.ensure(8 * ((size_t)ny * nz + 8)) ||
-        (!lite && (c->X.ensure(16 * vox) || c->y.ensure(8 * vox))))
+    if (c->V.ensure(16 * (lite ? vox : c->hvox())) || c->cost_dev.ensure(8) || c->cost_part.ensure(8 * ((size_t)ny * nz + 8)) ||
+        (!lite && (c->X.ensure(16 * c->hvox()) || c->y.ensure(8 * vox) || c->R.ensure(8 * vox))))
         return bail(WFM_ERR_NOMEM, "device allocation failed");
-    if (conv_upload_twiddles(c, c->twx, nx) != WFM_OK || conv_upload_twiddles(c, c->twz, nz) != WFM_OK)
+    if (conv_upload_twiddles(c, c->twx, nx) != WFM_OK || conv_upload_twiddles(c, c->twz, nz) != WFM_OK ||
+        conv_upload_twiddles(c, c->twh, nx / 2) != WFM_OK || conv_upload_twiddles(c, c->twn, nx / 2, nx) != WFM_OK)
         return bail(WFM_ERR_CUDA, "twiddle upload failed");
     *out = c;
     return WFM_OK;
@@ -133,7 +172,9 @@ int wfm_conv_destroy(wfm_conv* c) {
     if (!c) return WFM_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->V, &c->X, &c->y, &c->w, &c->hdev, &c->gdev, &c->cost_part, &c->cost_dev, &c->twx, &c->twz}) b->release();
+    for (DevBuf* b : {&c->V, &c->X, &c->y, &c->w, &c->R, &c->hdev, &c->gdev, &c->cost_part, &c->cost_dev, &c->twx, &c->twz,
+                      &c->twh, &c->twn})
+        b->release();
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return WFM_OK;
@@ -157,9 +198,9 @@ int wfm_conv_set_object(wfm_conv* c, const void* obj_host) {
     WFM_CK(c, cudaMemcpyAsync(c->hdev.p, obj_host, 8 * c->vox(), cudaMemcpyHostToDevice, c->stream));
     ConvArgs<double> a = conv_args(c);
     a.real_in = (const double*)c->hdev.p;
-    int rc = conv_rows_n<CL_REAL, CS_CPLX>(c, a); if (rc) return rc;
-    rc = conv_cols_n<CS_CPLX>(c, a, 1); if (rc) return rc;
-    rc = conv_cols_n<CS_SPECTRUM>(c, a, 2); if (rc) return rc;
+    int rc = conv_r2c_n<CS_CPLX>(c, a); if (rc) return rc;
+    rc = conv_cols_n<CS_CPLX>(c, a, 1, c->pitch()); if (rc) return rc;
+    rc = conv_cols_n<CS_SPECTRUM>(c, a, 2, c->pitch()); if (rc) return rc;
     WFM_CK(c, cudaStreamSynchronize(c->stream));
     c->have_obj = true;
     return WFM_OK;
@@ -196,40 +237,32 @@ int wfm_conv_cost_and_gradient_dev(wfm_conv* c, double alpha, const void* h_dev,
     ConvArgs<double> a = conv_args(c);
     a.real_in = (const double*)h_dev; a.grad = (double*)grad_dev; a.alpha = alpha; a.clear_grad = clr ? 1 : 0;
     a.cost_part = (double*)c->cost_part.p;
-    int rc;
-    // H = FFT3(h); V = conj(H X)
-    if ((rc = conv_rows_n<CL_REAL, CS_CPLX>(c, a))) return rc;
-    if ((rc = conv_cols_n<CS_CPLX>(c, a, 1))) return rc;
-    if ((rc = conv_cols_n<CS_MULX_CONJ>(c, a, 2))) return rc;
-    // r = IFFT3(H X) - y; cost; V = w r
-    if ((rc = conv_cols_n<CS_CPLX>(c, a, 2))) return rc;
-    if ((rc = conv_cols_n<CS_CPLX>(c, a, 1))) return rc;
-    if ((rc = conv_rows_n<CL_CPLX, CS_RESID>(c, a))) return rc;
+    a.resid = (double*)c->R.p;
+    const int P = c->pitch();
+    int rc, nparts = 0;
+    // H = FFT3(h) (half spectrum); V = conj(H X)
+    if ((rc = conv_r2c_n<CS_CPLX>(c, a))) return rc;
+    if ((rc = conv_cols_n<CS_CPLX>(c, a, 1, P))) return rc;
+    if ((rc = conv_cols_n<CS_MULX_CONJ>(c, a, 2, P))) return rc;
+    // r = IFFT3(H X) - y; cost; R = w r
+    if ((rc = conv_cols_n<CS_CPLX>(c, a, 2, P))) return rc;
+    if ((rc = conv_cols_n<CS_CPLX>(c, a, 1, P))) return rc;
+    if ((rc = conv_c2r_n<CS_RESID>(c, a, &nparts))) return rc;
     {
-        const size_t nrows = (size_t)c->ny * c->nz;
-        int nparts = 0;
-        switch (c->nx) {
-            case 32: nparts = (int)((nrows + RowCfg<32>::RB - 1) / RowCfg<32>::RB); break;
-            case 64: nparts = (int)((nrows + RowCfg<64>::RB - 1) / RowCfg<64>::RB); break;
-            case 128: nparts = (int)((nrows + RowCfg<128>::RB - 1) / RowCfg<128>::RB); break;
-            case 256: nparts = (int)((nrows + RowCfg<256>::RB - 1) / RowCfg<256>::RB); break;
-            case 512: nparts = (int)((nrows + RowCfg<512>::RB - 1) / RowCfg<512>::RB); break;
-            case 1024: nparts = (int)((nrows + RowCfg<1024>::RB - 1) / RowCfg<1024>::RB); break;
-            default: nparts = (int)((nrows + RowCfg<2048>::RB - 1) / RowCfg<2048>::RB); break;
-        }
         auto kfin = &k_conv_cost_final;
         WFM_LAUNCH(kfin, dim3(1), dim3(256), 0, c->stream, (const double*)c->cost_part.p, nparts, alpha,
                    cost_dev ? cost_dev : (double*)c->cost_dev.p);
         WFM_CK_LAUNCH(c, "k_conv_cost_final");
     }
     // W = FFT3(w r); V = conj(W conj(X))
-    if ((rc = conv_rows_n<CL_CPLX, CS_CPLX>(c, a))) return rc;
-    if ((rc = conv_cols_n<CS_CPLX>(c, a, 1))) return rc;
-    if ((rc = conv_cols_n<CS_MULCX_CONJ>(c, a, 2))) return rc;
+    a.real_in = (const double*)c->R.p;
+    if ((rc = conv_r2c_n<CS_CPLX>(c, a))) return rc;
+    if ((rc = conv_cols_n<CS_CPLX>(c, a, 1, P))) return rc;
+    if ((rc = conv_cols_n<CS_MULCX_CONJ>(c, a, 2, P))) return rc;
     // grad = alpha * IFFT3(W conj(X))
-    if ((rc = conv_cols_n<CS_CPLX>(c, a, 2))) return rc;
-    if ((rc = conv_cols_n<CS_CPLX>(c, a, 1))) return rc;
-    if ((rc = conv_rows_n<CL_CPLX, CS_GRAD>(c, a))) return rc;
+    if ((rc = conv_cols_n<CS_CPLX>(c, a, 2, P))) return rc;
+    if ((rc = conv_cols_n<CS_CPLX>(c, a, 1, P))) return rc;
+    if ((rc = conv_c2r_n<CS_GRAD>(c, a, nullptr))) return rc;
     return WFM_OK;
 }
 
@@ -304,8 +337,8 @@ int wfm_get_mtf(wfm_model* h, void* out_host) {
     ConvArgs<double> a = conv_args(c);
     a.real_in = (const double*)h->psf.p;
     a.Xout = (double2*)c->V.p;
-    if (!(rc = conv_rows_n<CL_REAL, CS_CPLX>(c, a)) && !(rc = conv_cols_n<CS_CPLX>(c, a, 1)) &&
-        !(rc = conv_cols_n<CS_CPLX>(c, a, 2))) {
+    if (!(rc = conv_rows_n<CL_REAL, CS_CPLX>(c, a)) && !(rc = conv_cols_n<CS_CPLX>(c, a, 1, c->nx)) &&
+        !(rc = conv_cols_n<CS_CPLX>(c, a, 2, c->nx))) {
         cudaError_t e = cudaMemcpyAsync(out_host, c->V.p, 16 * c->vox(), cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = h->fail(WFM_ERR_CUDA, "MTF copy failed: %s", cudaGetErrorString(e));

@@ -125,6 +125,7 @@ template <int N_, int E_, int R1_, int R2_, int R3_> struct PlanBase {
 };
 
 template <int N> struct Plan;
+template <> struct Plan<16> : PlanBase<16, 8, 4, 4, 1> {};     // half-length transform of the 32-point real rows (wfm_conv.cuh)
 template <> struct Plan<32> : PlanBase<32, 8, 8, 4, 1> {};
 template <> struct Plan<64> : PlanBase<64, 8, 8, 8, 1> {};
 template <> struct Plan<128> : PlanBase<128, 8, 8, 4, 4> {};
@@ -139,6 +140,7 @@ template <> struct Plan<2048> : PlanBase<2048, 16, 16, 16, 8> {};
 
 // Row padding shifts (PA, PB): pad(i) = i + (i >> PA) + (i >> PB), 0 disables a term.
 template <int N, int ESZ> struct RowPad;
+template <> struct RowPad<16, 16> { static constexpr int PA = 0, PB = 0; };
 template <> struct RowPad<32, 16> { static constexpr int PA = 3, PB = 4; };
 template <> struct RowPad<64, 16> { static constexpr int PA = 3, PB = 0; };
 template <> struct RowPad<128, 16> { static constexpr int PA = 0, PB = 4; };
@@ -150,6 +152,7 @@ template <> struct RowPad<512, 16> { static constexpr int PA = 0, PB = 6; };
 #endif
 template <> struct RowPad<1024, 16> { static constexpr int PA = 0, PB = 6; };
 template <> struct RowPad<2048, 16> { static constexpr int PA = 0, PB = 7; };
+template <> struct RowPad<16, 8> { static constexpr int PA = 0, PB = 0; };
 template <> struct RowPad<32, 8> { static constexpr int PA = 3, PB = 4; };
 template <> struct RowPad<64, 8> { static constexpr int PA = 3, PB = 5; };
 template <> struct RowPad<128, 8> { static constexpr int PA = 2, PB = 0; };

@@ -264,7 +264,7 @@ def _bead_object(N, Nz, radius_px=2.5):
     return np.roll(obj, (-(Nz // 2), -(N // 2), -(N // 2)), axis=(0, 1, 2))
 
 
-@pytest.mark.parametrize("N,Nz", [(32, 32), (64, 128), (128, 64), (256, 32)])
+@pytest.mark.parametrize("N,Nz", [(32, 32), (64, 128), (128, 64), (256, 32), (512, 32), (1024, 32)])
 def test_convolution_data_term_matches_oracle(lib, N, Nz):
     """Row f1: TiPi WeightedConvolutionCost as PSF_Estimation.java:147-157,206 drives it (restated, unpinned)."""
     from microtipi_b200 import WeightedConvolutionCost, DoubleShapedVectorSpace
