@@ -313,6 +313,13 @@ struct PipeCtl {
 #ifndef WFM_PIPE_KR
 #define WFM_PIPE_KR 4
 #endif
+// The Jacobian pipeline (80 registers) forms its twiddle powers as a tree of depth log2(R) (wfm_fft.cuh).
+#ifndef WFM_JAC_TW_TREE
+#define WFM_JAC_TW_TREE 1
+#endif
+#ifndef WFM_PSF_TW_TREE
+#define WFM_PSF_TW_TREE 0
+#endif
 // Row items of the Jacobian bulk-prefetch their next row of conj(a) and q into L2 (TMA prefetch).
 #ifndef WFM_L2_PREFETCH
 #define WFM_L2_PREFETCH 1
@@ -552,8 +559,8 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
             v[e] = val;
         }
     }
-    fft_inplace<T, P, L, CtaSync, PipePrefetchHook, NARROW>(v, cells + c, t, tw_s, tw_s + N, 0,
-                                                            PipePrefetchHook{qu, ctl, a.g.nzl});
+    fft_inplace<T, P, L, CtaSync, PipePrefetchHook, NARROW, WFM_PSF_TW_TREE>(v, cells + c, t, tw_s, tw_s + N, 0,
+                                                                             PipePrefetchHook{qu, ctl, a.g.nzl});
     pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
     cx<T>* dst = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)sub * N * C + c;
 #pragma unroll
@@ -613,7 +620,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
         for (int e = 0; e < E; ++e)
             v[e] = (leg_live<P::R1, NARROW>(e % P::R1) && xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
 #endif
-        fft_inplace<T, P, L, RowSync<TT>, NoHook, NARROW>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
+        fft_inplace<T, P, L, RowSync<TT>, NoHook, NARROW, WFM_PSF_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
         const size_t base = (size_t)pl * N * N + (size_t)N * ky;
 #pragma unroll
         for (int u = 0; u < E / P::RL; ++u)
@@ -762,7 +769,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
                 v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
             }
 #endif
-        fft_inplace<T, P, L, RowSync<TT>>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
+        fft_inplace<T, P, L, RowSync<TT>, NoHook, false, WFM_JAC_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
         cx<T>* dst = a.T2 + (size_t)(pl % ring) * N * a.pitch + (size_t)y * C;
 #pragma unroll
         for (int e = 0; e < E; ++e)
@@ -802,7 +809,8 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
         for (int r = 0; r < P::RL; ++r)
             if (leg_live<P::RL, NARROW>(r))
                 fl |= (unsigned)__ldg(&a.st.flags[tbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
-    fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + N, 0, PipePrefetchHook{qu, ctl, a.g.nzl});
+    fft_inplace<T, P, L, CtaSync, PipePrefetchHook, false, WFM_JAC_TW_TREE>(v, cells + c, t, tw_s, tw_s + N, 0,
+                                                                            PipePrefetchHook{qu, ctl, a.g.nzl});
     const int iz = a.g.z0 + pl;
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
     const bool mod_plane = (a.Gm != nullptr) && (!a.last_plane_only || iz == a.g.nz_global - 1);
