@@ -17,8 +17,10 @@
 using namespace wfm;
 
 namespace {
-
 thread_local std::string g_create_error;
+}  // namespace
+
+namespace wfm_detail {
 
 struct DevBuf {
     void* p = nullptr;
@@ -34,7 +36,8 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
-}  // namespace
+}  // namespace wfm_detail
+using wfm_detail::DevBuf;
 
 struct wfm_model {
     // geometry (MicroscopeModel.java:62-78, WFM:154-172)
@@ -317,7 +320,7 @@ int pipe_roles() {
 template <typename T, int N> int launch_psf(wfm_model* h) {
     using Cfg = PipeCfg<T, N>;
     auto kfn = &k_psf_pipeline<T, N, false>;
-    if constexpr (Plan<N>::R1 == 8) {
+    if constexpr (Plan<N>::R1 == 8 || Plan<N>::R1 == 16) {
         if (h->narrow) kfn = &k_psf_pipeline<T, N, true>;       // legs 2..5 of the first stages are zero: pruned kernels
     }
     int rc = set_smem(h, kfn, Cfg::SMEM); if (rc) return rc;

@@ -112,6 +112,16 @@ template <typename T> WFM_DEVI void dft8_in0167(cx<T> (&v)[8]) {
     v[3] = cadd(p3, B); v[7] = csub(p3, B);
 }
 
+// Radix-16 with inputs 4..11 zero: its even and odd halves are radix-8 transforms with inputs 2..5 zero.
+template <typename T> WFM_DEVI void dft16_in_narrow(cx<T> (&v)[16]) {
+    cx<T> e[8], o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+    dft8_in0167<T>(e);
+    dft8_in0167<T>(o);
+    DftCombine<T, 16, 0>::run(v, e, o);
+}
+
 // ---- plans ---------------------------------------------------------------------------------
 template <int N_, int E_, int R1_, int R2_, int R3_> struct PlanBase {
     static constexpr int N = N_, E = E_, R1 = R1_, R2 = R2_, R3 = R3_;
@@ -231,14 +241,14 @@ struct NoHook { WFM_DEVI void operator()() const {} };
 
 // Hook: callable run once by every thread right after the first exchange barrier (used by the
 // pipelines to claim the next work item while two thirds of the transform are still ahead).
-// SPARSE1: the caller guarantees that the stage-1 legs 2..5 of every butterfly are zero (R1 == 8 only); their
-// slots in v are ignored.
+// SPARSE1: the caller guarantees that the middle half of the stage-1 legs of every butterfly is zero (legs 2..5
+// for R1 == 8, 4..11 for R1 == 16); their slots in v are ignored.
 // TWTREE: 0 = sequential chain w, w^2, ... (2 live twiddles), 1 = tree (depth log2 R, up to R/2 live),
 //         2 = two interleaved chains stepping by w^2 (depth R/2, 3 live)
 template <typename T, class P, class L, class S, class Hook = NoHook, bool SPARSE1 = false, int TWTREE = 0>
 WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* tw, const cx<T>* tw2,
                           const int sync_id, const Hook& hook = Hook()) {
-    static_assert(!SPARSE1 || P::R1 == 8, "sparse first stage is a radix-8 special case");
+    static_assert(!SPARSE1 || P::R1 == 8 || P::R1 == 16, "sparse first stage: radix 8 or 16");
     constexpr int E = P::E, R1 = P::R1, R2 = P::R2, R3 = P::R3, TT = P::T, S1 = P::S1;
     // stage 1: radix R1 over legs of stride S1, twiddle W_N^(b*k1), scatter to cell k1*S1 + b
 #pragma unroll
@@ -246,7 +256,8 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
         cx<T> a[R1];
 #pragma unroll
         for (int r = 0; r < R1; ++r) a[r] = v[u * R1 + r];
-        if constexpr (SPARSE1) dft8_in0167<T>(reinterpret_cast<cx<T>(&)[8]>(a));
+        if constexpr (SPARSE1 && R1 == 8) dft8_in0167<T>(reinterpret_cast<cx<T>(&)[8]>(a));
+        else if constexpr (SPARSE1 && R1 == 16) dft16_in_narrow<T>(reinterpret_cast<cx<T>(&)[16]>(a));
         else Dft<T, R1>::run(a);
         const int b = t + TT * u;
         sm[L::at(b)] = a[0];
