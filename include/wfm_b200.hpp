@@ -97,6 +97,11 @@ public:
     // getPsf() WFM:1798: host copy (double or float according to `single`), flat order ix + Nx*(iy + Ny*izl)
     void getPsf(void* out) { if (PState < 1) computePsf(); check(wfm_get_psf(h_, out)); }
     void get_cpxPsf(void* out) { if (PState < 1) computePsf(); check(wfm_get_cpx_psf(h_, out)); }   // WFM:1856
+    // getMtf() WFM:1807-1828 as intended (the reference loop never terminates): 3-D DFT of the PSF, (2,Nx,Ny,Nz) doubles
+    void getMtf(double* out) { check(wfm_get_mtf(h_, out)); PState = 1; }
+    // ArrayUtils.roll(getPsf()) of BlindDeconvJob.java:100: the PSF centred in the volume
+    void getPsfRolled(void* out) { check(wfm_get_psf_rolled(h_, out)); PState = 1; }
+    void markPsfValid() { PState = wfm_psf_state(h_); }
 
     DoubleShapedVector apply_Jacobian(const void* grad, const DoubleShapedVectorSpace* xspace) override {   // WFM:399-409
         if (xspace && xspace == parameterSpace[DEFOCUS].get()) return apply_J_defocus(grad);
@@ -213,6 +218,48 @@ private:
     double NA_, lambda_, ni_, lambda_ni_ = 0, deltaX_ = 0, deltaY_ = 0;
     bool radial_;
     int nPhase_ = 0, nModulus_ = 1, Nzern_ = 4, nzl_ = 0;
+};
+
+// TiPi mitiv.conv.WeightedConvolutionCost as PSF_Estimation drives it (PSF_Estimation.java:147-150,157,206): the
+// object is the kernel of the operator, the PSF is the variable (restated semantics, see wfm_conv.cuh).
+class WeightedConvolutionCost {
+public:
+    WeightedConvolutionCost(int nx, int ny, int nz, int device = 0) : vox_((size_t)nx * ny * nz) {     // build(space) :147
+        const int rc = wfm_conv_create(&c_, nx, ny, nz, WFM_F64, device);
+        if (rc != WFM_OK) raise(rc, wfm_conv_last_error(nullptr));
+    }
+    ~WeightedConvolutionCost() { if (c_) wfm_conv_destroy(c_); }
+    WeightedConvolutionCost(const WeightedConvolutionCost&) = delete;
+    WeightedConvolutionCost& operator=(const WeightedConvolutionCost&) = delete;
+    void setPSF(const double* obj) { check(wfm_conv_set_object(c_, obj)); }               // setPSF(obj, {0,0,0}) :145,148
+    void setData(const double* data) { check(wfm_conv_set_data(c_, data)); }              // :149
+    void setWeights(const double* w) { check(wfm_conv_set_weights(c_, w)); }              // :150 (nullptr = unit weights)
+    double computeCostAndGradient(double alpha, const double* x, double* gx, bool clr) {  // :157,206
+        double cost = 0.0;
+        check(wfm_conv_cost_and_gradient(c_, alpha, x, gx, clr ? 1 : 0, &cost));
+        return cost;
+    }
+    // One COMPUTE_FG evaluation of PSF_Estimation.fitPSF (:202-217) on the device; returns the cost, fills g.
+    double evalFG(WideFieldModel& pupil, const DoubleShapedVector& x, std::vector<double>& g, double alpha = 1.0) {
+        int flag = -1;
+        for (int f = 0; f < 3; ++f) if (pupil.space(f) && x.getOwner() == pupil.space(f)) flag = f;
+        if (flag < 0) throw std::invalid_argument("DoubleShapedVector param does not belong to any space");
+        g.assign(x.getNumber(), 0.0);
+        double cost = 0.0;
+        const int rc = wfm_eval_fg(pupil.handle(), c_, flag, x.getData().data(), x.getNumber(), alpha, &cost, g.data());
+        if (rc != WFM_OK) raise(rc, wfm_last_error(pupil.handle()));
+        pupil.markPsfValid();
+        return cost;
+    }
+    size_t voxels() const { return vox_; }
+private:
+    void check(int rc) const { if (rc != WFM_OK) raise(rc, wfm_conv_last_error(c_)); }
+    [[noreturn]] static void raise(int rc, const char* msg) {
+        if (rc == WFM_ERR_INVALID_ARG || rc == WFM_ERR_UNSUPPORTED) throw std::invalid_argument(msg);
+        throw std::runtime_error(std::string("wfm_b200: ") + msg + " (status " + std::to_string(rc) + ")");
+    }
+    wfm_conv* c_ = nullptr;
+    size_t vox_;
 };
 
 }  // namespace microtipi

@@ -56,6 +56,39 @@ int main() {
     catch (const std::invalid_argument&) {}                            // quirk Q4
     DoubleShapedVector d = m.apply_J_defocus(q.data());
     CHECK(d.getNumber() == 3 && std::isfinite(d.get(0)));
+    // rows f1 / f4 through the C++ mirror: the data term and one COMPUTE_FG evaluation (PSF_Estimation.java:147-157,202-217)
+    {
+        const int Nc = 32, Nzc = 32;
+        WideFieldModel pupil(Nc, Nc, Nzc, 10, 1, 1.4, 542e-9, 1.518, 64.5e-9, 160e-9, false, false);
+        const size_t vox = (size_t)Nc * Nc * Nzc;
+        std::vector<double> obj(vox, 0.0), data(vox), psf0(vox), rolled(vox), mtf(2 * vox), gq(vox);
+        obj[0] = 1.0; obj[1] = 0.5; obj[Nc] = 0.25;                    // a small blob at the origin
+        pupil.getPsf(psf0.data());
+        for (size_t i = 0; i < vox; ++i) data[i] = 0.9 * psf0[i];
+        WeightedConvolutionCost fdata(Nc, Nc, Nzc);
+        fdata.setPSF(obj.data()); fdata.setData(data.data()); fdata.setWeights(nullptr);
+        const double c0 = fdata.computeCostAndGradient(1.0, psf0.data(), gq.data(), true);
+        CHECK(c0 > 0 && std::isfinite(c0));
+        DoubleShapedVector xa(pupil.space(WideFieldModel::PHASE), std::vector<double>(10, 0.01));
+        std::vector<double> gfg;
+        const double c1 = fdata.evalFG(pupil, xa, gfg);
+        // the same evaluation step by step through the host-buffer calls
+        pupil.setParam(xa);
+        std::vector<double> p1(vox);
+        pupil.getPsf(p1.data());
+        const double c2 = fdata.computeCostAndGradient(1.0, p1.data(), gq.data(), true);
+        DoubleShapedVector g2 = pupil.apply_Jacobian(gq.data(), xa.getSpace());
+        CHECK(std::fabs(c1 - c2) <= 1e-12 * std::fabs(c2));
+        double num = 0, den = 0;
+        for (int k = 0; k < 10; ++k) { num += (gfg[k] - g2.get(k)) * (gfg[k] - g2.get(k)); den += g2.get(k) * g2.get(k); }
+        CHECK(std::sqrt(num) <= 1e-12 * std::sqrt(den));
+        pupil.getPsfRolled(rolled.data());
+        CHECK(rolled[(Nc / 2) + (size_t)Nc * ((Nc / 2) + (size_t)Nc * (Nzc / 2))] == p1[0]);     // origin moved to the centre
+        pupil.getMtf(mtf.data());
+        double sum = 0;
+        for (double v : p1) sum += v;
+        CHECK(std::fabs(mtf[0] - sum) <= 1e-12 && std::fabs(mtf[1]) <= 1e-15);                   // DC term = total energy
+    }
     std::printf("OK energy=%.15f fd=%.6e g4=%.6e\n", e, fd, g.get(4));
     return 0;
 }
