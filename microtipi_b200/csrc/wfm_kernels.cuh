@@ -305,6 +305,9 @@ struct PipeCtl {
 #ifndef WFM_PIPE_C64
 #define WFM_PIPE_C64 4
 #endif
+#ifndef WFM_PIPE_C32
+#define WFM_PIPE_C32 4   /* 256-thread CTAs as in fp64: 0.592 -> 0.561 ms/step at 512^2 fp32 */
+#endif
 // Row items double-buffer their global loads in registers: the next row's loads are issued before
 // the current row's transform, so a row group always has a row in flight (needs ~48 more registers).
 #ifndef WFM_ROW_PREFETCH
@@ -326,7 +329,7 @@ struct PipeCtl {
 #endif
 template <typename T, int N> struct PipeCfg {
     using P = Plan<N>;
-    static constexpr int C = (N >= 256) ? (sizeof(T) == 8 ? WFM_PIPE_C64 : 8) : ColCfg<T, N>::C;   // columns per B-item == rows per A-item
+    static constexpr int C = (N >= 256) ? (sizeof(T) == 8 ? WFM_PIPE_C64 : WFM_PIPE_C32) : ColCfg<T, N>::C;   // columns per B-item == rows per A-item
     static_assert(P::T < 64 || C <= 15, "one named barrier per row transform");
     static constexpr int TT = P::T;
     static constexpr int THREADS = C * TT;
