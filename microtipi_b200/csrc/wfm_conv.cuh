@@ -297,6 +297,55 @@ __global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS) k_conv_cols(ConvA
     if constexpr (STORE == CS_RESID) conv_cost_reduce(cost_acc, &a.cost_part[blockIdx.x]);
 }
 
+// ---- z pass there and back: FFT_z, spectral product, conjugate, FFT_z again without leaving the SM ---------
+// MUL = CS_MULX_CONJ: V <- FFT_z(conj(FFT_z(V) * X));  CS_MULCX_CONJ: V <- FFT_z(conj(FFT_z(V) * conj(X))).
+// Saves one write + read of the work volume per transform pair; the only extra cost is one exchange through the
+// tile's shared cells (the first transform leaves its output in output-slot order, the second wants input-slot order).
+template <typename T, int LEN, int MUL>
+__global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS) k_conv_cols_zz(ConvArgs<T> a, size_t stride, int tiles_per_outer,
+                                                                               size_t outer_stride) {
+    using P = Plan<LEN>;
+    using Cfg = ConvColCfg<T, LEN>;
+    using L = typename Cfg::ColL;
+    constexpr int CW = Cfg::CW, TT = P::T, E = P::E;
+    WFM_DYN_SMEM(cx<T>, cells);
+    cx<T>* tw_s = cells + Cfg::CELLS;
+    for (int i = threadIdx.x; i < LEN; i += Cfg::THREADS) tw_s[i] = a.tw[i];
+    if (threadIdx.x < P::R3) tw_s[LEN + threadIdx.x] = a.tw[P::R1 * threadIdx.x];
+    __syncthreads();
+    const int c = threadIdx.x % CW, t = threadIdx.x / CW;
+    const size_t base = (size_t)(blockIdx.x / tiles_per_outer) * outer_stride + (size_t)(blockIdx.x % tiles_per_outer) * CW + c;
+    cx<T>* sm = cells + c;
+    cx<T> v[E];
+#pragma unroll
+    for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+        for (int r = 0; r < P::R1; ++r) v[u * P::R1 + r] = a.V[base + (size_t)((t + TT * u) + P::S1 * r) * stride];
+    fft_inplace<T, P, L, CtaSync>(v, sm, t, tw_s, tw_s + LEN, 0);
+    __syncthreads();                                   // the last stage has read the cells
+#pragma unroll
+    for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+        for (int r = 0; r < P::RL; ++r) {
+            const int k = (t + TT * u) + P::SL * r;
+            cx<T> x = a.X[base + (size_t)k * stride];
+            if constexpr (MUL == CS_MULCX_CONJ) x.y = -x.y;
+            const cx<T> p = cmul(v[u * P::RL + r], x);
+            sm[L::at(k)] = mkc<T>(p.x, -p.y);
+        }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+        for (int r = 0; r < P::R1; ++r) v[u * P::R1 + r] = sm[L::at((t + TT * u) + P::S1 * r)];
+    __syncthreads();                                   // everybody holds its inputs: the cells may be overwritten
+    fft_inplace<T, P, L, CtaSync>(v, sm, t, tw_s, tw_s + LEN, 0);
+#pragma unroll
+    for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+        for (int r = 0; r < P::RL; ++r) a.V[base + (size_t)((t + TT * u) + P::SL * r) * stride] = v[u * P::RL + r];
+}
+
 // fixed-order sum of the per-CTA partials: cost = alpha/2 * sum
 __global__ void k_conv_cost_final(const double* __restrict__ part, int n, double alpha, double* __restrict__ out) {
     __shared__ double red[8];

@@ -107,6 +107,20 @@ template <typename T, int LEN, int STORE> int conv_cols(wfm_conv* c, ConvArgs<T>
 template <int LOAD, int STORE> int conv_rows_n(wfm_conv* c, const ConvArgs<double>& a) {
     WFM_CONV_SWITCH(c->nx, (conv_rows<double, L_, LOAD, STORE>(c, a)))
 }
+// z pass there and back in one kernel (axis 2 only)
+template <typename T, int LEN, int MUL> int conv_cols_zz(wfm_conv* c, ConvArgs<T> a, int pitch) {
+    using Cfg = ConvColCfg<T, LEN>;
+    auto kfn = &k_conv_cols_zz<T, LEN, MUL>;
+    if (Cfg::SMEM > 48 * 1024) WFM_CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    const size_t npix = (size_t)pitch * a.ny;
+    a.tw = (const cx<T>*)c->twz.p;
+    WFM_LAUNCH(kfn, dim3((unsigned)(npix / Cfg::CW)), dim3(Cfg::THREADS), Cfg::SMEM, c->stream, a, npix, (int)(npix / Cfg::CW), (size_t)0);
+    WFM_CK_LAUNCH(c, "k_conv_cols_zz");
+    return WFM_OK;
+}
+template <int MUL> int conv_cols_zz_n(wfm_conv* c, const ConvArgs<double>& a, int pitch) {
+    WFM_CONV_SWITCH(c->nz, (conv_cols_zz<double, L_, MUL>(c, a, pitch)))
+}
 template <int STORE> int conv_cols_n(wfm_conv* c, const ConvArgs<double>& a, int axis, int pitch) {
     WFM_CONV_SWITCH(axis == 1 ? c->ny : c->nz, (conv_cols<double, L_, STORE>(c, a, axis, pitch)))
 }
@@ -240,12 +254,11 @@ int wfm_conv_cost_and_gradient_dev(wfm_conv* c, double alpha, const void* h_dev,
     a.resid = (double*)c->R.p;
     const int P = c->pitch();
     int rc, nparts = 0;
-    // H = FFT3(h) (half spectrum); V = conj(H X)
+    // H = FFT3(h) (half spectrum)
     if ((rc = conv_r2c_n<CS_CPLX>(c, a))) return rc;
     if ((rc = conv_cols_n<CS_CPLX>(c, a, 1, P))) return rc;
-    if ((rc = conv_cols_n<CS_MULX_CONJ>(c, a, 2, P))) return rc;
-    // r = IFFT3(H X) - y; cost; R = w r
-    if ((rc = conv_cols_n<CS_CPLX>(c, a, 2, P))) return rc;
+    // r = IFFT3(H X) - y; cost; R = w r      (z forward, product, z inverse fused: the volume stays on the SM)
+    if ((rc = conv_cols_zz_n<CS_MULX_CONJ>(c, a, P))) return rc;
     if ((rc = conv_cols_n<CS_CPLX>(c, a, 1, P))) return rc;
     if ((rc = conv_c2r_n<CS_RESID>(c, a, &nparts))) return rc;
     {
@@ -254,13 +267,12 @@ int wfm_conv_cost_and_gradient_dev(wfm_conv* c, double alpha, const void* h_dev,
                    cost_dev ? cost_dev : (double*)c->cost_dev.p);
         WFM_CK_LAUNCH(c, "k_conv_cost_final");
     }
-    // W = FFT3(w r); V = conj(W conj(X))
+    // W = FFT3(w r)
     a.real_in = (const double*)c->R.p;
     if ((rc = conv_r2c_n<CS_CPLX>(c, a))) return rc;
     if ((rc = conv_cols_n<CS_CPLX>(c, a, 1, P))) return rc;
-    if ((rc = conv_cols_n<CS_MULCX_CONJ>(c, a, 2, P))) return rc;
     // grad = alpha * IFFT3(W conj(X))
-    if ((rc = conv_cols_n<CS_CPLX>(c, a, 2, P))) return rc;
+    if ((rc = conv_cols_zz_n<CS_MULCX_CONJ>(c, a, P))) return rc;
     if ((rc = conv_cols_n<CS_CPLX>(c, a, 1, P))) return rc;
     if ((rc = conv_c2r_n<CS_GRAD>(c, a, nullptr))) return rc;
     return WFM_OK;

@@ -25,7 +25,8 @@ def build(force=False, sanitize=False):
            "-DWFM_EMU", "-include", os.path.join(HERE, "cuda_emu.h"), "-x", "c++"] + SRCS + \
           ["-o", out, "-lpthread"]
     if sanitize:
-        cmd[1:1] = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"]
+        cmd[1:1] = ["-fsanitize=address", "-fno-omit-frame-pointer"]
+        cmd[cmd.index("-O2")] = "-O1"          # the instrumented build is slow to compile at -O2
     subprocess.run(cmd, check=True)
     return out
 
