@@ -88,6 +88,19 @@ WFM_API int wfm_create(wfm_model** out, int nx, int ny, int nz, double dxy, doub
 WFM_API int wfm_create_slab(wfm_model** out, int nx, int ny, int nz_global, int z0, int nz_local,
                             double dxy, double dz, int precision, int device);
 
+/* Batch of `nbatch` INDEPENDENT models of the same shape on one handle (BASELINE config 5: parameter estimation
+ * over many bead PSFs; SURVEY.md 8 b3 asks for a batch dimension rather than nbatch handles).  The models share
+ * optics (wfm_set_optics), basis and support; each has its own phase / modulus / defocus vector, hence its own
+ * rho, phi, psi, maskPupil.  One computePsf() / apply_J_*() pass runs the planes of ALL models through a single
+ * pipeline launch.  Layouts gain a leading (slowest) model index: psf [nbatch][Nz][Ny][Nx], cpx likewise,
+ * rho/phi/psi/mask [nbatch][Npix], gradients [nbatch][3 + nPhase + nModulus].
+ * On a batch handle wfm_set_phase / _modulus / _defocus give every model the same vector; wfm_batch_set_* take one
+ * row per model.  wfm_apply_j_* (single-model outputs), wfm_set_pupil_arrays, the rolled PSF, the MTF and
+ * wfm_eval_fg return WFM_ERR_UNSUPPORTED / WFM_ERR_INVALID_ARG on a batch handle. */
+WFM_API int wfm_create_batch(wfm_model** out, int nx, int ny, int nz, int nbatch, double dxy, double dz,
+                             int precision, int device);
+WFM_API int wfm_batch_size(const wfm_model* h);
+
 WFM_API int wfm_destroy(wfm_model* h);
 
 /* Text of the last error on this handle (or of the last failed wfm_create* when h == NULL). */
@@ -122,6 +135,11 @@ WFM_API int wfm_set_modulus(wfm_model* h, const double* beta, int n);
  * n == 3: {ni/lambda, deltaX, deltaY}; n == 1: {ni/lambda}; n == 2 is rejected
  * (it indexes element 2 of a length-2 vector in the reference, quirk Q4). */
 WFM_API int wfm_set_defocus(wfm_model* h, const double* defoc, int n);
+
+/* Batch handles: setPhase / setModulus / setDefocus of every model, table[nbatch][n] (row b = model b). */
+WFM_API int wfm_batch_set_phase(wfm_model* h, const double* alpha_table, int n);
+WFM_API int wfm_batch_set_modulus(wfm_model* h, const double* beta_table, int n);
+WFM_API int wfm_batch_set_defocus(wfm_model* h, const double* defoc_table, int n);
 
 /* Escape hatch for "identical synthetic pupils": load rho, phi, psi (Npix doubles each) and
  * maskPupil (Npix bytes) verbatim.  Any pointer may be NULL to keep the current array. */
@@ -180,10 +198,15 @@ WFM_API int wfm_apply_jacobian(wfm_model* h, int param, const void* q_host, doub
 WFM_API int wfm_apply_j_all(wfm_model* h, const void* q_host, double* out_defocus3,
                             double* out_phase, double* out_modulus);
 
+/* Batch handles: the selected Jacobians (WFM_J_* bits) of every model in one pass.  q_host [nbatch][Nz][Ny][Nx];
+ * out [nbatch][3 + nPhase + nModulus] doubles, each row [defocus(3) | phase | modulus]. */
+WFM_API int wfm_batch_apply_jacobian(wfm_model* h, unsigned kinds, const void* q_host, double* out);
+
 /* Device-resident variant: q_dev and grad_dev are device pointers.  grad_dev receives
  * 3 + nPhase + nModulus doubles laid out [defocus(3) | phase | modulus]; entries of kinds not
  * selected are zero.  For a z-slab handle the values are this slab's PARTIAL sums, ready for
- * one sum-allreduce across ranks.  Asynchronous on the handle's stream. */
+ * one sum-allreduce across ranks.  Asynchronous on the handle's stream.  On a batch handle grad_dev receives
+ * nbatch such rows. */
 WFM_API int wfm_apply_jacobian_dev(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev);
 WFM_API int wfm_grad_length(const wfm_model* h);
 

@@ -6,7 +6,7 @@ Only the path BASELINE.json names lives here: the C-ABI library ``csrc/libwfm_b2
 the library; constructing a model does, and fails loudly when it is missing (no CPU fallback)."""
 from ._capi import load_library, LIB_PATH  # noqa: F401
 from .wide_field_model import (DoubleShapedVector, DoubleShapedVectorSpace, MicroscopeModel, Shape,  # noqa: F401
-                               WideFieldModel)
+                               WideFieldModel, WideFieldModelBatch)
 
 from .convolution_cost import WeightedConvolutionCost  # noqa: F401,E402
 

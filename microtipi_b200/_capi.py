@@ -33,6 +33,13 @@ SIGNATURES = {
     "wfm_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]),
     "wfm_create_slab": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                   C.c_double, C.c_int, C.c_int]),
+    "wfm_create_batch": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                   C.c_int]),
+    "wfm_batch_size": (C.c_int, [_vp]),
+    "wfm_batch_set_phase": (C.c_int, [_vp, _vp, C.c_int]),
+    "wfm_batch_set_modulus": (C.c_int, [_vp, _vp, C.c_int]),
+    "wfm_batch_set_defocus": (C.c_int, [_vp, _vp, C.c_int]),
+    "wfm_batch_apply_jacobian": (C.c_int, [_vp, C.c_uint, _vp, _vp]),
     "wfm_destroy": (C.c_int, [_vp]),
     "wfm_last_error": (C.c_char_p, [_vp]),
     "wfm_set_stream": (C.c_int, [_vp, _vp]),

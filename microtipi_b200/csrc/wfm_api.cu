@@ -42,6 +42,10 @@ using wfm_detail::DevBuf;
 struct wfm_model {
     // geometry (MicroscopeModel.java:62-78, WFM:154-172)
     int N = 0, nz_global = 0, z0 = 0, nzl = 0;
+    // batch of independent models (wfm_create_batch): nbatch models of nzm planes each, stacked: nzl = nbatch*nzm.
+    // They share optics, basis and support; rho/phi/psi/mask and the coefficient vectors are per model.
+    int nbatch = 1, nzm = 0;
+    std::vector<double> alpha_b, beta_b, bpar_h;  // [nbatch][nphase], [nbatch][nmod], [nbatch][4] = {ni/lambda, dX, dY, 1/|beta|}
     double dxy = 0, dz = 0;
     int precision = WFM_F64;
     int device = 0;
@@ -79,6 +83,7 @@ struct wfm_model {
     int pstate = 0;
     // scratch
     DevBuf scratch, Gj, Gm, ctl, block_part, grad, qdev;
+    DevBuf alpha_dev, beta_dev, bpar_dev;         // device copies of the batch tables
     int num_sms = 148;
     unsigned long pipe_checks = 0;
     bool ctl_dirty = true;
@@ -150,7 +155,7 @@ bool supported_n(int n) { return n == 32 || n == 64 || n == 128 || n == 256 || n
 
 Geom geom_of(const wfm_model* h) {
     Geom g;
-    g.N = h->N; g.nz_global = h->nz_global; g.z0 = h->z0; g.nzl = h->nzl; g.dz = h->dz;
+    g.N = h->N; g.nz_global = h->nz_global; g.z0 = h->z0; g.nzl = h->nzl; g.nzm = h->nzm; g.dz = h->dz;
     g.psf_norm = 1.0 / ((double)h->N * (double)h->N * (double)h->nz_global);   // WFM:284
     return g;
 }
@@ -250,12 +255,12 @@ template <class K> int set_smem(wfm_model* h, K kfn, size_t bytes) {
 // Pupil arrays -> strip layout (after any setter, before the next pipeline launch).
 int pack_strip(wfm_model* h) {
     if (!h->strip_dirty) return WFM_OK;
-    const size_t cells = (size_t)h->N * h->pitch;
-    WFM_CK(h, h->s_rho.ensure(8 * cells)); WFM_CK(h, h->s_phi.ensure(8 * cells));
-    WFM_CK(h, h->s_psi.ensure(8 * cells)); WFM_CK(h, h->s_flags.ensure(cells));
+    const size_t cells = (size_t)h->N * h->pitch, all = cells * h->nbatch;
+    WFM_CK(h, h->s_rho.ensure(8 * all)); WFM_CK(h, h->s_phi.ensure(8 * all));
+    WFM_CK(h, h->s_psi.ensure(8 * all)); WFM_CK(h, h->s_flags.ensure(all));
     KernelSpan span(h, WFM_K_SETTERS);
     auto kfn = &k_pack_strip;
-    WFM_LAUNCH_PDL(kfn, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, h->stream, (double*)h->s_rho.p,
+    WFM_LAUNCH_PDL(kfn, dim3((unsigned)((cells + 255) / 256), (unsigned)h->nbatch), dim3(256), 0, h->stream, (double*)h->s_rho.p,
                (double*)h->s_phi.p, (double*)h->s_psi.p, (uint8_t*)h->s_flags.p, (const double*)h->rho.p,
                (const double*)h->phi.p, (const double*)h->psi.p, (const uint8_t*)h->mask.p,
                (const uint8_t*)h->support.p, (const int*)h->act_x.p, h->N, h->nax, h->pitch, h->ctile);
@@ -402,8 +407,11 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         r.kinds = kinds; r.last_plane_only = a.last_plane_only;
         r.dxy = h->dxy; r.lambda_ni = h->lambda_ni; r.deltaX = h->deltaX; r.deltaY = h->deltaY;
         r.glen = h->glen();
+        const bool batch = h->nbatch > 1;
+        r.bpar = batch ? (const double*)h->bpar_dev.p : nullptr;
+        r.cpm = (h->nzm + WFM_RED_PLANES - 1) / WFM_RED_PLANES;
         const int nblocks = h->ncells > 0 ? (h->ncells + WFM_RED_THREADS - 1) / WFM_RED_THREADS : 1;
-        const int nchunks = (h->nzl + WFM_RED_PLANES - 1) / WFM_RED_PLANES;
+        const int nchunks = r.cpm * h->nbatch;
         WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * nchunks * r.glen));
         r.block_part = (double*)h->block_part.p;
         auto kred = &k_jac_reduce;
@@ -416,8 +424,9 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
             nbeta = 1.0 / std::sqrt(s);                                        // WFM:435
         }
         auto kfin = &k_jac_final;
-        WFM_LAUNCH_PDL(kfin, dim3(r.glen), dim3(WFM_FINAL_THREADS), 0, h->stream, (const double*)r.block_part,
-                   nblocks * nchunks, r.glen, h->nphase, a.g.psf_norm, h->beta, nbeta, kinds, grad_dev);
+        WFM_LAUNCH_PDL(kfin, dim3(r.glen, h->nbatch), dim3(WFM_FINAL_THREADS), 0, h->stream, (const double*)r.block_part,
+                   nblocks * r.cpm, r.glen, h->nphase, a.g.psf_norm, h->beta, nbeta, kinds,
+                   batch ? (const double*)h->beta_dev.p : (const double*)nullptr, h->nmod, r.bpar, grad_dev);
         WFM_CK_LAUNCH(h, "k_jac_final");
     }
     return WFM_OK;
@@ -480,6 +489,80 @@ int check_pipeline(wfm_model* h) {
 
 int elementwise_grid(int n) { return (n + 255) / 256; }
 
+int upload_table(wfm_model* h, DevBuf& buf, const std::vector<double>& v) {
+    WFM_CK(h, buf.ensure(8 * v.size()));
+    WFM_CK(h, cudaMemcpyAsync(buf.p, v.data(), 8 * v.size(), cudaMemcpyHostToDevice, h->stream));
+    return WFM_OK;
+}
+int upload_bpar(wfm_model* h) { return upload_table(h, h->bpar_dev, h->bpar_h); }
+
+// setPhase / setModulus / setDefocus of every model of a batch handle; tab = [nbatch][n] (stride 0: one row, broadcast)
+int batch_set_phase(wfm_model* h, const double* tab, int n, int stride) {
+    if (n < 0 || n > WFM_MAX_COEF || (n > 0 && !tab)) return h->fail(WFM_ERR_INVALID_ARG, "bad phase coefficient vector");
+    const int off = h->radial ? 1 : 3;
+    if (n > 0 && (h->nzern <= 0)) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
+    if (n > 0 && n + off > h->nzern)
+        return h->fail(WFM_ERR_INVALID_ARG, "phase parameter does not belong to the right space  ");   // WFM:1629
+    WFM_CK(h, cudaSetDevice(h->device));
+    h->alpha_b.assign((size_t)h->nbatch * (n > 0 ? n : 1), 0.0);
+    for (int b = 0; b < h->nbatch; ++b)
+        for (int k = 0; k < n; ++k) h->alpha_b[(size_t)b * n + k] = tab[(size_t)b * stride + k];
+    for (int k = 0; k < n; ++k) h->alpha.v[k] = h->alpha_b[k];
+    h->nphase = n;
+    int rc = upload_table(h, h->alpha_dev, h->alpha_b); if (rc) return rc;
+    KernelSpan span(h, WFM_K_SETTERS);
+    auto kfn = &k_set_phase_b;
+    WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix()), h->nbatch), dim3(256), 0, h->stream, (double*)h->phi.p,
+               (const double*)h->Z.p, (const uint8_t*)h->mask.p, (const double*)h->alpha_dev.p, n, off, h->npix());
+    WFM_CK_LAUNCH(h, "k_set_phase_b");
+    return invalidate(h);
+}
+
+int batch_set_modulus(wfm_model* h, const double* tab, int n, int stride) {
+    if (n <= 0 || n > WFM_MAX_COEF || !tab) return h->fail(WFM_ERR_INVALID_ARG, "bad modulus coefficient vector");
+    if (h->nzern <= 0) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
+    if (n > h->nzern)
+        return h->fail(WFM_ERR_INVALID_ARG, "DoubleShapedVector beta does not belong to the modulus space");  // WFM:1592
+    WFM_CK(h, cudaSetDevice(h->device));
+    h->beta_b.assign((size_t)h->nbatch * n, 0.0);
+    for (int b = 0; b < h->nbatch; ++b) {
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) { const double v = tab[(size_t)b * stride + k]; h->beta_b[(size_t)b * n + k] = v; s += v * v; }
+        h->bpar_h[4 * b + 3] = 1.0 / std::sqrt(s);                             // WFM:1597 (and WFM:435 for the Jacobian)
+    }
+    for (int k = 0; k < n; ++k) h->beta.v[k] = h->beta_b[k];
+    h->nmod = n;
+    int rc = upload_table(h, h->beta_dev, h->beta_b); if (rc) return rc;
+    rc = upload_bpar(h); if (rc) return rc;
+    auto kfn = &k_set_modulus_b;
+    WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix()), h->nbatch), dim3(256), 0, h->stream, (double*)h->rho.p,
+               (const double*)h->Z.p, (const uint8_t*)h->mask.p, (const double*)h->beta_dev.p,
+               (const double*)h->bpar_dev.p, n, h->npix());
+    WFM_CK_LAUNCH(h, "k_set_modulus_b");
+    h->have_rho = true;
+    return invalidate(h);
+}
+
+int batch_set_defocus(wfm_model* h, const double* tab, int n, int stride) {
+    if (!tab || (n != 1 && n != 3)) return h->fail(WFM_ERR_INVALID_ARG, "bad defocus  parameters");   // WFM:1530, Q4
+    if (!h->have_optics) return h->fail(WFM_ERR_STATE, "optics not set: call wfm_set_optics first");
+    WFM_CK(h, cudaSetDevice(h->device));
+    for (int b = 0; b < h->nbatch; ++b) {
+        const double* d = tab + (size_t)b * stride;
+        if (n == 3) { h->bpar_h[4 * b + 1] = d[1]; h->bpar_h[4 * b + 2] = d[2]; }   // WFM:1518-1520
+        h->bpar_h[4 * b] = d[0];                                                     // WFM:1522
+    }
+    h->lambda_ni = h->bpar_h[0]; h->deltaX = h->bpar_h[1]; h->deltaY = h->bpar_h[2];
+    h->ni = h->lambda_ni * h->lambda;
+    h->ndefocus = n;
+    int rc = upload_bpar(h); if (rc) return rc;
+    auto kfn = &k_compute_defocus_b;
+    WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix()), h->nbatch), dim3(256), 0, h->stream, (double*)h->psi.p,
+               (uint8_t*)h->mask.p, (const uint8_t*)h->map.p, h->N, h->dxy, (const double*)h->bpar_dev.p);
+    WFM_CK_LAUNCH(h, "k_compute_defocus_b");
+    return invalidate(h);
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -487,14 +570,15 @@ int elementwise_grid(int n) { return (n + 255) / 256; }
 // =====================================================================================================
 extern "C" {
 
-int wfm_create_slab(wfm_model** out, int nx, int ny, int nz_global, int z0, int nz_local, double dxy,
-                    double dz, int precision, int device) {
+static int create_impl(wfm_model** out, int nx, int ny, int nz_global, int z0, int nz_local, int nbatch, double dxy,
+                       double dz, int precision, int device) {
     if (!out) { g_create_error = "out is NULL"; return WFM_ERR_INVALID_ARG; }
     *out = nullptr;
     if (nx != ny) { g_create_error = "Nx should equal Ny"; return WFM_ERR_INVALID_ARG; }      // WFM:158-160
     if (nx <= 0 || nz_global <= 0 || nz_local <= 0 || z0 < 0 || z0 + nz_local > nz_global) {
         g_create_error = "bad shape / slab"; return WFM_ERR_INVALID_ARG;
     }
+    if (nbatch < 1 || (long long)nbatch * nz_local > (1ll << 24)) { g_create_error = "bad batch size"; return WFM_ERR_INVALID_ARG; }
     if (precision != WFM_F64 && precision != WFM_F32) { g_create_error = "bad precision"; return WFM_ERR_INVALID_ARG; }
     if (!supported_n(nx)) {
         g_create_error = "Nx must be a power of two in [32, 2048]"; return WFM_ERR_UNSUPPORTED;
@@ -506,8 +590,10 @@ int wfm_create_slab(wfm_model** out, int nx, int ny, int nz_global, int z0, int 
     if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return WFM_ERR_INVALID_ARG; }
     wfm_model* h = new (std::nothrow) wfm_model();
     if (!h) { g_create_error = "out of host memory"; return WFM_ERR_NOMEM; }
-    h->N = nx; h->nz_global = nz_global; h->z0 = z0; h->nzl = nz_local; h->dxy = dxy; h->dz = dz;
+    h->N = nx; h->nz_global = nz_global; h->z0 = z0; h->nzm = nz_local; h->nbatch = nbatch; h->nzl = nbatch * nz_local;
+    h->dxy = dxy; h->dz = dz;
     h->precision = precision; h->device = device;
+    if (nbatch > 1) h->bpar_h.assign(4 * (size_t)nbatch, 0.0);
     auto bail = [&](int code, const char* what) { g_create_error = what; wfm_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(WFM_ERR_CUDA, "cudaSetDevice failed");
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -518,17 +604,29 @@ int wfm_create_slab(wfm_model** out, int nx, int ny, int nz_global, int z0, int 
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0)
             h->num_sms = prop.multiProcessorCount;
     }
-    const size_t npix = (size_t)nx * nx;
+    const size_t npix = (size_t)nx * nx, all = npix * nbatch;
     // this.phi = new double[Ny*Nx]; this.psi = new double[Ny*Nx]  (WFM:167-168); rho starts empty
-    if (h->rho.ensure(8 * npix) || h->phi.ensure(8 * npix) || h->psi.ensure(8 * npix) || h->mask.ensure(npix) ||
-        h->map.ensure(npix) || h->grad.ensure(8 * (3 + 2 * WFM_MAX_COEF)))
+    if (h->rho.ensure(8 * all) || h->phi.ensure(8 * all) || h->psi.ensure(8 * all) || h->mask.ensure(all) ||
+        h->map.ensure(npix) || h->grad.ensure(8 * (3 + 2 * WFM_MAX_COEF) * (size_t)nbatch))
         return bail(WFM_ERR_NOMEM, "device allocation failed");
-    cudaMemset(h->rho.p, 0, 8 * npix); cudaMemset(h->phi.p, 0, 8 * npix); cudaMemset(h->psi.p, 0, 8 * npix);
-    cudaMemset(h->mask.p, 0, npix); cudaMemset(h->map.p, 0, npix);
+    cudaMemset(h->rho.p, 0, 8 * all); cudaMemset(h->phi.p, 0, 8 * all); cudaMemset(h->psi.p, 0, 8 * all);
+    cudaMemset(h->mask.p, 0, all); cudaMemset(h->map.p, 0, npix);
     if (upload_twiddles(h) != WFM_OK) return bail(WFM_ERR_CUDA, "twiddle upload failed");
     *out = h;
     return WFM_OK;
 }
+
+int wfm_create_slab(wfm_model** out, int nx, int ny, int nz_global, int z0, int nz_local, double dxy,
+                    double dz, int precision, int device) {
+    return create_impl(out, nx, ny, nz_global, z0, nz_local, 1, dxy, dz, precision, device);
+}
+
+int wfm_create_batch(wfm_model** out, int nx, int ny, int nz, int nbatch, double dxy, double dz, int precision,
+                     int device) {
+    return create_impl(out, nx, ny, nz, 0, nz, nbatch, dxy, dz, precision, device);
+}
+
+int wfm_batch_size(const wfm_model* h) { return h ? h->nbatch : 0; }
 
 int wfm_create(wfm_model** out, int nx, int ny, int nz, double dxy, double dz, int precision, int device) {
     return wfm_create_slab(out, nx, ny, nz, 0, nz, dxy, dz, precision, device);
@@ -540,7 +638,7 @@ int wfm_destroy(wfm_model* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->Z, &h->rho, &h->phi, &h->psi, &h->mask, &h->map, &h->support, &h->act_x, &h->inv_x,
                       &h->act_y, &h->inv_y, &h->cell_list, &h->in_list, &h->Zs, &h->s_rho, &h->s_phi, &h->s_psi, &h->s_flags, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gj, &h->Gm, &h->ctl, &h->block_part,
-                      &h->grad, &h->qdev})
+                      &h->grad, &h->qdev, &h->alpha_dev, &h->beta_dev, &h->bpar_dev})
         b->release();
     drain_spans(h);
     for (cudaEvent_t e : h->free_events) cudaEventDestroy(e);
@@ -579,6 +677,10 @@ int wfm_set_optics(wfm_model* h, double NA, double lambda, double ni) {
     WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix())), dim3(256), 0, h->stream, (uint8_t*)h->map.p,
                (uint8_t*)h->mask.p, h->N, h->dxy, h->radius);
     WFM_CK_LAUNCH(h, "k_mask_pupil");
+    for (int b = 1; b < h->nbatch; ++b)           // every model of a batch starts from maskPupil = mapPupil
+        WFM_CK(h, cudaMemcpyAsync((uint8_t*)h->mask.p + (size_t)b * h->npix(), h->map.p, h->npix(), cudaMemcpyDeviceToDevice, h->stream));
+    for (int b = 0; b < h->nbatch && h->nbatch > 1; ++b) h->bpar_h[4 * b] = h->lambda_ni;
+    if (h->nbatch > 1) { int rcb = upload_bpar(h); if (rcb) return rcb; }
     h->h_map.resize(h->npix());
     WFM_CK(h, cudaMemcpyAsync(h->h_map.data(), h->map.p, h->npix(), cudaMemcpyDeviceToHost, h->stream));
     WFM_CK(h, cudaStreamSynchronize(h->stream));
@@ -697,6 +799,7 @@ int wfm_get_basis(wfm_model* h, double* out, int nzern) {
 
 int wfm_set_phase(wfm_model* h, const double* alpha, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->nbatch > 1) return batch_set_phase(h, alpha, n, 0);     // batch handle: the same vector for every model
     if (n < 0 || n > WFM_MAX_COEF || (n > 0 && !alpha)) return h->fail(WFM_ERR_INVALID_ARG, "bad phase coefficient vector");
     const int off = h->radial ? 1 : 3;
     if (n > 0 && (h->nzern <= 0)) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
@@ -715,6 +818,7 @@ int wfm_set_phase(wfm_model* h, const double* alpha, int n) {
 
 int wfm_set_modulus(wfm_model* h, const double* beta, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->nbatch > 1) return batch_set_modulus(h, beta, n, 0);
     if (n <= 0 || n > WFM_MAX_COEF || !beta) return h->fail(WFM_ERR_INVALID_ARG, "bad modulus coefficient vector");
     if (h->nzern <= 0) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
     if (n > h->nzern)
@@ -734,6 +838,7 @@ int wfm_set_modulus(wfm_model* h, const double* beta, int n) {
 
 int wfm_set_defocus(wfm_model* h, const double* defoc, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->nbatch > 1) return batch_set_defocus(h, defoc, n, 0);
     if (!defoc || (n != 1 && n != 3)) return h->fail(WFM_ERR_INVALID_ARG, "bad defocus  parameters");   // WFM:1530, Q4
     if (!h->have_optics) return h->fail(WFM_ERR_STATE, "optics not set: call wfm_set_optics first");
     WFM_CK(h, cudaSetDevice(h->device));
@@ -748,8 +853,26 @@ int wfm_set_defocus(wfm_model* h, const double* defoc, int n) {
     return invalidate(h);                                                      // WFM:1533
 }
 
+// Batch handles: one table row per model.
+int wfm_batch_set_phase(wfm_model* h, const double* alpha, int n) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->nbatch <= 1) return wfm_set_phase(h, alpha, n);
+    return batch_set_phase(h, alpha, n, n);
+}
+int wfm_batch_set_modulus(wfm_model* h, const double* beta, int n) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->nbatch <= 1) return wfm_set_modulus(h, beta, n);
+    return batch_set_modulus(h, beta, n, n);
+}
+int wfm_batch_set_defocus(wfm_model* h, const double* defoc, int n) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->nbatch <= 1) return wfm_set_defocus(h, defoc, n);
+    return batch_set_defocus(h, defoc, n, n);
+}
+
 int wfm_set_pupil_arrays(wfm_model* h, const double* rho, const double* phi, const double* psi, const uint8_t* mask) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->nbatch > 1) return h->fail(WFM_ERR_UNSUPPORTED, "wfm_set_pupil_arrays: not available on a batch handle");
     WFM_CK(h, cudaSetDevice(h->device));
     const size_t npix = h->npix();
     WFM_CK(h, cudaStreamSynchronize(h->stream));
@@ -786,10 +909,11 @@ static int copy_out(wfm_model* h, void* out, const void* dev, size_t bytes) {
     return check_pipeline(h);
 }
 
-int wfm_get_rho(wfm_model* h, double* out) { return h ? copy_out(h, out, h->rho.p, 8 * (size_t)h->npix()) : WFM_ERR_INVALID_ARG; }
-int wfm_get_phi(wfm_model* h, double* out) { return h ? copy_out(h, out, h->phi.p, 8 * (size_t)h->npix()) : WFM_ERR_INVALID_ARG; }
-int wfm_get_psi(wfm_model* h, double* out) { return h ? copy_out(h, out, h->psi.p, 8 * (size_t)h->npix()) : WFM_ERR_INVALID_ARG; }
-int wfm_get_mask(wfm_model* h, uint8_t* out) { return h ? copy_out(h, out, h->mask.p, (size_t)h->npix()) : WFM_ERR_INVALID_ARG; }
+// (batch handles: nbatch arrays, model after model)
+int wfm_get_rho(wfm_model* h, double* out) { return h ? copy_out(h, out, h->rho.p, 8 * (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
+int wfm_get_phi(wfm_model* h, double* out) { return h ? copy_out(h, out, h->phi.p, 8 * (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
+int wfm_get_psi(wfm_model* h, double* out) { return h ? copy_out(h, out, h->psi.p, 8 * (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
+int wfm_get_mask(wfm_model* h, uint8_t* out) { return h ? copy_out(h, out, h->mask.p, (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
 
 int wfm_compute_psf(wfm_model* h) { return h ? compute_psf_impl(h) : WFM_ERR_INVALID_ARG; }
 int wfm_invalidate(wfm_model* h) { return h ? invalidate(h) : WFM_ERR_INVALID_ARG; }
@@ -833,7 +957,7 @@ int wfm_roll_psf_dev(wfm_model* h, void* out_dev) {
     if (!h) return WFM_ERR_INVALID_ARG;
     if (!out_dev) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
     if (h->z0 != 0 || h->nzl != h->nz_global)
-        return h->fail(WFM_ERR_UNSUPPORTED, "the rolled PSF needs the whole stack on one handle (z roll crosses slabs)");
+        return h->fail(WFM_ERR_UNSUPPORTED, "the rolled PSF needs the whole stack of ONE model on the handle (z roll crosses slabs)");
     int rc = compute_psf_impl(h); if (rc) return rc;
     const size_t vox = (size_t)h->npix() * h->nzl;
     const unsigned grid = (unsigned)((vox + 255) / 256);
@@ -896,14 +1020,17 @@ static int apply_host(wfm_model* h, unsigned kinds, const void* q_host, std::vec
     WFM_CK(h, h->qdev.ensure(bytes));
     WFM_CK(h, cudaMemcpyAsync(h->qdev.p, q_host, bytes, cudaMemcpyHostToDevice, h->stream));
     int rc = wfm_apply_jacobian_dev(h, kinds, h->qdev.p, (double*)h->grad.p); if (rc) return rc;
-    g.resize(h->glen());
+    g.resize((size_t)h->glen() * h->nbatch);
     WFM_CK(h, cudaMemcpyAsync(g.data(), h->grad.p, 8 * g.size(), cudaMemcpyDeviceToHost, h->stream));
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     return check_pipeline(h);
 }
 
+#define WFM_NO_BATCH(h) do { if ((h)->nbatch > 1) return (h)->fail(WFM_ERR_UNSUPPORTED, "batch handle: use wfm_batch_apply_jacobian"); } while (0)
+
 int wfm_apply_j_phase(wfm_model* h, const void* q, double* out, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_NO_BATCH(h);
     if (!out || n != h->nphase || n <= 0) return h->fail(WFM_ERR_INVALID_ARG, "output length must equal nPhase");
     std::vector<double> g;
     int rc = apply_host(h, WFM_J_PHASE, q, g); if (rc) return rc;
@@ -913,6 +1040,7 @@ int wfm_apply_j_phase(wfm_model* h, const void* q, double* out, int n) {
 
 int wfm_apply_j_defocus(wfm_model* h, const void* q, double* out, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_NO_BATCH(h);
     if (!out || (n != 1 && n != 3)) return h->fail(WFM_ERR_INVALID_ARG, "defocus gradient has 1 or 3 elements");   // Q4
     std::vector<double> g;
     int rc = apply_host(h, WFM_J_DEFOCUS, q, g); if (rc) return rc;
@@ -922,6 +1050,7 @@ int wfm_apply_j_defocus(wfm_model* h, const void* q, double* out, int n) {
 
 int wfm_apply_j_modulus(wfm_model* h, const void* q, double* out, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_NO_BATCH(h);
     if (!out || n != h->nmod || n <= 0) return h->fail(WFM_ERR_INVALID_ARG, "output length must equal nModulus");
     std::vector<double> g;
     int rc = apply_host(h, WFM_J_MODULUS, q, g); if (rc) return rc;
@@ -939,8 +1068,20 @@ int wfm_apply_jacobian(wfm_model* h, int param, const void* q, double* out, int 
     }
 }
 
+// Batch handles: the Jacobians of every model in one pass.  q_host = [nbatch][Nz][Ny][Nx] like the PSF;
+// out = [nbatch][3 + nPhase + nModulus] = [defocus(3) | phase | modulus] per model (zeros for kinds not selected).
+int wfm_batch_apply_jacobian(wfm_model* h, unsigned kinds, const void* q, double* out) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
+    std::vector<double> g;
+    int rc = apply_host(h, kinds, q, g); if (rc) return rc;
+    memcpy(out, g.data(), 8 * g.size());
+    return WFM_OK;
+}
+
 int wfm_apply_j_all(wfm_model* h, const void* q, double* d3, double* ph, double* mo) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_NO_BATCH(h);
     unsigned kinds = 0;
     if (d3) kinds |= WFM_J_DEFOCUS;
     if (ph) kinds |= WFM_J_PHASE;

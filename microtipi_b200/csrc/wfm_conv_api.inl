@@ -303,7 +303,7 @@ int wfm_eval_fg(wfm_model* h, wfm_conv* c, int param, const double* x, int n, do
     if (!h || !c) return WFM_ERR_INVALID_ARG;
     if (!x || !cost || !grad_out) return h->fail(WFM_ERR_INVALID_ARG, "x / cost / grad_out is NULL");
     if (h->precision != WFM_F64) return h->fail(WFM_ERR_UNSUPPORTED, "wfm_eval_fg is fp64 only in this revision");
-    if (h->N != c->nx || h->nz_global != c->nz || h->z0 != 0 || h->nzl != h->nz_global)
+    if (h->N != c->nx || h->nz_global != c->nz || h->z0 != 0 || h->nzl != h->nz_global || h->nbatch != 1)
         return h->fail(WFM_ERR_INVALID_ARG, "model and data term must have the same (unsharded) shape");
     if (h->device != c->device) return h->fail(WFM_ERR_INVALID_ARG, "model and data term live on different devices");
     int rc;

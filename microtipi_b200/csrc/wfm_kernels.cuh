@@ -31,7 +31,8 @@ struct Geom {
     int N;          // Nx == Ny (WFM:158)
     int nz_global;  // Nz of the whole stack: drives PSFnorm and the wrap rule
     int z0;         // first plane of this slab
-    int nzl;        // planes in this slab
+    int nzl;        // planes in this handle: the slab, or nbatch stacked models of nzm planes each
+    int nzm;        // planes per model (== nzl unless the handle is a batch of independent models)
     double dz;
     double psf_norm;  // 1/(Nx*Ny*Nz)  WFM:284
 };
@@ -136,6 +137,53 @@ __global__ void k_set_modulus(double* __restrict__ rho, const double* __restrict
             acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(Z[in + (size_t)k * npix], beta.v[k]), beta_norm));
     }
     rho[in] = acc;
+}
+
+// Batch variants (handles created by wfm_create_batch: nbatch independent models that share optics and basis, each
+// with its own coefficient vectors -- BASELINE config 5).  blockIdx.y = model; coefficients come from device tables;
+// the arithmetic is that of the single-model kernels above, term by term.
+__global__ void k_set_phase_b(double* __restrict__ phi, const double* __restrict__ Z, const uint8_t* __restrict__ mask,
+                              const double* __restrict__ alpha_tab, int n, int off, int npix) {
+    const int in = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t mo = (size_t)blockIdx.y * npix;
+    wfm_grid_dep_trigger();
+    if (in >= npix) return;
+    double acc = 0.0;
+    if (mask[mo + in]) {
+        const double* al = alpha_tab + (size_t)blockIdx.y * n;
+        for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(Z[in + (size_t)(k + off) * npix], al[k]));
+    }
+    phi[mo + in] = acc;
+}
+__global__ void k_set_modulus_b(double* __restrict__ rho, const double* __restrict__ Z, const uint8_t* __restrict__ mask,
+                                const double* __restrict__ beta_tab, const double* __restrict__ bpar, int n, int npix) {
+    const int in = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t mo = (size_t)blockIdx.y * npix;
+    if (in >= npix) return;
+    double acc = 0.0;
+    if (mask[mo + in]) {
+        const double* be = beta_tab + (size_t)blockIdx.y * n;
+        const double bn = bpar[4 * blockIdx.y + 3];          // 1/|beta| of this model
+        for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(Z[in + (size_t)k * npix], be[k]), bn));
+    }
+    rho[mo + in] = acc;
+}
+// par[b] = {ni/lambda, deltaX, deltaY, -}
+__global__ void k_compute_defocus_b(double* __restrict__ psi, uint8_t* __restrict__ mask, const uint8_t* __restrict__ map,
+                                    int N, double dxy, const double* __restrict__ par) {
+    const int in = blockIdx.x * blockDim.x + threadIdx.x;
+    if (in >= N * N) return;
+    if (!map[in]) return;
+    const size_t mo = (size_t)blockIdx.y * N * N;
+    const double lambda_ni = par[4 * blockIdx.y], deltaX = par[4 * blockIdx.y + 1], deltaY = par[4 * blockIdx.y + 2];
+    const int nx = in % N, ny = in / N;
+    const double scale = 1.0 / __dmul_rn((double)N, dxy);
+    const double ay = __dsub_rn(__dmul_rn(scale, (double)kappa_dev(ny, N)), deltaY);
+    const double ax = __dsub_rn(__dmul_rn(scale, (double)kappa_dev(nx, N)), deltaX);
+    const double ry = __dmul_rn(ay, ay), rx = __dmul_rn(ax, ax);
+    const double q = __dsub_rn(__dsub_rn(__dmul_rn(lambda_ni, lambda_ni), rx), ry);
+    if (q < 0.0) { psi[mo + in] = 0.0; mask[mo + in] = 0; }
+    else { psi[mo + in] = __dsqrt_rn(q); mask[mo + in] = 1; }
 }
 
 // ================================================================================================
@@ -259,6 +307,7 @@ __global__ void k_pack_strip(double* __restrict__ s_rho, double* __restrict__ s_
     wfm_grid_dep_trigger();
     wfm_grid_dep_wait();
     if (cell >= N * pitch) return;
+    const size_t mo = (size_t)blockIdx.y * N * N, so = (size_t)blockIdx.y * N * pitch;   // model of a batch handle
     const int tile = cell / (N * C), rem = cell % (N * C);
     const int ky = rem / C, xi = tile * C + rem % C;
     double r = 0.0, f = 0.0, p = 0.0;
@@ -266,11 +315,11 @@ __global__ void k_pack_strip(double* __restrict__ s_rho, double* __restrict__ s_
     if (xi < nax) {
         const int in = act_x[xi] + N * ky;
         if (support[in]) {
-            fl = (uint8_t)(2u | (mask[in] ? 1u : 0u));
-            r = rho[in]; f = phi[in]; p = psi[in];
+            fl = (uint8_t)(2u | (mask[mo + in] ? 1u : 0u));
+            r = rho[mo + in]; f = phi[mo + in]; p = psi[mo + in];
         }
     }
-    s_rho[cell] = r; s_phi[cell] = f; s_psi[cell] = p; s_flags[cell] = fl;
+    s_rho[so + cell] = r; s_phi[so + cell] = f; s_psi[so + cell] = p; s_flags[so + cell] = fl;
 }
 
 // ================================================================================================
@@ -535,14 +584,16 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
     const int c = threadIdx.x % C, t = threadIdx.x / C;
-    const double s = defoc_scale_dev(a.g.z0 + pl, a.g.nz_global, a.g.dz);
+    const int bm = pl / a.g.nzm;                       // model of a batch handle (0 otherwise): its strip follows
+    const int ssub = sub + bm * (a.pitch / C);         // the previous model's, i.e. pitch/C tiles further on
+    const double s = defoc_scale_dev(a.g.z0 + (pl - bm * a.g.nzm), a.g.nz_global, a.g.dz);
     double rho[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r)
             if (leg_live<P::R1, NARROW>(r))
-                rho[u * P::R1 + r] = __ldg(&a.st.rho[((size_t)sub * N + (t + TT * u) + P::S1 * r) * C + c]);
+                rho[u * P::R1 + r] = __ldg(&a.st.rho[((size_t)ssub * N + (t + TT * u) + P::S1 * r) * C + c]);
     cx<T> v[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u) {
@@ -552,7 +603,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
             cx<T> val = mkc<T>((T)0, (T)0);
             if (leg_live<P::R1, NARROW>(r)) {
                 if (rho[e] != 0.0) {
-                    const size_t cell = ((size_t)sub * N + (t + TT * u) + P::S1 * r) * C + c;
+                    const size_t cell = ((size_t)ssub * N + (t + TT * u) + P::S1 * r) * C + c;
                     const double ph = __dadd_rn(__ldg(&a.st.phi[cell]), __dmul_rn(s, __ldg(&a.st.psi[cell])));
                     double sn, cs;
                     WFM_SINCOS(ph, &sn, &cs);
@@ -795,6 +846,8 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
     const int xi = sub * C + c;
     const bool colvalid = xi < a.nax;
     const size_t tbase = (size_t)sub * N * C + c;      // this thread's column inside the tile-major strip
+    const int bm = pl / a.g.nzm;                       // model of a batch handle (0 otherwise)
+    const size_t sbase = tbase + (size_t)bm * N * a.pitch;   // the same column in that model's pupil strip
     const cx<T>* src = a.T2 + (size_t)(pl % ring) * N * a.pitch + tbase;
     cx<T> v[E];
 #pragma unroll
@@ -811,14 +864,14 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 #pragma unroll
         for (int r = 0; r < P::RL; ++r)
             if (leg_live<P::RL, NARROW>(r))
-                fl |= (unsigned)__ldg(&a.st.flags[tbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
+                fl |= (unsigned)__ldg(&a.st.flags[sbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
     fft_inplace<T, P, L, CtaSync, PipePrefetchHook, false, WFM_JAC_TW_TREE>(v, cells + c, t, tw_s, tw_s + N, 0,
                                                                             PipePrefetchHook{qu, ctl, a.g.nzl});
-    const int iz = a.g.z0 + pl;
+    const int iz = a.g.z0 + (pl - bm * a.g.nzm);
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
     const bool mod_plane = (a.Gm != nullptr) && (!a.last_plane_only || iz == a.g.nz_global - 1);
     const unsigned want = mod_plane ? 3u : 1u;         // mask bit, plus the support bit when J is needed
-    const size_t obase = (size_t)pl * N * a.pitch;
+    const size_t obase = (size_t)pl * N * a.pitch + tbase;
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
@@ -827,14 +880,15 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
             if (!leg_live<P::RL, NARROW>(r)) continue;
             const unsigned f = (fl >> (2 * e)) & want;
             if (!f) continue;
-            const size_t cell = tbase + (size_t)((t + TT * u) + P::SL * r) * C;
+            const size_t row = (size_t)((t + TT * u) + P::SL * r) * C;
+            const size_t cell = sbase + row;
             const double ph = __dadd_rn(__ldg(&a.st.phi[cell]), __dmul_rn(s, __ldg(&a.st.psi[cell])));
             const double rho = __ldg(&a.st.rho[cell]);
             double sn, cs;
             WFM_SINCOS(ph, &sn, &cs);
             const double br = (double)v[e].x, bi = (double)v[e].y;
-            if (f & 1u) a.Gj[obase + cell] = rho * (br * sn + bi * cs);
-            if (mod_plane) a.Gm[obase + cell] = br * cs - bi * sn;
+            if (f & 1u) a.Gj[obase + row] = rho * (br * sn + bi * cs);
+            if (mod_plane) a.Gm[obase + row] = br * cs - bi * sn;
         }
 }
 
@@ -902,7 +956,9 @@ struct ReduceArgs {
     unsigned kinds;
     int last_plane_only;
     double dxy, lambda_ni, deltaX, deltaY;
-    double* block_part;      // [nchunks][nblocks][glen]
+    const double* bpar;      // batch handles: [nbatch][4] = {ni/lambda, deltaX, deltaY, 1/|beta|} per model, else NULL
+    int cpm;                 // plane chunks per model: grid.y = nbatch * cpm
+    double* block_part;      // [nbatch][cpm][nblocks][glen]
     int glen;                // 3 + nphase + nmod
 };
 
@@ -924,9 +980,11 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     const int in = sup ? a.in_list[li] : 0;
     wfm_grid_dep_trigger();
     wfm_grid_dep_wait();                               // Gj / Gm come from the pipeline kernel before us
-    const bool m = sup && (a.flags[cell] & 1u);
-    const int p0 = blockIdx.y * WFM_RED_PLANES;
-    const int p1 = (p0 + WFM_RED_PLANES < a.g.nzl) ? p0 + WFM_RED_PLANES : a.g.nzl;
+    const int bm = blockIdx.y / a.cpm;                 // model of a batch handle (0 otherwise); chunks never straddle models
+    const int zl0 = (blockIdx.y - bm * a.cpm) * WFM_RED_PLANES;   // first plane of the chunk inside its model
+    const int p0 = bm * a.g.nzm + zl0;
+    const int p1 = (zl0 + WFM_RED_PLANES < a.g.nzm) ? p0 + WFM_RED_PLANES : (bm + 1) * a.g.nzm;
+    const bool m = sup && (a.flags[(size_t)bm * img + cell] & 1u);
     double gP = 0.0, gD = 0.0, gM = 0.0;
     if (m) {
         // all loads of the chunk in flight at once (the kernel is latency-bound: one DRAM round trip per thread
@@ -937,25 +995,26 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
 #pragma unroll
         for (int k = 0; k < WFM_RED_PLANES; ++k) {
             gP += jin[k];
-            gD += defoc_depth_dev(a.g.z0 + p0 + k, a.g.nz_global, a.g.dz) * jin[k];
+            gD += defoc_depth_dev(a.g.z0 + zl0 + k, a.g.nz_global, a.g.dz) * jin[k];
         }
     }
     if (sup && (a.kinds & 4u)) {
         double jm[WFM_RED_PLANES];
 #pragma unroll
         for (int k = 0; k < WFM_RED_PLANES; ++k)
-            jm[k] = (p0 + k < p1 && (!a.last_plane_only || a.g.z0 + p0 + k == a.g.nz_global - 1))
+            jm[k] = (p0 + k < p1 && (!a.last_plane_only || a.g.z0 + zl0 + k == a.g.nz_global - 1))
                         ? __ldcs(&a.Gm[(size_t)(p0 + k) * img + cell]) : 0.0;
 #pragma unroll
         for (int k = 0; k < WFM_RED_PLANES; ++k) gM += jm[k];
     }
     // defocus weights: idef = 1/psi on maskPupil (WFM:1251); rx, ry of the prologue WFM:1040-1061
     double wD = 0.0, rx = 0.0, ry = 0.0;
+    const double lambda_ni = a.bpar ? a.bpar[4 * bm] : a.lambda_ni;
     if (m && (a.kinds & 1u)) {
         const double scale = 1.0 / ((double)N * a.dxy);
-        wD = gD * (1.0 / a.psi[in]);
-        rx = (double)kappa_dev(in % N, N) * scale - a.deltaX;
-        ry = (double)kappa_dev(in / N, N) * scale - a.deltaY;
+        wD = gD * (1.0 / a.psi[(size_t)bm * N * N + in]);
+        rx = (double)kappa_dev(in % N, N) * scale - (a.bpar ? a.bpar[4 * bm + 1] : a.deltaX);
+        ry = (double)kappa_dev(in / N, N) * scale - (a.bpar ? a.bpar[4 * bm + 2] : a.deltaY);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* out = a.block_part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * a.glen;
@@ -967,7 +1026,7 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
             double val = 0.0;
             if (j < a.glen && sup) {
                 if (j < 3) {
-                    if (a.kinds & 1u) val = (j == 0) ? wD * a.lambda_ni : (j == 1 ? wD * rx : wD * ry);
+                    if (a.kinds & 1u) val = (j == 0) ? wD * lambda_ni : (j == 1 ? wD * rx : wD * ry);
                 } else if (j < 3 + a.nphase) {
                     if ((a.kinds & 2u) && m) val = gP * a.Zs[(size_t)(j - 3 + a.phase_off) * a.ncells + li];
                 } else {
@@ -1004,14 +1063,19 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
 //   modulus: 2*PSFnorm*sum J*Z_k * (1-(beta_k*NBeta)^2)*NBeta (WFM:674)
 #define WFM_FINAL_THREADS 128
 // One CTA per gradient component: strided partial sums, warp shuffle, then across warps.
+// Batch handles: blockIdx.y = model, nblocks partials per model, beta / 1/|beta| from the device tables.
 __global__ void __launch_bounds__(WFM_FINAL_THREADS) k_jac_final(const double* __restrict__ block_part, int nblocks,
                                                                 int glen, int nphase, double psf_norm, Coefs beta,
                                                                 double nbeta, unsigned kinds,
+                                                                const double* __restrict__ beta_tab, int nmod,
+                                                                const double* __restrict__ bpar,
                                                                 double* __restrict__ grad) {
     __shared__ double red[WFM_FINAL_THREADS / 32];
     const int j = blockIdx.x;
     double x = 0.0;
     wfm_grid_dep_wait();
+    block_part += (size_t)blockIdx.y * nblocks * glen;
+    grad += (size_t)blockIdx.y * glen;
     for (int b = threadIdx.x; b < nblocks; b += WFM_FINAL_THREADS) x += block_part[(size_t)b * glen + j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
@@ -1027,7 +1091,8 @@ __global__ void __launch_bounds__(WFM_FINAL_THREADS) k_jac_final(const double* _
         if (kinds & 2u) out = -2.0 * psf_norm * x;
     } else {
         if (kinds & 4u) {
-            const double bk = beta.v[j - 3 - nphase] * nbeta;
+            if (beta_tab) nbeta = bpar[4 * blockIdx.y + 3];
+            const double bk = (beta_tab ? beta_tab[(size_t)blockIdx.y * nmod + (j - 3 - nphase)] : beta.v[j - 3 - nphase]) * nbeta;
             out = 2.0 * psf_norm * x * (1.0 - bk * bk) * nbeta;
         }
     }

@@ -155,18 +155,26 @@ class WideFieldModel(MicroscopeModel):
     parametersFlag = [0, 1, 2]                   # WFM:123
 
     def __init__(self, psfShape, nPhase=0, nModulus=1, NA=None, lambda_=None, ni=None, dxy=None, dz=None,
-                 radial=False, single=False, *, device=0, z0=0, nz_local=None, lib=None, basis=None):
+                 radial=False, single=False, *, device=0, z0=0, nz_local=None, lib=None, basis=None, nbatch=1):
         """WFM:154-188.  ``z0/nz_local`` make this object one z-slab of the global stack (SURVEY 8e);
         ``lib`` lets the tests bind another build of the same ABI; ``basis`` (optional
-        ``callable(Nzern) -> Z[Nzern, Npix]``) replaces the device-side computeZernike()."""
+        ``callable(Nzern) -> Z[Nzern, Npix]``) replaces the device-side computeZernike(); ``nbatch`` > 1 makes the
+        handle a batch of independent models (see WideFieldModelBatch)."""
         super().__init__(psfShape, dxy, dz, single)
         self._lib = lib if lib is not None else capi.load_library()
         self._h = C.c_void_p()
         self._basis_fn = basis
         nzl = self.Nz - z0 if nz_local is None else nz_local
         self.z0, self.nz_local = int(z0), int(nzl)
-        rc = self._lib.wfm_create_slab(C.byref(self._h), self.Nx, self.Ny, self.Nz, self.z0, self.nz_local,
-                                       self.dxy, self.dz, capi.WFM_F32 if single else capi.WFM_F64, int(device))
+        self.nbatch = int(nbatch)
+        prec = capi.WFM_F32 if single else capi.WFM_F64
+        if self.nbatch > 1:
+            rc = self._lib.wfm_create_batch(C.byref(self._h), self.Nx, self.Ny, self.Nz, self.nbatch, self.dxy,
+                                            self.dz, prec, int(device))
+            self.nz_local = self.Nz * self.nbatch                          # planes held by the handle
+        else:
+            rc = self._lib.wfm_create_slab(C.byref(self._h), self.Nx, self.Ny, self.Nz, self.z0, self.nz_local,
+                                           self.dxy, self.dz, prec, int(device))
         if rc != capi.WFM_OK:
             msg = self._lib.wfm_last_error(None).decode()
             self._h = C.c_void_p()
@@ -464,9 +472,9 @@ class WideFieldModel(MicroscopeModel):
     def _get_pupil(self, name, dtype=np.float64):
         if self.PState < 1:
             self.computePsf()                                              # WFM:1674-1676 etc.
-        out = np.empty(self._npix(), dtype=dtype)
+        out = np.empty(self._npix() * self.nbatch, dtype=dtype)
         self._call(name, out.ctypes.data_as(C.c_void_p))
-        return out
+        return out if self.nbatch == 1 else out.reshape(self.nbatch, -1)
 
     def getRho(self):                                                      # WFM:1673
         return self._get_pupil("wfm_get_rho")
@@ -569,3 +577,58 @@ class WideFieldModel(MicroscopeModel):
         self.psf = None
         if self._h:
             self._lib.wfm_invalidate(self._h)
+
+
+class WideFieldModelBatch(WideFieldModel):
+    """``nbatch`` independent WideFieldModels of one shape on ONE handle (BASELINE config 5: parameter estimation over
+    many bead PSFs).  The models share optics and basis; ``setPhaseBatch / setModulusBatch / setDefocusBatch`` take one
+    row per model, the inherited scalar setters give every model the same vector.  ``getPsf()`` has shape
+    (nbatch, Nz, Ny, Nx); ``applyJacobianBatch`` returns (defocus[nbatch,3], phase[nbatch,nPhase], modulus[nbatch,nModulus])
+    -- per model exactly what apply_J_defocus / apply_J_phase / apply_J_modulus (WFM:1029, 738, 429) return."""
+
+    def __init__(self, psfShape, nbatch, *args, **kw):
+        super().__init__(psfShape, *args, nbatch=nbatch, **kw)
+
+    def _table(self, tab, n=None):
+        t = np.ascontiguousarray(tab, dtype=np.float64)
+        if t.ndim != 2 or t.shape[0] != self.nbatch or (n is not None and t.shape[1] != n):
+            raise ValueError("coefficient table must have one row per model")
+        return t
+
+    def setPhaseBatch(self, alpha):                                        # setPhase (WFM:1625-1649) per model
+        t = self._table(alpha)
+        if t.shape[1] != self.nPhase:
+            self.setNPhase(t.shape[1])
+        self._call("wfm_batch_set_phase", t.ctypes.data_as(C.c_void_p), t.shape[1])
+        self.freeMem()
+
+    def setModulusBatch(self, beta):                                       # setModulus (WFM:1588-1610) per model
+        t = self._table(beta)
+        if t.shape[1] != self.nModulus:
+            self.setNModulus(t.shape[1])
+        self._call("wfm_batch_set_modulus", t.ctypes.data_as(C.c_void_p), t.shape[1])
+        self.freeMem()
+
+    def setDefocusBatch(self, defoc):                                      # setDefocus (WFM:1510-1534) per model
+        t = self._table(defoc)
+        if t.shape[1] not in (1, 3):
+            raise ValueError("bad defocus  parameters")
+        self._call("wfm_batch_set_defocus", t.ctypes.data_as(C.c_void_p), t.shape[1])
+        self.freeMem()
+
+    def getPsf(self):
+        return super().getPsf().reshape(self.nbatch, self.Nz, self.Ny, self.Nx)
+
+    def get_cpxPsf(self):
+        return super().get_cpxPsf().reshape(self.nbatch, self.Nz, self.Ny, self.Nx, 2)
+
+    def applyJacobianBatch(self, q, kinds=capi.WFM_J_DEFOCUS | capi.WFM_J_PHASE | capi.WFM_J_MODULUS):
+        qh = _as_host(q, self._dtype())
+        if qh.size != self._npix() * self.nz_local:
+            raise ValueError("gradient does not have the shape of the PSF batch")
+        out = np.zeros((self.nbatch, self.gradLength()))
+        self._call("wfm_batch_apply_jacobian", int(kinds), qh.ctypes.data_as(C.c_void_p),
+                   out.ctypes.data_as(C.c_void_p))
+        self.PState = self._lib.wfm_psf_state(self._h)
+        nP = self.getNPhase()
+        return out[:, :3], out[:, 3:3 + nP], out[:, 3 + nP:]

@@ -224,3 +224,50 @@ def test_wide_pupil_uses_generic_kernels(lib):
     assert o.rel_l2(m.apply_J_phase(q).data, ref.apply_J_phase(q)) <= 1e-12
     assert o.rel_l2(m.apply_J_defocus(q).data, ref.apply_J_defocus(q)) <= 1e-12
     m.close()
+
+
+def _batch_case(lib, N, Nz, B, single, nModulus=4):
+    """B models with different phase / modulus / defocus vectors on one batch handle vs B oracle models."""
+    from microtipi_b200 import WideFieldModelBatch
+    rng = np.random.default_rng(77)
+    alpha = rng.normal(0, 0.3, (B, 10))
+    beta = np.tile(np.array([1.0, 0.1, -0.05, 0.02][:nModulus]), (B, 1)) + rng.normal(0, 0.02, (B, nModulus))
+    defoc = np.stack([[P["ni"] / P["lam"] * (1 + 0.01 * b), 2e4 * b, -1e4 * b] for b in range(B)])
+    m = WideFieldModelBatch((N, N, Nz), B, 10, nModulus, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, single,
+                            lib=lib, basis=lambda nz: o.compute_zernike(nz, N, N, P["NA"], P["lam"], P["dxy"]))
+    m.setPhaseBatch(alpha)
+    m.setModulusBatch(beta)
+    m.setDefocusBatch(defoc)
+    refs = []
+    for b in range(B):
+        r = o.WideFieldModelOracle((N, N, Nz), 10, nModulus, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], single=single)
+        r.setPhase(alpha[b]); r.setModulus(beta[b]); r.setDefocus(defoc[b])
+        refs.append(r)
+    return m, refs
+
+
+@pytest.mark.parametrize("N,Nz,B,single", [(32, 5, 3, False), (64, 17, 2, False), (32, 4, 3, True)])
+def test_batch_handle_matches_independent_oracle_models(lib, N, Nz, B, single):
+    m, refs = _batch_case(lib, N, Nz, B, single)
+    t = tol(single)
+    tj = 20 * t if single else t
+    rho, phi, psi, mask = m.getRho(), m.getPhi(), m.getPsi(), m.getMaskPupil()
+    psf, cpx = m.getPsf(), m.get_cpxPsf()
+    q = np.stack([o.synthetic_q(N, N, Nz, seed=42 + b, single=single) for b in range(B)])
+    d, p, mo = m.applyJacobianBatch(q)
+    for b, r in enumerate(refs):
+        np.testing.assert_array_equal(rho[b], r.rho.ravel())           # setters stay bit exact per model
+        np.testing.assert_array_equal(phi[b], r.phi.ravel())
+        np.testing.assert_array_equal(psi[b], r.psi.ravel())
+        np.testing.assert_array_equal(mask[b], r.maskPupil.ravel())
+        assert o.rel_l2(psf[b], r.getPsf()) <= t
+        assert o.rel_l2(cpx[b], r.get_cpxPsf()) <= t
+        assert o.rel_l2(d[b], r.apply_J_defocus(q[b])) <= tj
+        assert o.rel_l2(p[b], r.apply_J_phase(q[b])) <= tj
+        assert o.rel_l2(mo[b], r.apply_J_modulus(q[b])) <= tj
+    # scalar setters broadcast; single-model outputs are refused on a batch handle
+    m.setPhase(np.zeros(10))
+    assert np.all(m.getPhi() == 0)
+    with pytest.raises(RuntimeError):
+        m.apply_J_phase(q)
+    m.close()

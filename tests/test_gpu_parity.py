@@ -258,6 +258,31 @@ def test_config5_independent_models(lib, single):
         m.close()
 
 
+@pytest.mark.parametrize("N,Nz,B,single", [(64, 17, 3, False), (256, 8, 4, False), (256, 8, 3, True), (512, 3, 2, False)])
+def test_config5_batch_handle(lib, N, Nz, B, single):
+    """BASELINE config 5 on ONE batch handle (wfm_create_batch): every model has its own phase, modulus and
+    defocus vector; PSF, cpxPsf and the three Jacobians of each model against its own oracle model."""
+    from tests.test_emu_parity import _batch_case
+    m, refs = _batch_case(lib, N, Nz, B, single)
+    t = tol(single)
+    tj = 20 * t if single else t
+    rho, phi, psi, mask = m.getRho(), m.getPhi(), m.getPsi(), m.getMaskPupil()
+    psf, cpx = m.getPsf(), m.get_cpxPsf()
+    q = np.stack([o.synthetic_q(N, N, Nz, seed=42 + b, single=single) for b in range(B)])
+    d, p, mo = m.applyJacobianBatch(q)
+    for b, r in enumerate(refs):
+        np.testing.assert_array_equal(rho[b], r.rho.ravel())
+        np.testing.assert_array_equal(phi[b], r.phi.ravel())
+        np.testing.assert_array_equal(psi[b], r.psi.ravel())
+        np.testing.assert_array_equal(mask[b], r.maskPupil.ravel())
+        assert o.rel_l2(psf[b], r.getPsf()) <= t
+        assert o.rel_l2(cpx[b], r.get_cpxPsf()) <= t
+        assert o.rel_l2(d[b], r.apply_J_defocus(q[b])) <= tj
+        assert o.rel_l2(p[b], r.apply_J_phase(q[b])) <= tj
+        assert o.rel_l2(mo[b], r.apply_J_modulus(q[b])) <= tj
+    m.close()
+
+
 def _bead_object(N, Nz, radius_px=2.5):
     zz, yy, xx = np.meshgrid(*(np.arange(n) - n // 2 for n in (Nz, N, N)), indexing="ij")
     obj = ((zz ** 2 + yy ** 2 + xx ** 2) <= radius_px ** 2).astype(np.float64)

@@ -1,6 +1,7 @@
 """BASELINE config 5: batched PSF parameter estimation over B independent 256x256x64 bead PSFs
-(throughput mode).  Every model is its own handle on its own CUDA stream; one evaluation =
-setParam(phase) -> computePsf -> apply_J_phase for every model.  Prints one JSON line."""
+(throughput mode).  One evaluation = setParam(phase) -> computePsf -> apply_J_phase for every model.
+Default: every model is its own handle on its own CUDA stream.  --batch: ONE batch handle
+(wfm_create_batch), all planes of all models through one pipeline launch.  Prints one JSON line."""
 import argparse
 import json
 import os
@@ -12,7 +13,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from microtipi_b200 import WideFieldModel  # noqa: E402
+from microtipi_b200 import WideFieldModel, WideFieldModelBatch  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--models", type=int, default=64)
@@ -21,13 +22,24 @@ ap.add_argument("--nz", type=int, default=64)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--single", action="store_true")
 ap.add_argument("--one-stream", action="store_true", help="all models on one stream (no overlap)")
+ap.add_argument("--batch", action="store_true", help="one batch handle instead of one handle per model")
 a = ap.parse_args()
 P = dict(NA=1.4, lam=542e-9, ni=1.518, dxy=64.5e-9, dz=160e-9)
 dev = torch.device("cuda", 0)
 tdt = torch.float32 if a.single else torch.float64
 models, qs, grads = [], [], []
 shared = torch.cuda.Stream()
-for b in range(a.models):
+alphas = [np.random.default_rng(1234 + b).normal(0.0, 0.3, 10) for b in range(a.models)]
+if a.batch:
+    bm = WideFieldModelBatch((a.nxy, a.nxy, a.nz), a.models, 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"],
+                             False, a.single)
+    vox = a.nxy * a.nxy * a.nz * a.models
+    bq = torch.empty(vox, dtype=tdt, device=dev)
+    for b in range(a.models):
+        bm.fillUniform(bq.data_ptr() + b * (vox // a.models) * bq.element_size(), 42 + b, 0, vox // a.models)
+    bg = torch.zeros(a.models * bm.gradLength(), dtype=torch.float64, device=dev)
+    atab = np.stack(alphas)
+for b in range(0 if a.batch else a.models):
     m = WideFieldModel((a.nxy, a.nxy, a.nz), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, a.single)
     if a.one_stream:
         m.setStream(shared.cuda_stream)
@@ -36,10 +48,14 @@ for b in range(a.models):
     m.fillUniform(q.data_ptr(), 42 + b, 0, vox)
     g = torch.zeros(m.gradLength(), dtype=torch.float64, device=dev)
     models.append(m); qs.append(q); grads.append(g)
-alphas = [np.random.default_rng(1234 + b).normal(0.0, 0.3, 10) for b in range(a.models)]
 
 
 def evaluate(i):
+    if a.batch:
+        bm.setPhaseBatch(atab + 1e-3 * (i % 7))
+        bm.computePsf()
+        bm.applyJacobianDevice(2, bq.data_ptr(), bg.data_ptr())
+        return
     for b, m in enumerate(models):
         x = m.parameterCoefs[m.PHASE]
         x.data[:] = alphas[b] + 1e-3 * (i % 7)
@@ -60,6 +76,6 @@ planes = a.models * a.nz * a.steps
 es = 4 if a.single else 8
 gbs = planes * 6 * es * a.nxy * a.nxy / dt / 1e9
 print(json.dumps({"config": f"{a.models} x {a.nxy}x{a.nxy}x{a.nz} {'fp32' if a.single else 'fp64'}",
-                  "streams": "one" if a.one_stream else "per-model", "z_planes_per_s": planes / dt,
+                  "streams": "batch handle" if a.batch else ("one" if a.one_stream else "per-model"), "z_planes_per_s": planes / dt,
                   "ms_per_evaluation_of_all_models": 1e3 * dt / a.steps, "algorithmic_GBps": gbs,
                   "roofline_frac_of_6459": gbs / 6459.0}))
