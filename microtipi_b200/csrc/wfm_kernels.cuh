@@ -347,6 +347,7 @@ struct PipeCtl {
     int lag;           // B(p - lag) is queued next to A(p)
     int nA, nB;        // items per plane
     int roles;         // bit 0: run A items, bit 1: run B items (both set in production)
+    int nzm;           // planes per model (batch handles), else the slab's plane count
 };
 
 // fp64 column tile of the pipelines for N >= 256: 4 columns (64-byte segments of conj(a)) give
@@ -417,10 +418,12 @@ template <typename T, int N> struct PipeCfg {
 #endif
 };
 
-struct PipeItem { int type; int plane; int sub; };   // type 0 = A, 1 = B, -1 = done
+// type 0 = A, 1 = B, -1 = done; model = plane / nzm (batch handles: which model's pupil; 0 otherwise)
+struct PipeItem { int type; int plane; int sub; int model; };
 
 WFM_DEVI PipeItem pipe_decode(unsigned idx, int P, const PipeCtl& c) {
     PipeItem it;
+    it.model = 0;
     const int lag = c.lag < P ? c.lag : P;
     const unsigned headA = (unsigned)lag * c.nA;
     const unsigned per = (unsigned)(c.nA + c.nB);
@@ -481,9 +484,13 @@ WFM_DEVI void pipe_finish(const PipeCtl& c, int P) {
 // the ring size -- is ~1.3 items per CTA instead of 2.  At claim time thread 0 also probes the
 // item's dependency counter once (acquire): in steady state it is already met.
 struct PipeQueue {
-    unsigned* s;   // shared: s[0..1] item index, s[2..3] dependency already satisfied
+    // shared: per slot {type, plane, sub, model, dependency already satisfied}.  Thread 0 decodes the queue index
+    // when it claims it (late in the previous item), so the other threads start an item with five shared-memory
+    // reads instead of the integer divisions of pipe_decode (measured: 0.8445 -> 0.8335 ms/step for one division).
+    int* s;
     int cur;
     bool pre;      // (thread 0) next item already claimed during this item
+    static constexpr int SLOT = 5;
     WFM_DEVI static bool probe(const PipeItem& it, const PipeCtl& c) {
         const unsigned* cnt; unsigned target;
         if (it.type == 0) {
@@ -500,19 +507,23 @@ struct PipeQueue {
     WFM_DEVI void claim(int slot, const PipeCtl& c, int P) {
         const unsigned idx = atomicAdd(c.queue, 1u);
         const PipeItem it = pipe_decode(idx, P, c);
-        s[slot] = idx;
-        s[2 + slot] = (it.type < 0 || probe(it, c)) ? 1u : 0u;
+        int* d = s + slot * SLOT;
+        d[0] = it.type; d[1] = it.plane; d[2] = it.sub; d[3] = it.type < 0 ? 0 : it.plane / c.nzm;
+        d[4] = (it.type < 0 || probe(it, c)) ? 1 : 0;
     }
-    WFM_DEVI void init(unsigned* smem4, const PipeCtl& c, int P) {
-        s = smem4; cur = 0; pre = false;
+    WFM_DEVI void init(int* smem10, const PipeCtl& c, int P) {
+        s = smem10; cur = 0; pre = false;
         if (threadIdx.x == 0) claim(0, c, P);
         __syncthreads();
     }
     // the current item; `ready` tells whether its dependency was already observed as met
-    WFM_DEVI PipeItem take(const PipeCtl& c, int P, bool& ready) {
+    WFM_DEVI PipeItem take(const PipeCtl&, int, bool& ready) {
         pre = false;
-        ready = s[2 + cur] != 0u;
-        return pipe_decode(s[cur], P, c);
+        const int* d = s + cur * SLOT;
+        PipeItem it;
+        it.type = d[0]; it.plane = d[1]; it.sub = d[2]; it.model = d[3];
+        ready = d[4] != 0;
+        return it;
     }
     // claim the next item (thread 0, once per item; called from inside the item and again, as a
     // no-op, before the item is published)
@@ -578,13 +589,13 @@ template <typename T> struct PsfArgs {
 template <int R, bool NARROW> WFM_DEVI constexpr bool leg_live(int r) { return !NARROW || r < R / 4 || r >= R - R / 4; }
 
 template <typename T, int N, bool NARROW>
-WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int bm, int ring, cx<T>* cells, const cx<T>* tw_s,
                             const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
     const int c = threadIdx.x % C, t = threadIdx.x / C;
-    const int bm = pl / a.g.nzm;                       // model of a batch handle (0 otherwise): its strip follows
+    // bm: model of a batch handle (0 otherwise): its strip follows
     const int ssub = sub + bm * (a.pitch / C);         // the previous model's, i.e. pitch/C tiles further on
     const double s = defoc_scale_dev(a.g.z0 + (pl - bm * a.g.nzm), a.g.nz_global, a.g.dz);
     double rho[E];
@@ -703,7 +714,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
     wfm_grid_dep_trigger();  // the next kernel's CTAs may take the place of ours as we exit
     wfm_grid_dep_wait();     // the tables above are constants; everything below depends on the previous kernel
-    __shared__ unsigned s_queue[4];
+    __shared__ int s_queue[2 * PipeQueue::SLOT];
     PipeQueue qu;
     const int P = a.g.nzl;
     qu.init(s_queue, ctl, P);
@@ -715,7 +726,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                psf_cols_item<T, N, NARROW>(a, it.plane, it.sub, ctl.ring, cells, tw_s, dep, qu, ctl);
+                psf_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, ctl.ring, cells, tw_s, dep, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntA[it.plane]);
@@ -837,7 +848,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 //   jin = rho*(B_re sin ph + B_im cos ph)   on maskPupil   (WFM:925-928, 1253)
 //   J   = B_re cos ph - B_im sin ph         on the support (WFM:607-611)
 template <typename T, int N, bool NARROW>
-WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int bm, int ring, cx<T>* cells, const cx<T>* tw_s,
                             PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
@@ -846,7 +857,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
     const int xi = sub * C + c;
     const bool colvalid = xi < a.nax;
     const size_t tbase = (size_t)sub * N * C + c;      // this thread's column inside the tile-major strip
-    const int bm = pl / a.g.nzm;                       // model of a batch handle (0 otherwise)
+    // bm: model of a batch handle (0 otherwise)
     const size_t sbase = tbase + (size_t)bm * N * a.pitch;   // the same column in that model's pupil strip
     const cx<T>* src = a.T2 + (size_t)(pl % ring) * N * a.pitch + tbase;
     cx<T> v[E];
@@ -903,7 +914,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
     wfm_grid_dep_trigger();  // the next kernel's CTAs may take the place of ours as we exit
     wfm_grid_dep_wait();     // the tables above are constants; everything below depends on the previous kernel
-    __shared__ unsigned s_queue[4];
+    __shared__ int s_queue[2 * PipeQueue::SLOT];
     PipeQueue qu;
     const int P = a.g.nzl;
     qu.init(s_queue, ctl, P);
@@ -922,7 +933,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
         } else {
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                jac_cols_item<T, N, NARROW>(a, it.plane, it.sub, ctl.ring, cells, tw_s, qu, ctl);
+                jac_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, ctl.ring, cells, tw_s, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntB[it.plane]);
