@@ -260,12 +260,21 @@ __global__ void __launch_bounds__(RowCfg<N / 2>::THREADS) k_conv_rows_c2r(ConvAr
 // tile -> base: tiles_per_outer tiles of CW columns inside each of `nouter` blocks of `outer_stride` elements
 template <typename T, int LEN> struct ConvColCfg {
     static constexpr int TT = Plan<LEN>::T;
-    static constexpr int CW = (sizeof(T) == 8) ? (TT >= 64 ? 4 : 8) : 8;
+#ifndef WFM_CONV_CW_LONG
+#define WFM_CONV_CW_LONG 8   /* columns per tile when the transform takes >= 64 threads: full 128-byte lines (eval_fg 3.53 -> 3.29 ms against 4 columns) */
+#endif
+    static constexpr int CW = (sizeof(T) == 8) ? (TT >= 64 ? (Plan<LEN>::E == 8 ? WFM_CONV_CW_LONG : 4) : 8) : 8;   // (E = 16 plans: 4, registers)
     static constexpr int THREADS = CW * TT;
     static constexpr int SH = ilog2_c(Plan<LEN>::S1);
     using ColL = ColLayout<CW, SH>;
     static constexpr int CELLS = CW * (ColL::pad_c(LEN - 1) + 1);
     static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + LEN + 16);
+    // k_conv_cols_zz took 88-92 registers = 2 CTAs per SM (ncu, profiles/r01n_conv_ncu_full.md: warps active 24 %,
+    // DRAM 42 %); three resident CTAs where the tile allows it
+#ifndef WFM_CONV_ZZ_MINB
+#define WFM_CONV_ZZ_MINB 3
+#endif
+    static constexpr int MINB_ZZ = (THREADS <= 256 && LEN <= 256) ? WFM_CONV_ZZ_MINB : 1;
 };
 
 template <typename T, int LEN, int STORE>
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS) k_conv_cols(ConvA
 // Saves one write + read of the work volume per transform pair; the only extra cost is one exchange through the
 // tile's shared cells (the first transform leaves its output in output-slot order, the second wants input-slot order).
 template <typename T, int LEN, int MUL>
-__global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS) k_conv_cols_zz(ConvArgs<T> a, size_t stride, int tiles_per_outer,
+__global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS, ConvColCfg<T, LEN>::MINB_ZZ) k_conv_cols_zz(ConvArgs<T> a, size_t stride, int tiles_per_outer,
                                                                                size_t outer_stride) {
     using P = Plan<LEN>;
     using Cfg = ConvColCfg<T, LEN>;
@@ -347,10 +356,16 @@ __global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS) k_conv_cols_zz(Co
 }
 
 // fixed-order sum of the per-CTA partials: cost = alpha/2 * sum
-__global__ void k_conv_cost_final(const double* __restrict__ part, int n, double alpha, double* __restrict__ out) {
-    __shared__ double red[8];
-    double x = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) x += part[i];
+// (1024 threads, four independent partial sums each: one CTA of 256 threads with a single dependent chain took 32 us)
+__global__ void __launch_bounds__(1024) k_conv_cost_final(const double* __restrict__ part, int n, double alpha,
+                                                          double* __restrict__ out) {
+    __shared__ double red[32];
+    const int bd = blockDim.x;
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+    int i = threadIdx.x;
+    for (; i + 3 * bd < n; i += 4 * bd) { x0 += part[i]; x1 += part[i + bd]; x2 += part[i + 2 * bd]; x3 += part[i + 3 * bd]; }
+    for (; i < n; i += bd) x0 += part[i];
+    double x = (x0 + x1) + (x2 + x3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;

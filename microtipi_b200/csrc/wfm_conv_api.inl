@@ -263,7 +263,7 @@ int wfm_conv_cost_and_gradient_dev(wfm_conv* c, double alpha, const void* h_dev,
     if ((rc = conv_c2r_n<CS_RESID>(c, a, &nparts))) return rc;
     {
         auto kfin = &k_conv_cost_final;
-        WFM_LAUNCH(kfin, dim3(1), dim3(256), 0, c->stream, (const double*)c->cost_part.p, nparts, alpha,
+        WFM_LAUNCH(kfin, dim3(1), dim3(1024), 0, c->stream, (const double*)c->cost_part.p, nparts, alpha,
                    cost_dev ? cost_dev : (double*)c->cost_dev.p);
         WFM_CK_LAUNCH(c, "k_conv_cost_final");
     }
