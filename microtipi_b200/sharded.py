@@ -103,3 +103,55 @@ class ShardedWideFieldModel:
         parts = [None] * self.world
         self._dist.all_gather_object(parts, local, group=self.group)
         return np.concatenate(parts, axis=0)
+
+
+class ShardedWideFieldModelBatch:
+    """BASELINE config 5 across the GPUs of one box: ``nbatch`` INDEPENDENT models are split by model index
+    (``slab_bounds(nbatch, world, rank)``), every rank holds its share on one batch handle
+    (``WideFieldModelBatch``).  The models share nothing, so the data path has NO collective (SURVEY.md 8e2 (3));
+    the only exchange offered is the optional all-gather of the small per-model gradient rows."""
+
+    def __init__(self, psfShape, nbatch, nPhase, nModulus, NA, lambda_, ni, dxy, dz, radial=False, single=False, *,
+                 group=None, device=0, lib=None, basis=None):
+        import torch.distributed as dist
+        from .wide_field_model import WideFieldModelBatch
+        self._dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.nbatch = int(nbatch)
+        self.b0, self.nb_local = slab_bounds(self.nbatch, self.world, self.rank)
+        if self.nb_local <= 0:
+            raise ValueError("more ranks than models")
+        # (a batch handle needs nbatch >= 2 to differ from a plain one; one model is simply a batch of one)
+        self.model = WideFieldModelBatch(psfShape, self.nb_local, nPhase, nModulus, NA, lambda_, ni, dxy, dz, radial,
+                                         single, device=device, lib=lib, basis=basis)
+
+    def __getattr__(self, name):
+        return getattr(self.model, name)
+
+    def local_rows(self, table):
+        """Rows [b0, b0 + nb_local) of a global per-model table."""
+        t = np.asarray(table)
+        if t.shape[0] != self.nbatch:
+            raise ValueError("table must have one row per model of the GLOBAL batch")
+        return t[self.b0:self.b0 + self.nb_local]
+
+    def setPhaseBatch(self, alpha_global):
+        self.model.setPhaseBatch(self.local_rows(alpha_global))
+
+    def setModulusBatch(self, beta_global):
+        self.model.setModulusBatch(self.local_rows(beta_global))
+
+    def setDefocusBatch(self, defoc_global):
+        self.model.setDefocusBatch(self.local_rows(defoc_global))
+
+    def applyJacobianBatch(self, q_local, kinds=capi.WFM_J_DEFOCUS | capi.WFM_J_PHASE | capi.WFM_J_MODULUS, gather=False):
+        """q_local: this rank's models only, (nb_local, Nz, Ny, Nx).  gather=True returns the rows of ALL models."""
+        d, p, m = self.model.applyJacobianBatch(q_local, kinds)
+        if not gather or self.world == 1:
+            return d, p, m
+        parts = [None] * self.world
+        self._dist.all_gather_object(parts, np.concatenate([d, p, m], axis=1), group=self.group)
+        full = np.concatenate(parts, axis=0)
+        return full[:, :3], full[:, 3:3 + p.shape[1]], full[:, 3 + p.shape[1]:]
