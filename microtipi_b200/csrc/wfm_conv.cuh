@@ -150,20 +150,20 @@ __global__ void __launch_bounds__(RowCfg<N / 2>::THREADS) k_conv_rows_r2c(ConvAr
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + RB * L::LEN;
     cx<T>* twn_s = tw_s + M + 16;
-    for (int i = threadIdx.x; i < M; i += RowCfg<M>::THREADS) { tw_s[i] = a.tw[i]; twn_s[i] = a.twn[i]; }
-    if (threadIdx.x < P::R3) tw_s[M + threadIdx.x] = a.tw[P::R1 * threadIdx.x];
-    __syncthreads();
     const int slot = threadIdx.x / TT, t = threadIdx.x % TT;
     const size_t nrows = (size_t)a.ny * a.nz;
     const size_t row = (size_t)blockIdx.x * RB + slot;
     const bool valid = row < nrows;
     const cx<T>* src = reinterpret_cast<const cx<T>*>(a.real_in + (valid ? row : 0) * N);
-    cx<T> v[E];
+    cx<T> v[E];                                        // the row's loads go out first: the twiddle copy overlaps them
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r)
             v[u * P::R1 + r] = valid ? src[(t + TT * u) + P::S1 * r] : mkc<T>((T)0, (T)0);
+    for (int i = threadIdx.x; i < M; i += RowCfg<M>::THREADS) { tw_s[i] = a.tw[i]; twn_s[i] = a.twn[i]; }
+    if (threadIdx.x < P::R3) tw_s[M + threadIdx.x] = a.tw[P::R1 * threadIdx.x];
+    __syncthreads();
     cx<T>* sm = cells + slot * L::LEN;
     fft_inplace<T, P, L, RowSync<TT>>(v, sm, t, tw_s, tw_s + M, slot);
     RowSync<TT>::sync(slot);                           // the last stage has read the cells: reuse them for the mirror
@@ -271,6 +271,9 @@ template <typename T, int LEN> struct ConvColCfg {
     static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + LEN + 16);
     // k_conv_cols_zz took 88-92 registers = 2 CTAs per SM (ncu, profiles/r01n_conv_ncu_full.md: warps active 24 %,
     // DRAM 42 %); three resident CTAs where the tile allows it
+#ifndef WFM_CONV_ZZ_PREFETCH
+#define WFM_CONV_ZZ_PREFETCH 1
+#endif
 #ifndef WFM_CONV_ZZ_MINB
 #define WFM_CONV_ZZ_MINB 3
 #endif
@@ -286,16 +289,16 @@ __global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS) k_conv_cols(ConvA
     constexpr int CW = Cfg::CW, TT = P::T, E = P::E;
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
-    for (int i = threadIdx.x; i < LEN; i += Cfg::THREADS) tw_s[i] = a.tw[i];
-    if (threadIdx.x < P::R3) tw_s[LEN + threadIdx.x] = a.tw[P::R1 * threadIdx.x];
-    __syncthreads();
     const int c = threadIdx.x % CW, t = threadIdx.x / CW;
     const size_t base = (size_t)(blockIdx.x / tiles_per_outer) * outer_stride + (size_t)(blockIdx.x % tiles_per_outer) * CW + c;
-    cx<T> v[E];
+    cx<T> v[E];                                        // the tile's loads go out first: the twiddle copy overlaps them
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r) v[u * P::R1 + r] = a.V[base + (size_t)((t + TT * u) + P::S1 * r) * stride];
+    for (int i = threadIdx.x; i < LEN; i += Cfg::THREADS) tw_s[i] = a.tw[i];
+    if (threadIdx.x < P::R3) tw_s[LEN + threadIdx.x] = a.tw[P::R1 * threadIdx.x];
+    __syncthreads();
     fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + LEN, 0);
     double cost_acc = 0.0;
 #pragma unroll
@@ -319,17 +322,22 @@ __global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS, ConvColCfg<T, LEN
     constexpr int CW = Cfg::CW, TT = P::T, E = P::E;
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
-    for (int i = threadIdx.x; i < LEN; i += Cfg::THREADS) tw_s[i] = a.tw[i];
-    if (threadIdx.x < P::R3) tw_s[LEN + threadIdx.x] = a.tw[P::R1 * threadIdx.x];
-    __syncthreads();
     const int c = threadIdx.x % CW, t = threadIdx.x / CW;
     const size_t base = (size_t)(blockIdx.x / tiles_per_outer) * outer_stride + (size_t)(blockIdx.x % tiles_per_outer) * CW + c;
     cx<T>* sm = cells + c;
-    cx<T> v[E];
+    cx<T> v[E];                                        // the tile's loads go out first: the twiddle copy overlaps them
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
         for (int r = 0; r < P::R1; ++r) v[u * P::R1 + r] = a.V[base + (size_t)((t + TT * u) + P::S1 * r) * stride];
+#if WFM_CONV_ZZ_PREFETCH
+    // the tile of X = FFT3(obj) the spectral product will read after the first transform: DRAM -> L2 now
+    for (int k = threadIdx.x; k < LEN; k += Cfg::THREADS)
+        wfm_prefetch_l2(&a.X[base - c + (size_t)k * stride], (unsigned)(CW * sizeof(cx<T>)));
+#endif
+    for (int i = threadIdx.x; i < LEN; i += Cfg::THREADS) tw_s[i] = a.tw[i];
+    if (threadIdx.x < P::R3) tw_s[LEN + threadIdx.x] = a.tw[P::R1 * threadIdx.x];
+    __syncthreads();
     fft_inplace<T, P, L, CtaSync>(v, sm, t, tw_s, tw_s + LEN, 0);
     __syncthreads();                                   // the last stage has read the cells
 #pragma unroll
