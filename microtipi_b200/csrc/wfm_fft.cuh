@@ -176,6 +176,15 @@ template <typename T, int N> struct RowLayout {
     __host__ __device__ static constexpr int pad_c(int i) { return i + (P::PA ? (i >> P::PA) : 0) + (P::PB ? (i >> P::PB) : 0); }
     static constexpr int LEN = pad_c(N - 1) + 1;      // cells per transform
     static WFM_DEVI int at(int i) { return pad_c(i); }
+    __host__ __device__ static constexpr int at_c(int i) { return pad_c(i); }
+    // Index arithmetic the engine may rely on for blocks of B consecutive indices starting at multiples of B
+    // (B = N/R1): at(k*B + b) == at(b) + k*at_c(B) for b < B, and at(base + j) == at(base) + j while base + j stays
+    // inside its block.  Both hold when every padding term steps exactly once per block, i.e. 2^shift == B
+    // (constant inside a block, and (k*B + b) >> shift == k + (b >> shift)).
+    template <int B> __host__ __device__ static constexpr bool affine() {
+        return (P::PA == 0 || (1 << P::PA) == B) && (P::PB == 0 || (1 << P::PB) == B);
+    }
+    static constexpr int UNIT = 1;                    // distance between consecutive indices of a block
 };
 
 // Column layout: cell = (i + (i >> SH)) * C + column.  With SH = log2(N/R1) the stage-3 reads of a
@@ -184,6 +193,9 @@ template <typename T, int N> struct RowLayout {
 template <int C, int SH> struct ColLayout {
     __host__ __device__ static constexpr int pad_c(int i) { return i + (i >> SH); }
     static WFM_DEVI int at(int i) { return pad_c(i) * C; }
+    __host__ __device__ static constexpr int at_c(int i) { return pad_c(i) * C; }
+    template <int B> __host__ __device__ static constexpr bool affine() { return (1 << SH) == B; }
+    static constexpr int UNIT = C;
 };
 __host__ __device__ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
 
@@ -250,6 +262,15 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
                           const int sync_id, const Hook& hook = Hook()) {
     static_assert(!SPARSE1 || P::R1 == 8 || P::R1 == 16, "sparse first stage: radix 8 or 16");
     constexpr int E = P::E, R1 = P::R1, R2 = P::R2, R3 = P::R3, TT = P::T, S1 = P::S1;
+    // AFF: the layout is affine over the S1-blocks (see RowLayout::affine): every stage then needs ONE address per
+    // butterfly, its legs are compile-time offsets.  (Without it the compiler kept one address register per leg for
+    // most exchanges: cuobjdump on the 512-point pipelines.)
+#ifdef WFM_NO_AFFINE
+    constexpr bool AFF = false;
+#else
+    constexpr bool AFF = L::template affine<S1>();
+#endif
+    constexpr int LS1 = L::at_c(S1), UNIT = L::UNIT;
     // stage 1: radix R1 over legs of stride S1, twiddle W_N^(b*k1), scatter to cell k1*S1 + b
 #pragma unroll
     for (int u = 0; u < E / R1; ++u) {
@@ -260,20 +281,22 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
         else if constexpr (SPARSE1 && R1 == 16) dft16_in_narrow<T>(reinterpret_cast<cx<T>(&)[16]>(a));
         else Dft<T, R1>::run(a);
         const int b = t + TT * u;
-        sm[L::at(b)] = a[0];
+        cx<T>* const s1 = sm + L::at(b);               // AFF: leg k of this butterfly lives at s1[k * LS1]
+        auto cell1 = [&](int k) -> cx<T>& { return AFF ? s1[k * LS1] : sm[L::at(k * S1 + b)]; };
+        cell1(0) = a[0];
         if constexpr (TWTREE == 1) {
             cx<T> pw[R1];
             twiddle_powers<T, R1>(pw, tw[b]);
 #pragma unroll
-            for (int k = 1; k < R1; ++k) sm[L::at(k * S1 + b)] = cmul(a[k], pw[k]);
+            for (int k = 1; k < R1; ++k) cell1(k) = cmul(a[k], pw[k]);
         } else if constexpr (TWTREE == 2) {
             const cx<T> w = tw[b];
             const cx<T> w2 = cmul(w, w);
             cx<T> wo = w, we = w2;
 #pragma unroll
             for (int k = 1; k < R1; k += 2) {
-                sm[L::at(k * S1 + b)] = cmul(a[k], wo);
-                if (k + 1 < R1) sm[L::at((k + 1) * S1 + b)] = cmul(a[k + 1], we);
+                cell1(k) = cmul(a[k], wo);
+                if (k + 1 < R1) cell1(k + 1) = cmul(a[k + 1], we);
                 if (k + 2 < R1) wo = cmul(wo, w2);
                 if (k + 3 < R1) we = cmul(we, w2);
             }
@@ -282,7 +305,7 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
             cx<T> wk = w;
 #pragma unroll
             for (int k = 1; k < R1; ++k) {
-                sm[L::at(k * S1 + b)] = cmul(a[k], wk);
+                cell1(k) = cmul(a[k], wk);
                 if (k + 1 < R1) wk = cmul(wk, w);
             }
         }
@@ -296,9 +319,11 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
             const int b = t + TT * u;
             const int k1 = b / R3, d3 = b % R3;
             const int base = k1 * S1 + d3;
+            cx<T>* const s2 = sm + L::at(base);            // AFF: legs r*R3 further on inside block k1
+            auto cell2 = [&](int r) -> cx<T>& { return AFF ? s2[r * R3 * UNIT] : sm[L::at(base + r * R3)]; };
             cx<T> a[R2];
 #pragma unroll
-            for (int r = 0; r < R2; ++r) a[r] = sm[L::at(base + r * R3)];
+            for (int r = 0; r < R2; ++r) a[r] = cell2(r);
             Dft<T, R2>::run(a);
 #ifdef WFM_FAKE_NO_X2   /* timing experiment only (wrong results): what would the step cost without the second exchange? */
             const cx<T> w = tw2[d3];
@@ -311,21 +336,21 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
             }
         }
 #else
-            sm[L::at(base)] = a[0];
+            cell2(0) = a[0];
             // compact table tw2[d] = W_N^(R1*d): adjacent lanes, adjacent cells
             if constexpr (TWTREE == 1) {
                 cx<T> pw[R2];
                 twiddle_powers<T, R2>(pw, tw2[d3]);
 #pragma unroll
-                for (int k = 1; k < R2; ++k) sm[L::at(base + k * R3)] = cmul(a[k], pw[k]);
+                for (int k = 1; k < R2; ++k) cell2(k) = cmul(a[k], pw[k]);
             } else if constexpr (TWTREE == 2) {
                 const cx<T> w = tw2[d3];
                 const cx<T> w2 = cmul(w, w);
                 cx<T> wo = w, we = w2;
 #pragma unroll
                 for (int k = 1; k < R2; k += 2) {
-                    sm[L::at(base + k * R3)] = cmul(a[k], wo);
-                    if (k + 1 < R2) sm[L::at(base + (k + 1) * R3)] = cmul(a[k + 1], we);
+                    cell2(k) = cmul(a[k], wo);
+                    if (k + 1 < R2) cell2(k + 1) = cmul(a[k + 1], we);
                     if (k + 2 < R2) wo = cmul(wo, w2);
                     if (k + 3 < R2) we = cmul(we, w2);
                 }
@@ -334,7 +359,7 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
                 cx<T> wk = w;
 #pragma unroll
                 for (int k = 1; k < R2; ++k) {
-                    sm[L::at(base + k * R3)] = cmul(a[k], wk);
+                    cell2(k) = cmul(a[k], wk);
                     if (k + 1 < R2) wk = cmul(wk, w);
                 }
             }
@@ -353,8 +378,9 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
             for (int r = 0; r < R3; ++r) a[r] = v[u * R3 + r];
             (void)base;
 #else
+            const cx<T>* const s3 = sm + L::at(base);      // AFF: R3 adjacent cells of block k1
 #pragma unroll
-            for (int r = 0; r < R3; ++r) a[r] = sm[L::at(base + r)];
+            for (int r = 0; r < R3; ++r) a[r] = AFF ? s3[r * UNIT] : sm[L::at(base + r)];
 #endif
             Dft<T, R3>::run(a);
 #pragma unroll
@@ -366,9 +392,10 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
         for (int u = 0; u < E / R2; ++u) {
             const int b = t + TT * u;
             const int base = b * S1;
+            const cx<T>* const s2 = sm + L::at(base);
             cx<T> a[R2];
 #pragma unroll
-            for (int r = 0; r < R2; ++r) a[r] = sm[L::at(base + r)];
+            for (int r = 0; r < R2; ++r) a[r] = AFF ? s2[r * UNIT] : sm[L::at(base + r)];
             Dft<T, R2>::run(a);
 #pragma unroll
             for (int r = 0; r < R2; ++r) v[u * R2 + r] = a[r];
