@@ -312,6 +312,7 @@ int prepare_ctl(wfm_model* h, const PipePlan& pp, PipeCtl& ctl, int roles) {
     unsigned* base = (unsigned*)h->ctl.p;
     ctl.queue = base; ctl.err = base + 1; ctl.done = base + 2; ctl.cntA = base + 4; ctl.cntB = base + 4 + h->nzl;
     ctl.ring = pp.ring; ctl.lag = pp.lag; ctl.nA = pp.nA; ctl.nB = pp.nB; ctl.roles = roles; ctl.nzm = h->nzm;
+    ctl.ring_stride = h->N * h->pitch;
     return WFM_OK;
 }
 

@@ -348,6 +348,7 @@ struct PipeCtl {
     int nA, nB;        // items per plane
     int roles;         // bit 0: run A items, bit 1: run B items (both set in production)
     int nzm;           // planes per model (batch handles), else the slab's plane count
+    int ring_stride;   // elements per ring slot (N * pitch)
 };
 
 // fp64 column tile of the pipelines for N >= 256: 4 columns (64-byte segments of conj(a)) give
@@ -418,12 +419,13 @@ template <typename T, int N> struct PipeCfg {
 #endif
 };
 
-// type 0 = A, 1 = B, -1 = done; model = plane / nzm (batch handles: which model's pupil; 0 otherwise)
-struct PipeItem { int type; int plane; int sub; int model; };
+// type 0 = A, 1 = B, -1 = done; model = plane / nzm (batch handles: which model's pupil; 0 otherwise);
+// ringoff = (plane % ring) * ring_stride, the plane's slot in the intermediate ring, in elements
+struct PipeItem { int type; int plane; int sub; int model; int ringoff; };
 
 WFM_DEVI PipeItem pipe_decode(unsigned idx, int P, const PipeCtl& c) {
     PipeItem it;
-    it.model = 0;
+    it.model = 0; it.ringoff = 0;
     const int lag = c.lag < P ? c.lag : P;
     const unsigned headA = (unsigned)lag * c.nA;
     const unsigned per = (unsigned)(c.nA + c.nB);
@@ -484,13 +486,15 @@ WFM_DEVI void pipe_finish(const PipeCtl& c, int P) {
 // the ring size -- is ~1.3 items per CTA instead of 2.  At claim time thread 0 also probes the
 // item's dependency counter once (acquire): in steady state it is already met.
 struct PipeQueue {
-    // shared: per slot {type, plane, sub, model, dependency already satisfied}.  Thread 0 decodes the queue index
-    // when it claims it (late in the previous item), so the other threads start an item with five shared-memory
-    // reads instead of the integer divisions of pipe_decode (measured: 0.8445 -> 0.8335 ms/step for one division).
+    // shared: per slot {type, plane, sub, model, dependency already satisfied, ring offset}.  Thread 0 decodes the
+    // queue index when it claims it (late in the previous item), so the other threads start an item with six
+    // shared-memory reads instead of the integer divisions of pipe_decode (measured: 0.8445 -> 0.8335 ms/step for one
+    // division), and no thread computes plane % ring: that modulo and the 64-bit slot offset sat in every ROW of the
+    // row items (the compiler rematerialised them per row at 64 registers: ~60 of ~430 instructions, cuobjdump).
     int* s;
     int cur;
     bool pre;      // (thread 0) next item already claimed during this item
-    static constexpr int SLOT = 5;
+    static constexpr int SLOT = 6;
     WFM_DEVI static bool probe(const PipeItem& it, const PipeCtl& c) {
         const unsigned* cnt; unsigned target;
         if (it.type == 0) {
@@ -510,9 +514,10 @@ struct PipeQueue {
         int* d = s + slot * SLOT;
         d[0] = it.type; d[1] = it.plane; d[2] = it.sub; d[3] = it.type < 0 ? 0 : it.plane / c.nzm;
         d[4] = (it.type < 0 || probe(it, c)) ? 1 : 0;
+        d[5] = it.type < 0 ? 0 : (it.plane % c.ring) * c.ring_stride;
     }
-    WFM_DEVI void init(int* smem10, const PipeCtl& c, int P) {
-        s = smem10; cur = 0; pre = false;
+    WFM_DEVI void init(int* smem12, const PipeCtl& c, int P) {
+        s = smem12; cur = 0; pre = false;
         if (threadIdx.x == 0) claim(0, c, P);
         __syncthreads();
     }
@@ -521,7 +526,7 @@ struct PipeQueue {
         pre = false;
         const int* d = s + cur * SLOT;
         PipeItem it;
-        it.type = d[0]; it.plane = d[1]; it.sub = d[2]; it.model = d[3];
+        it.type = d[0]; it.plane = d[1]; it.sub = d[2]; it.model = d[3]; it.ringoff = d[5];
         ready = d[4] != 0;
         return it;
     }
@@ -589,7 +594,7 @@ template <typename T> struct PsfArgs {
 template <int R, bool NARROW> WFM_DEVI constexpr bool leg_live(int r) { return !NARROW || r < R / 4 || r >= R - R / 4; }
 
 template <typename T, int N, bool NARROW>
-WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int bm, int ring, cx<T>* cells, const cx<T>* tw_s,
+WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int bm, int ringoff, cx<T>* cells, const cx<T>* tw_s,
                             const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
@@ -627,7 +632,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int bm, int ri
     fft_inplace<T, P, L, CtaSync, PipePrefetchHook, NARROW, WFM_PSF_TW_TREE>(v, cells + c, t, tw_s, tw_s + N, 0,
                                                                              PipePrefetchHook{qu, ctl, a.g.nzl});
     pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
-    cx<T>* dst = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)sub * N * C + c;
+    cx<T>* dst = a.T1 + (size_t)ringoff + (size_t)sub * N * C + c;
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
@@ -638,7 +643,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int bm, int ri
 // (inactive columns are zero), then the fused streaming store of conj(a) and |a|^2*PSFnorm
 // (WFM:323-328) as full contiguous rows.  No CTA-wide barrier inside.
 template <typename T, int N, bool NARROW>
-WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ringoff, cx<T>* cells, const cx<T>* tw_s,
                             const int* invx_s, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
@@ -659,7 +664,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
 #if WFM_ROW_PREFETCH
     cx<T> nv[E];
     {
-        const cx<T>* src0 = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)(sub * Cfg::ROWS_PER_ITEM + slot) * C;
+        const cx<T>* src0 = a.T1 + (size_t)ringoff + (size_t)(sub * Cfg::ROWS_PER_ITEM + slot) * C;
 #pragma unroll
         for (int e = 0; e < E; ++e)
             if (leg_live<P::R1, NARROW>(e % P::R1)) nv[e] = (xis[e] >= 0) ? __ldcg(&src0[xis[e]]) : mkc<T>((T)0, (T)0);
@@ -669,7 +674,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ring, cx<T
     for (int kk = 0; kk < Cfg::KR; ++kk) {
         if (kk == Cfg::KR - 1) qu.prefetch(ctl, a.g.nzl);             // claim the next item behind the last row
         const int ky = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;     // N % ROWS_PER_ITEM == 0
-        const cx<T>* src = a.T1 + (size_t)(pl % ring) * N * a.pitch + (size_t)ky * C;
+        const cx<T>* src = a.T1 + (size_t)ringoff + (size_t)ky * C;
         cx<T> v[E];
 #if WFM_ROW_PREFETCH
 #pragma unroll
@@ -720,20 +725,23 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     qu.init(s_queue, ctl, P);
     for (;;) {
         bool ready;
-        const PipeItem it = qu.take(ctl, P, ready);
+        PipeItem it = qu.take(ctl, P, ready);
         if (it.type < 0) break;
+#ifdef WFM_RING_MOD_IN_ITEM   /* A/B knob: the slot offset computed by every thread, as before */
+        it.ringoff = (it.plane % ctl.ring) * ctl.ring_stride;
+#endif
         if (it.type == 0) {
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                psf_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, ctl.ring, cells, tw_s, dep, qu, ctl);
+                psf_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, it.ringoff, cells, tw_s, dep, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                psf_rows_item<T, N, NARROW>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, qu, ctl);
+                psf_rows_item<T, N, NARROW>(a, it.plane, it.sub, it.ringoff, cells, tw_s, invx_s, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntB[it.plane]);
@@ -764,7 +772,7 @@ template <typename T> struct JacArgs {
 // A-item: ROWS_PER_ITEM rows of plane pl (each TT-thread group walks KR of them).  Aq = conj(a)*q
 // fused into the streaming load (WFM:907-914), FFT along x, keep the active kx only.
 template <typename T, int N, bool NARROW>
-WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T>* cells, const cx<T>* tw_s,
+WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, cx<T>* cells, const cx<T>* tw_s,
                             const int* invx_s, const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
@@ -835,7 +843,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
             }
 #endif
         fft_inplace<T, P, L, RowSync<TT>, NoHook, false, WFM_JAC_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
-        cx<T>* dst = a.T2 + (size_t)(pl % ring) * N * a.pitch + (size_t)y * C;
+        cx<T>* dst = a.T2 + (size_t)ringoff + (size_t)y * C;
 #pragma unroll
         for (int e = 0; e < E; ++e)
             if (leg_live<P::RL, NARROW>(e % P::RL) && xis[e] >= 0) __stcg(&dst[xis[e]], v[e]);
@@ -848,7 +856,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ring, cx<T
 //   jin = rho*(B_re sin ph + B_im cos ph)   on maskPupil   (WFM:925-928, 1253)
 //   J   = B_re cos ph - B_im sin ph         on the support (WFM:607-611)
 template <typename T, int N, bool NARROW>
-WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int bm, int ring, cx<T>* cells, const cx<T>* tw_s,
+WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int bm, int ringoff, cx<T>* cells, const cx<T>* tw_s,
                             PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
@@ -859,7 +867,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int bm, int ri
     const size_t tbase = (size_t)sub * N * C + c;      // this thread's column inside the tile-major strip
     // bm: model of a batch handle (0 otherwise)
     const size_t sbase = tbase + (size_t)bm * N * a.pitch;   // the same column in that model's pupil strip
-    const cx<T>* src = a.T2 + (size_t)(pl % ring) * N * a.pitch + tbase;
+    const cx<T>* src = a.T2 + (size_t)ringoff + tbase;
     cx<T> v[E];
 #pragma unroll
     for (int u = 0; u < E / P::R1; ++u)
@@ -920,20 +928,23 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
     qu.init(s_queue, ctl, P);
     for (;;) {
         bool ready;
-        const PipeItem it = qu.take(ctl, P, ready);
+        PipeItem it = qu.take(ctl, P, ready);
         if (it.type < 0) break;
+#ifdef WFM_RING_MOD_IN_ITEM   /* A/B knob: the slot offset computed by every thread, as before */
+        it.ringoff = (it.plane % ctl.ring) * ctl.ring_stride;
+#endif
         if (it.type == 0) {
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                jac_rows_item<T, N, NARROW>(a, it.plane, it.sub, ctl.ring, cells, tw_s, invx_s, dep, qu, ctl);
+                jac_rows_item<T, N, NARROW>(a, it.plane, it.sub, it.ringoff, cells, tw_s, invx_s, dep, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                jac_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, ctl.ring, cells, tw_s, qu, ctl);
+                jac_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, it.ringoff, cells, tw_s, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntB[it.plane]);
