@@ -343,7 +343,7 @@ def run_b200(args):
         assert np.isfinite(cost) and np.all(np.isfinite(gfg))
         eval_fg = {"ms_per_eval": fg_ms, "value": nzg / (fg_ms * 1e-3), "unit": UNIT, "steps": nf,
                    "h2d_bytes_per_step": 80, "d2h_bytes_per_step": 88,
-                   "note": "wfm_eval_fg: PSF + 3-D FFT convolution cost/gradient (12 volume sweeps) + Jacobian, host wall clock"}
+                   "note": "wfm_eval_fg: PSF + 3-D FFT convolution cost/gradient (10 volume sweeps) + Jacobian, host wall clock"}
         f.close()
 
     if rank == 0:
