@@ -271,3 +271,31 @@ def test_batch_handle_matches_independent_oracle_models(lib, N, Nz, B, single):
     with pytest.raises(RuntimeError):
         m.apply_J_phase(q)
     m.close()
+
+
+def test_batch_handle_modes_and_subsets(lib):
+    """Batch handle corner cases: Jacobian subsets (unselected kinds come back as zeros), the quirk-Q1 last-plane
+    modulus mode per model, a chunk boundary inside a model (Nz = 19 > 16 planes per reduce chunk), nPhase = 0."""
+    N, Nz, B = 32, 19, 2
+    m, refs = _batch_case(lib, N, Nz, B, False)
+    q = np.stack([o.synthetic_q(N, N, Nz, seed=7 + b) for b in range(B)])
+    d, p, mo = m.applyJacobianBatch(q, kinds=capi.WFM_J_PHASE)
+    assert np.all(d == 0) and np.all(mo == 0)
+    for b, r in enumerate(refs):
+        assert o.rel_l2(p[b], r.apply_J_phase(q[b])) <= 1e-12
+    d, p, mo = m.applyJacobianBatch(q, kinds=capi.WFM_J_DEFOCUS | capi.WFM_J_MODULUS)
+    assert np.all(p == 0)
+    m.setModulusMode(True)
+    d2, p2, mo2 = m.applyJacobianBatch(q, kinds=capi.WFM_J_MODULUS)
+    for b, r in enumerate(refs):
+        assert o.rel_l2(d[b], r.apply_J_defocus(q[b])) <= 1e-12
+        assert o.rel_l2(mo[b], r.apply_J_modulus(q[b])) <= 1e-12
+        r.modulus_mode = o.MODULUS_REFERENCE_LAST_PLANE
+        assert o.rel_l2(mo2[b], r.apply_J_modulus(q[b])) <= 1e-12
+    # errors: a table with the wrong number of rows, a defocus vector of length 2 (quirk Q4)
+    with pytest.raises(ValueError):
+        m.setPhaseBatch(np.zeros((B + 1, 10)))
+    with pytest.raises(ValueError):
+        m.setDefocusBatch(np.zeros((B, 2)))
+    assert lib.wfm_batch_size(m.handle) == B
+    m.close()
