@@ -579,7 +579,11 @@ static int create_impl(wfm_model** out, int nx, int ny, int nz_global, int z0, i
     if (nx <= 0 || nz_global <= 0 || nz_local <= 0 || z0 < 0 || z0 + nz_local > nz_global) {
         g_create_error = "bad shape / slab"; return WFM_ERR_INVALID_ARG;
     }
-    if (nbatch < 1 || (long long)nbatch * nz_local > (1ll << 24)) { g_create_error = "bad batch size"; return WFM_ERR_INVALID_ARG; }
+    // (the model index is a grid.y dimension of the setters and, times the plane chunks per model, of the reduction)
+    if (nbatch < 1 || (long long)nbatch * nz_local > (1ll << 24) ||
+        (long long)nbatch * ((nz_local + WFM_RED_PLANES - 1) / WFM_RED_PLANES) > 65535) {
+        g_create_error = "bad batch size"; return WFM_ERR_INVALID_ARG;
+    }
     if (precision != WFM_F64 && precision != WFM_F32) { g_create_error = "bad precision"; return WFM_ERR_INVALID_ARG; }
     if (!supported_n(nx)) {
         g_create_error = "Nx must be a power of two in [32, 2048]"; return WFM_ERR_UNSUPPORTED;

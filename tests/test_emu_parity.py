@@ -299,3 +299,5 @@ def test_batch_handle_modes_and_subsets(lib):
         m.setDefocusBatch(np.zeros((B, 2)))
     assert lib.wfm_batch_size(m.handle) == B
     m.close()
+    hb = C.c_void_p()                                               # more models than the reduction grid can index
+    assert lib.wfm_create_batch(C.byref(hb), 32, 32, 4, 70000, 1e-7, 1e-7, capi.WFM_F64, 0) == capi.WFM_ERR_INVALID_ARG
