@@ -171,6 +171,7 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
     }
 
     /** WFM:412-422. */
+    @Override
     public void setParam(DoubleShapedVector param) {
         if (param.getOwner() == parameterSpace[DEFOCUS]) setDefocus(param);
         else if (param.getOwner() == parameterSpace[PHASE]) setPhase(param);
@@ -178,6 +179,7 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
         else throw new IllegalArgumentException("DoubleShapedVector param does not belong to any space");
     }
     /** WFM:1553-1556. */
+    @Override
     public void setParam(double[] param) { setDefocus(param); }
 
     // ---- pupil setters ------------------------------------------------------------------------------------------------
