@@ -136,12 +136,12 @@ def test_fill_uniform_matches_oracle_generator(lib):
     m.close()
 
 
-def test_convolution_data_term_matches_oracle(lib):
+@pytest.mark.parametrize("N,Nz", [(32, 32), (64, 32), (32, 64), (128, 32), (64, 128)])
+def test_convolution_data_term_matches_oracle(lib, N, Nz):
     # row f1 (TiPi WeightedConvolutionCost as PSF_Estimation.java:147-157 drives it): 3-D FFT convolution cost
     # and gradient through the same kernel sources, with weights, alpha and the clr flag
     from microtipi_b200 import WeightedConvolutionCost, DoubleShapedVectorSpace
     rng = np.random.default_rng(11)
-    N, Nz = 32, 32
     shp = (Nz, N, N)
     obj, h, y = rng.normal(size=shp), rng.normal(size=shp), rng.normal(size=shp)
     w = rng.uniform(0.0, 2.0, size=shp)
