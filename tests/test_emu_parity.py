@@ -19,7 +19,8 @@ def lib():
     return emu_lib()
 
 
-@pytest.mark.parametrize("N,Nz,single", [(32, 6, False), (64, 4, False), (128, 3, False), (64, 4, True)])
+@pytest.mark.parametrize("N,Nz,single", [(32, 6, False), (64, 4, False), (128, 3, False), (64, 4, True),
+                                         (256, 2, False), (512, 2, False), (512, 2, True), (1024, 1, False)])   # production-size plans (narrow, affine)
 def test_psf_and_jacobians_match_oracle(lib, N, Nz, single):
     ref, m = make_pair(N, Nz, lib, single=single)
     t = tol(single)
@@ -246,7 +247,7 @@ def _batch_case(lib, N, Nz, B, single, nModulus=4):
     return m, refs
 
 
-@pytest.mark.parametrize("N,Nz,B,single", [(32, 5, 3, False), (64, 17, 2, False), (32, 4, 3, True)])
+@pytest.mark.parametrize("N,Nz,B,single", [(32, 5, 3, False), (64, 17, 2, False), (32, 4, 3, True), (256, 3, 2, False)])
 def test_batch_handle_matches_independent_oracle_models(lib, N, Nz, B, single):
     m, refs = _batch_case(lib, N, Nz, B, single)
     t = tol(single)
