@@ -986,7 +986,9 @@ struct ReduceArgs {
 
 #define WFM_RED_THREADS 256
 #define WFM_RED_CHUNK 8
-#define WFM_RED_PLANES 16   // planes summed by one CTA (grid.y = ceil(nzl / WFM_RED_PLANES))
+#ifndef WFM_RED_PLANES
+#define WFM_RED_PLANES 16   // planes summed by one CTA ("chunk"); 4 and 8 measured slower (more basis re-reads)
+#endif
 
 // One thread per support cell and per chunk of WFM_RED_PLANES planes.  Sums the planes of the chunk
 // in fixed order (gP = sum jin, gD = sum defoc*jin, gM = sum J), then forms the glen dot products
