@@ -227,6 +227,22 @@ def test_wide_pupil_uses_generic_kernels(lib):
     m.close()
 
 
+@pytest.mark.parametrize("N,single", [(512, False), (512, True), (256, False)])
+def test_generic_kernels_at_production_size(lib, monkeypatch, N, single):
+    # WFM_NO_NARROW=1 forces the un-pruned pipelines (the ones a wide pupil selects) at the sizes whose row layout is
+    # affine (512) and is not (256): same results as the narrow kernels and as the oracle
+    monkeypatch.setenv("WFM_NO_NARROW", "1")
+    Nz = 2
+    ref, m = make_pair(N, Nz, lib, single=single)
+    t = tol(single)
+    q = o.synthetic_q(N, N, Nz, single=single)
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= t
+    d, p, mo = m.apply_J_all(q)
+    assert o.rel_l2(np.concatenate([d, p, mo]), np.concatenate([ref.apply_J_defocus(q), ref.apply_J_phase(q),
+                                                                ref.apply_J_modulus(q)])) <= (20 * t if single else t)
+    m.close()
+
+
 def _batch_case(lib, N, Nz, B, single, nModulus=4):
     """B models with different phase / modulus / defocus vectors on one batch handle vs B oracle models."""
     from microtipi_b200 import WideFieldModelBatch
