@@ -137,7 +137,7 @@ def test_fill_uniform_matches_oracle_generator(lib):
     m.close()
 
 
-@pytest.mark.parametrize("N,Nz", [(32, 32), (64, 32), (32, 64), (128, 32), (64, 128)])
+@pytest.mark.parametrize("N,Nz", [(32, 32), (64, 32), (32, 64), (128, 32), (64, 128), (256, 32), (512, 32)])
 def test_convolution_data_term_matches_oracle(lib, N, Nz):
     # row f1 (TiPi WeightedConvolutionCost as PSF_Estimation.java:147-157 drives it): 3-D FFT convolution cost
     # and gradient through the same kernel sources, with weights, alpha and the clr flag
