@@ -110,6 +110,11 @@ WFM_API const char* wfm_last_error(const wfm_model* h);
  * NULL restores the handle's own stream. */
 WFM_API int wfm_set_stream(wfm_model* h, void* cuda_stream);
 WFM_API int wfm_synchronize(wfm_model* h);
+/* Device-side ordering against another stream (no host stall): wfm_wait_stream makes the handle's stream wait for
+ * everything queued on `cuda_stream` so far (e.g. the producer of q); wfm_fence_stream makes `cuda_stream` wait for
+ * everything queued on the handle's stream so far (e.g. before a collective on the gradient it just wrote). */
+WFM_API int wfm_wait_stream(wfm_model* h, void* cuda_stream);
+WFM_API int wfm_fence_stream(wfm_model* h, void* cuda_stream);
 
 /* ---- pupil construction ------------------------------------------------------------- */
 
@@ -232,7 +237,9 @@ WFM_API int wfm_conv_cost_and_gradient_dev(wfm_conv* c, double alpha, const void
                                            double* cost_dev);
 /* One COMPUTE_FG step of PSF_Estimation.fitPSF (PSF_Estimation.java:202-217) entirely on the device:
  * setParam(x) -> computePsf() -> computeCostAndGradient(alpha, psf, gcost, true) -> apply_Jacobian(gcost, space).
- * Only x (n doubles) crosses to the device; the cost and the n gradient doubles come back. */
+ * Only x (n doubles) crosses to the device; the cost and the n gradient doubles come back.  x == NULL: the caller
+ * has already taken the setParam step through wfm_set_defocus / _phase / _modulus (what the host mirrors do, so
+ * that their parameterCoefs stay in step); the chain then starts at computePsf(). */
 WFM_API int wfm_eval_fg(wfm_model* h, wfm_conv* c, int param, const double* x, int n, double alpha, double* cost,
                         double* grad_out);
 

@@ -136,7 +136,12 @@ public:
     void setNi(double v) { ni_ = v; lambda_ni_ = v / lambda_; setDefocus({ni_ / lambda_, deltaX_, deltaY_}); }   // WFM:1698
     void setModulus(const std::vector<double>& beta) { setNModulus((int)beta.size()); setModulusCoefs(beta); }   // WFM:1616
     void setPhase(const std::vector<double>& alpha) {                                     // WFM:1655-1665
-        if (alpha.empty()) { nPhase_ = 0; parameterCoefs[PHASE].reset(); return; }
+        if (alpha.empty()) {
+            nPhase_ = 0; parameterSpace[PHASE].reset(); parameterCoefs[PHASE].reset();
+            check(wfm_set_phase(h_, nullptr, 0));                                         // the device side drops its vector too
+            freeMem();
+            return;
+        }
         setNPhase((int)alpha.size());
         setPhaseCoefs(alpha);
     }
@@ -246,7 +251,8 @@ public:
         if (flag < 0) throw std::invalid_argument("DoubleShapedVector param does not belong to any space");
         g.assign(x.getNumber(), 0.0);
         double cost = 0.0;
-        const int rc = wfm_eval_fg(pupil.handle(), c_, flag, x.getData().data(), x.getNumber(), alpha, &cost, g.data());
+        pupil.setParam(x);        // WFM:412-422: parameterCoefs (and ni / deltaX / deltaY for the defocus group) follow x
+        const int rc = wfm_eval_fg(pupil.handle(), c_, flag, nullptr, x.getNumber(), alpha, &cost, g.data());
         if (rc != WFM_OK) raise(rc, wfm_last_error(pupil.handle()));
         pupil.markPsfValid();
         return cost;

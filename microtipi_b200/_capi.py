@@ -44,6 +44,8 @@ SIGNATURES = {
     "wfm_last_error": (C.c_char_p, [_vp]),
     "wfm_set_stream": (C.c_int, [_vp, _vp]),
     "wfm_synchronize": (C.c_int, [_vp]),
+    "wfm_wait_stream": (C.c_int, [_vp, _vp]),
+    "wfm_fence_stream": (C.c_int, [_vp, _vp]),
     "wfm_set_optics": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double]),
     "wfm_set_basis": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "wfm_build_basis": (C.c_int, [_vp, C.c_int, C.c_int]),

@@ -101,9 +101,22 @@ class WeightedConvolutionCost:
         """One COMPUTE_FG step of PSF_Estimation.fitPSF (PSF_Estimation.java:202-217) on the device:
         setParam(x) -> computePsf -> computeCostAndGradient -> apply_Jacobian.  Returns (cost, gradient)."""
         xv = np.ascontiguousarray(x.data if isinstance(x, DoubleShapedVector) else x, dtype=np.float64)
+        if int(param_flag) not in (model.DEFOCUS, model.PHASE, model.MODULUS):
+            raise ValueError("DoubleShapedVector param does not belong to any space")
+        # the host mirror takes the step setParam(x) takes (WFM:412-422: x is stored in parameterCoefs, and for the
+        # defocus group ni / lambda_ni / deltaX / deltaY follow, WFM:1516-1531); its setter call IS the first link of
+        # the device chain, so wfm_eval_fg gets x = NULL ("parameters already set")
+        if int(param_flag) == model.PHASE and xv.size == 0:
+            raise ValueError("phase space is empty")
+        setter = {model.DEFOCUS: model.setDefocus, model.PHASE: model.setPhase, model.MODULUS: model.setModulus}
+        owner = model.parameterSpace[int(param_flag)]
+        if isinstance(x, DoubleShapedVector) and x.getOwner() is owner:
+            setter[int(param_flag)](x)
+        else:
+            setter[int(param_flag)](xv.copy())
         g = np.zeros(xv.size)
         cost = C.c_double()
-        rc = self._lib.wfm_eval_fg(model.handle, self._h, int(param_flag), xv.ctypes.data_as(C.c_void_p), xv.size,
+        rc = self._lib.wfm_eval_fg(model.handle, self._h, int(param_flag), None, xv.size,
                                    float(alpha), C.byref(cost), g.ctypes.data_as(C.c_void_p))
         if rc != capi.WFM_OK:
             msg = self._lib.wfm_last_error(model.handle).decode()

@@ -52,7 +52,7 @@ struct wfm_model {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // second stream for wfm_get_psf_async: the D2H of the PSF runs beside the H2D of q (full-duplex PCIe)
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_ready = nullptr, ev_copied = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_copied = nullptr, ev_order = nullptr;
     bool copy_pending = false;
     // optics (WFM:161-166)
     bool have_optics = false;
@@ -122,6 +122,23 @@ struct wfm_model {
         if (e__ != cudaSuccess)                                                                 \
             return (h)->fail(WFM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e__)); \
     } while (0)
+
+// Every entry point that allocates, copies or launches runs with the handle's device current and hands the
+// caller's device back on return: a fresh host thread starts on device 0, whatever device its handle lives on.
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false, ok = true;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) { ok = cudaSetDevice(dev) == cudaSuccess; switched = ok && prev >= 0; }
+    }
+    ~DeviceScope() { if (switched) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+#define WFM_ENTER(h)                                                                             \
+    DeviceScope dev_scope__((h)->device);                                                        \
+    if (!dev_scope__.ok) return (h)->fail(WFM_ERR_CUDA, "cudaSetDevice(%d) failed", (h)->device)
 
 namespace {
 
@@ -464,7 +481,7 @@ template <typename T> int dispatch_jac(wfm_model* h, unsigned kinds, const void*
 int compute_psf_impl(wfm_model* h) {
     if (h->pstate > 0) return WFM_OK;                                          // WFM:207
     if (!h->have_rho) return h->fail(WFM_ERR_STATE, "pupil modulus not set: call wfm_set_modulus or wfm_set_pupil_arrays first");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     int rc = rebuild_activity(h); if (rc) return rc;
     const size_t vox = (size_t)h->npix() * h->nzl;
     WFM_CK(h, h->cpx.ensure(vox * 2 * h->esz()));
@@ -490,6 +507,18 @@ int check_pipeline(wfm_model* h) {
 
 int elementwise_grid(int n) { return (n + 255) / 256; }
 
+// A new basis invalidates coefficient vectors that no longer fit it: they are dropped (nPhase / nModulus = 0, phi
+// cleared) exactly as setNPhase / setNModulus rebuild their spaces with the basis (WFM:1899-1914, 1939-1961).
+int revalidate_coefs(wfm_model* h) {
+    const int off = h->radial ? 1 : 3;
+    if (h->nphase > 0 && h->nphase + off > h->nzern) {
+        h->nphase = 0; h->alpha_b.clear();
+        WFM_CK(h, cudaMemsetAsync(h->phi.p, 0, 8 * (size_t)h->npix() * h->nbatch, h->stream));
+    }
+    if (h->nmod > h->nzern) { h->nmod = 0; h->beta_b.clear(); h->have_rho = false; }
+    return WFM_OK;
+}
+
 int upload_table(wfm_model* h, DevBuf& buf, const std::vector<double>& v) {
     WFM_CK(h, buf.ensure(8 * v.size()));
     WFM_CK(h, cudaMemcpyAsync(buf.p, v.data(), 8 * v.size(), cudaMemcpyHostToDevice, h->stream));
@@ -504,7 +533,7 @@ int batch_set_phase(wfm_model* h, const double* tab, int n, int stride) {
     if (n > 0 && (h->nzern <= 0)) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
     if (n > 0 && n + off > h->nzern)
         return h->fail(WFM_ERR_INVALID_ARG, "phase parameter does not belong to the right space  ");   // WFM:1629
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     h->alpha_b.assign((size_t)h->nbatch * (n > 0 ? n : 1), 0.0);
     for (int b = 0; b < h->nbatch; ++b)
         for (int k = 0; k < n; ++k) h->alpha_b[(size_t)b * n + k] = tab[(size_t)b * stride + k];
@@ -524,7 +553,7 @@ int batch_set_modulus(wfm_model* h, const double* tab, int n, int stride) {
     if (h->nzern <= 0) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
     if (n > h->nzern)
         return h->fail(WFM_ERR_INVALID_ARG, "DoubleShapedVector beta does not belong to the modulus space");  // WFM:1592
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     h->beta_b.assign((size_t)h->nbatch * n, 0.0);
     for (int b = 0; b < h->nbatch; ++b) {
         double s = 0.0;
@@ -547,7 +576,7 @@ int batch_set_modulus(wfm_model* h, const double* tab, int n, int stride) {
 int batch_set_defocus(wfm_model* h, const double* tab, int n, int stride) {
     if (!tab || (n != 1 && n != 3)) return h->fail(WFM_ERR_INVALID_ARG, "bad defocus  parameters");   // WFM:1530, Q4
     if (!h->have_optics) return h->fail(WFM_ERR_STATE, "optics not set: call wfm_set_optics first");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     for (int b = 0; b < h->nbatch; ++b) {
         const double* d = tab + (size_t)b * stride;
         if (n == 3) { h->bpar_h[4 * b + 1] = d[1]; h->bpar_h[4 * b + 2] = d[2]; }   // WFM:1518-1520
@@ -614,8 +643,10 @@ static int create_impl(wfm_model** out, int nx, int ny, int nz_global, int z0, i
     if (h->rho.ensure(8 * all) || h->phi.ensure(8 * all) || h->psi.ensure(8 * all) || h->mask.ensure(all) ||
         h->map.ensure(npix) || h->grad.ensure(8 * (3 + 2 * WFM_MAX_COEF) * (size_t)nbatch))
         return bail(WFM_ERR_NOMEM, "device allocation failed");
-    cudaMemset(h->rho.p, 0, 8 * all); cudaMemset(h->phi.p, 0, 8 * all); cudaMemset(h->psi.p, 0, 8 * all);
-    cudaMemset(h->mask.p, 0, all); cudaMemset(h->map.p, 0, npix);
+    if (cudaMemset(h->rho.p, 0, 8 * all) != cudaSuccess || cudaMemset(h->phi.p, 0, 8 * all) != cudaSuccess ||
+        cudaMemset(h->psi.p, 0, 8 * all) != cudaSuccess || cudaMemset(h->mask.p, 0, all) != cudaSuccess ||
+        cudaMemset(h->map.p, 0, npix) != cudaSuccess)
+        return bail(WFM_ERR_CUDA, "clearing the pupil arrays failed");
     if (upload_twiddles(h) != WFM_OK) return bail(WFM_ERR_CUDA, "twiddle upload failed");
     *out = h;
     return WFM_OK;
@@ -650,6 +681,7 @@ int wfm_destroy(wfm_model* h) {
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->ev_ready) cudaEventDestroy(h->ev_ready);
     if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+    if (h->ev_order) cudaEventDestroy(h->ev_order);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return WFM_OK;
@@ -659,13 +691,34 @@ const char* wfm_last_error(const wfm_model* h) { return h ? h->err.c_str() : g_c
 
 int wfm_set_stream(wfm_model* h, void* s) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     cudaStreamSynchronize(h->stream);
     h->stream = s ? (cudaStream_t)s : h->own_stream;
     return WFM_OK;
 }
 
+// Ordering against a caller-owned stream without stalling the host (one cached event, re-recorded per call).
+static int order_streams(wfm_model* h, cudaStream_t first, cudaStream_t then) {
+    if (first == then) return WFM_OK;
+    if (!h->ev_order) WFM_CK(h, cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
+    WFM_CK(h, cudaEventRecord(h->ev_order, first));
+    WFM_CK(h, cudaStreamWaitEvent(then, h->ev_order, 0));
+    return WFM_OK;
+}
+int wfm_wait_stream(wfm_model* h, void* s) {          // the handle's stream waits for what `s` holds so far
+    if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
+    return order_streams(h, (cudaStream_t)s, h->stream);
+}
+int wfm_fence_stream(wfm_model* h, void* s) {         // `s` waits for what the handle's stream holds so far
+    if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
+    return order_streams(h, h->stream, (cudaStream_t)s);
+}
+
 int wfm_synchronize(wfm_model* h) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     return check_pipeline(h);
 }
@@ -673,7 +726,7 @@ int wfm_synchronize(wfm_model* h) {
 int wfm_set_optics(wfm_model* h, double NA, double lambda, double ni) {
     if (!h) return WFM_ERR_INVALID_ARG;
     if (!(NA > 0) || !(lambda > 0) || !(ni > 0)) return h->fail(WFM_ERR_INVALID_ARG, "NA, lambda and ni must be positive");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     h->NA = NA; h->lambda = lambda; h->ni = ni;
     h->radius = NA / lambda;                                                   // WFM:165
     h->lambda_ni = ni / lambda;                                                // WFM:166
@@ -696,7 +749,7 @@ int wfm_set_optics(wfm_model* h, double NA, double lambda, double ni) {
 int wfm_set_basis(wfm_model* h, const double* Z, int nzern, int radial) {
     if (!h) return WFM_ERR_INVALID_ARG;
     if (!Z || nzern <= 0) return h->fail(WFM_ERR_INVALID_ARG, "Z is NULL or nzern <= 0");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     const size_t npix = h->npix();
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     WFM_CK(h, h->Z.ensure(8 * npix * nzern));
@@ -707,6 +760,7 @@ int wfm_set_basis(wfm_model* h, const double* Z, int nzern, int radial) {
         for (size_t i = 0; i < npix; ++i)
             if (Z[(size_t)k * npix + i] != 0.0) h->h_zsup[i] = 1;
     h->activity_dirty = true;
+    { int rcv = revalidate_coefs(h); if (rcv) return rcv; }
     return invalidate(h);
 }
 
@@ -715,7 +769,7 @@ int wfm_build_basis(wfm_model* h, int nzern, int radial) {
     if (!h) return WFM_ERR_INVALID_ARG;
     if (nzern <= 0) return h->fail(WFM_ERR_INVALID_ARG, "nzern <= 0");
     if (!h->have_optics) return h->fail(WFM_ERR_STATE, "optics not set: call wfm_set_optics first");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     const int N = h->N, npix = h->npix();
     // Noll index -> (n, m)  Zernike.java:37-52
     auto noll = [](int J, int& n, int& m) {
@@ -791,11 +845,13 @@ int wfm_build_basis(wfm_model* h, int nzern, int radial) {
             if (std::sqrt(kx * kx + ky * ky) < radius_px) h->h_zsup[x + N * y] = 1;
         }
     h->activity_dirty = true;
+    { int rcv = revalidate_coefs(h); if (rcv) return rcv; }
     return invalidate(h);
 }
 
 int wfm_get_basis(wfm_model* h, double* out, int nzern) {
     if (!h || !out) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     if (nzern <= 0 || nzern > h->nzern) return h->fail(WFM_ERR_INVALID_ARG, "nzern out of range");
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     WFM_CK(h, cudaMemcpy(out, h->Z.p, 8 * (size_t)h->npix() * nzern, cudaMemcpyDeviceToHost));
@@ -810,7 +866,7 @@ int wfm_set_phase(wfm_model* h, const double* alpha, int n) {
     if (n > 0 && (h->nzern <= 0)) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
     if (n > 0 && n + off > h->nzern)
         return h->fail(WFM_ERR_INVALID_ARG, "phase parameter does not belong to the right space  ");   // WFM:1629
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     for (int k = 0; k < n; ++k) h->alpha.v[k] = alpha[k];
     h->nphase = n;
     KernelSpan span(h, WFM_K_SETTERS);
@@ -828,7 +884,7 @@ int wfm_set_modulus(wfm_model* h, const double* beta, int n) {
     if (h->nzern <= 0) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
     if (n > h->nzern)
         return h->fail(WFM_ERR_INVALID_ARG, "DoubleShapedVector beta does not belong to the modulus space");  // WFM:1592
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     double s = 0.0;
     for (int k = 0; k < n; ++k) { h->beta.v[k] = beta[k]; s += beta[k] * beta[k]; }
     h->nmod = n;
@@ -846,7 +902,7 @@ int wfm_set_defocus(wfm_model* h, const double* defoc, int n) {
     if (h->nbatch > 1) return batch_set_defocus(h, defoc, n, 0);
     if (!defoc || (n != 1 && n != 3)) return h->fail(WFM_ERR_INVALID_ARG, "bad defocus  parameters");   // WFM:1530, Q4
     if (!h->have_optics) return h->fail(WFM_ERR_STATE, "optics not set: call wfm_set_optics first");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     if (n == 3) { h->deltaX = defoc[1]; h->deltaY = defoc[2]; }                // WFM:1518-1520
     h->lambda_ni = defoc[0];                                                   // WFM:1522
     h->ni = h->lambda_ni * h->lambda;                                          // WFM:1523
@@ -878,7 +934,7 @@ int wfm_batch_set_defocus(wfm_model* h, const double* defoc, int n) {
 int wfm_set_pupil_arrays(wfm_model* h, const double* rho, const double* phi, const double* psi, const uint8_t* mask) {
     if (!h) return WFM_ERR_INVALID_ARG;
     if (h->nbatch > 1) return h->fail(WFM_ERR_UNSUPPORTED, "wfm_set_pupil_arrays: not available on a batch handle");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     const size_t npix = h->npix();
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     if (h->h_esc.empty()) h->h_esc.assign(npix, 0);
@@ -908,7 +964,7 @@ int wfm_set_modulus_mode(wfm_model* h, int mode) {
 
 static int copy_out(wfm_model* h, void* out, const void* dev, size_t bytes) {
     if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     WFM_CK(h, cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     return check_pipeline(h);
@@ -920,12 +976,17 @@ int wfm_get_phi(wfm_model* h, double* out) { return h ? copy_out(h, out, h->phi.
 int wfm_get_psi(wfm_model* h, double* out) { return h ? copy_out(h, out, h->psi.p, 8 * (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
 int wfm_get_mask(wfm_model* h, uint8_t* out) { return h ? copy_out(h, out, h->mask.p, (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
 
-int wfm_compute_psf(wfm_model* h) { return h ? compute_psf_impl(h) : WFM_ERR_INVALID_ARG; }
+int wfm_compute_psf(wfm_model* h) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
+    return compute_psf_impl(h);
+}
 int wfm_invalidate(wfm_model* h) { return h ? invalidate(h) : WFM_ERR_INVALID_ARG; }
 int wfm_psf_state(const wfm_model* h) { return h ? h->pstate : 0; }
 
 int wfm_get_psf(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1800-1802
     return copy_out(h, out, h->psf.p, (size_t)h->npix() * h->nzl * h->esz());
 }
@@ -935,6 +996,7 @@ int wfm_get_psf(wfm_model* h, void* out) {
 // computePsf() on this handle is ordered after the copy, so the slab is never overwritten while it is read.
 int wfm_get_psf_async(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
     int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1800-1802
     if (!h->copy_stream) {
@@ -952,6 +1014,7 @@ int wfm_get_psf_async(wfm_model* h, void* out) {
 
 int wfm_wait_transfers(wfm_model* h) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     if (h->copy_stream) WFM_CK(h, cudaStreamSynchronize(h->copy_stream));
     h->copy_pending = false;
     return check_pipeline(h);
@@ -960,6 +1023,7 @@ int wfm_wait_transfers(wfm_model* h) {
 // ArrayUtils.roll(pupil.getPsf()) (BlindDeconvJob.java:100) -- "next" row f4: the centred PSF, shifted on the device.
 int wfm_roll_psf_dev(wfm_model* h, void* out_dev) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     if (!out_dev) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
     if (h->z0 != 0 || h->nzl != h->nz_global)
         return h->fail(WFM_ERR_UNSUPPORTED, "the rolled PSF needs the whole stack of ONE model on the handle (z roll crosses slabs)");
@@ -980,7 +1044,7 @@ int wfm_roll_psf_dev(wfm_model* h, void* out_dev) {
 int wfm_get_psf_rolled(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
     if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     const size_t bytes = (size_t)h->npix() * h->nzl * h->esz();
     WFM_CK(h, h->qdev.ensure(bytes));                    // reuse the q staging buffer
     int rc = wfm_roll_psf_dev(h, h->qdev.p); if (rc) return rc;
@@ -989,17 +1053,20 @@ int wfm_get_psf_rolled(wfm_model* h, void* out) {
 
 int wfm_get_cpx_psf(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1857-1859
     return copy_out(h, out, h->cpx.p, (size_t)h->npix() * h->nzl * 2 * h->esz());
 }
 
 int wfm_device_psf(wfm_model* h, void** p) {
     if (!h || !p) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     int rc = compute_psf_impl(h); if (rc) return rc;
     *p = h->psf.p; return WFM_OK;
 }
 int wfm_device_cpx_psf(wfm_model* h, void** p) {
     if (!h || !p) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     int rc = compute_psf_impl(h); if (rc) return rc;
     *p = h->cpx.p; return WFM_OK;
 }
@@ -1008,6 +1075,7 @@ int wfm_grad_length(const wfm_model* h) { return h ? h->glen() : 0; }
 
 int wfm_apply_jacobian_dev(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     if (!q_dev || !grad_dev) return h->fail(WFM_ERR_INVALID_ARG, "q_dev / grad_dev is NULL");
     if (!(kinds & 7u)) return h->fail(WFM_ERR_INVALID_ARG, "no Jacobian selected");
     if ((kinds & WFM_J_PHASE) && h->nphase <= 0) return h->fail(WFM_ERR_STATE, "phase space is empty (nPhase = 0)");
@@ -1020,7 +1088,7 @@ int wfm_apply_jacobian_dev(wfm_model* h, unsigned kinds, const void* q_dev, doub
 
 static int apply_host(wfm_model* h, unsigned kinds, const void* q_host, std::vector<double>& g) {
     if (!q_host) return h->fail(WFM_ERR_INVALID_ARG, "q is NULL");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     const size_t bytes = (size_t)h->npix() * h->nzl * h->esz();
     WFM_CK(h, h->qdev.ensure(bytes));
     WFM_CK(h, cudaMemcpyAsync(h->qdev.p, q_host, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -1102,7 +1170,7 @@ int wfm_apply_j_all(wfm_model* h, const void* q, double* d3, double* ph, double*
 int wfm_fill_uniform(wfm_model* h, void* dev, int precision, uint64_t seed, uint64_t first, uint64_t count) {
     if (!h) return WFM_ERR_INVALID_ARG;
     if (!dev) return h->fail(WFM_ERR_INVALID_ARG, "dev_ptr is NULL");
-    WFM_CK(h, cudaSetDevice(h->device));
+    WFM_ENTER(h);
     const unsigned grid = (unsigned)((count + 255) / 256);
     if (precision == WFM_F64) {
         auto kfn = &k_fill_uniform<double>;
@@ -1138,6 +1206,7 @@ int wfm_get_info(const wfm_model* h, int* nx, int* ny, int* nzg, int* z0, int* n
 
 int wfm_active_extent(const wfm_model* h, int* nax, int* nay) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    DeviceScope dev_scope__(h->device);
     int rc = rebuild_activity(const_cast<wfm_model*>(h)); if (rc) return rc;
     if (nax) *nax = h->nax;
     if (nay) *nay = h->nay;
@@ -1146,6 +1215,7 @@ int wfm_active_extent(const wfm_model* h, int* nax, int* nay) {
 
 int wfm_set_profiling(wfm_model* h, int on) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     drain_spans(h);
     h->profiling = on != 0;
@@ -1155,6 +1225,7 @@ int wfm_set_profiling(wfm_model* h, int on) {
 
 int wfm_get_kernel_times(wfm_model* h, double* ms, uint64_t* counts, int n) {
     if (!h || !ms || !counts || n < WFM_KERNEL_IDS) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(h);
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     drain_spans(h);
     for (int i = 0; i < WFM_KERNEL_IDS; ++i) { ms[i] = h->k_ms[i]; counts[i] = h->k_count[i]; }

@@ -198,6 +198,7 @@ const char* wfm_conv_last_error(const wfm_conv* c) { return c ? c->err.c_str() :
 
 int wfm_conv_set_stream(wfm_conv* c, void* s) {
     if (!c) return WFM_ERR_INVALID_ARG;
+    WFM_ENTER(c);
     cudaStreamSynchronize(c->stream);
     c->stream = s ? (cudaStream_t)s : c->own_stream;
     return WFM_OK;
@@ -207,7 +208,7 @@ int wfm_conv_set_stream(wfm_conv* c, void* s) {
 int wfm_conv_set_object(wfm_conv* c, const void* obj_host) {
     if (!c) return WFM_ERR_INVALID_ARG;
     if (!obj_host) return c->fail(WFM_ERR_INVALID_ARG, "object is NULL");
-    WFM_CK(c, cudaSetDevice(c->device));
+    WFM_ENTER(c);
     WFM_CK(c, c->hdev.ensure(8 * c->vox()));
     WFM_CK(c, cudaMemcpyAsync(c->hdev.p, obj_host, 8 * c->vox(), cudaMemcpyHostToDevice, c->stream));
     ConvArgs<double> a = conv_args(c);
@@ -223,7 +224,7 @@ int wfm_conv_set_object(wfm_conv* c, const void* obj_host) {
 int wfm_conv_set_data(wfm_conv* c, const void* y_host) {          // fdata.setData(data)  PSF_Estimation.java:149
     if (!c) return WFM_ERR_INVALID_ARG;
     if (!y_host) return c->fail(WFM_ERR_INVALID_ARG, "data is NULL");
-    WFM_CK(c, cudaSetDevice(c->device));
+    WFM_ENTER(c);
     WFM_CK(c, cudaMemcpyAsync(c->y.p, y_host, 8 * c->vox(), cudaMemcpyHostToDevice, c->stream));
     WFM_CK(c, cudaStreamSynchronize(c->stream));
     c->have_data = true;
@@ -232,7 +233,7 @@ int wfm_conv_set_data(wfm_conv* c, const void* y_host) {          // fdata.setDa
 
 int wfm_conv_set_weights(wfm_conv* c, const void* w_host) {       // fdata.setWeights(weights, true)  :150
     if (!c) return WFM_ERR_INVALID_ARG;
-    WFM_CK(c, cudaSetDevice(c->device));
+    WFM_ENTER(c);
     if (!w_host) { c->have_w = false; return WFM_OK; }
     WFM_CK(c, c->w.ensure(8 * c->vox()));
     WFM_CK(c, cudaMemcpyAsync(c->w.p, w_host, 8 * c->vox(), cudaMemcpyHostToDevice, c->stream));
@@ -247,7 +248,7 @@ int wfm_conv_cost_and_gradient_dev(wfm_conv* c, double alpha, const void* h_dev,
     if (!c) return WFM_ERR_INVALID_ARG;
     if (!h_dev || !grad_dev) return c->fail(WFM_ERR_INVALID_ARG, "h_dev / grad_dev is NULL");
     if (!c->have_obj || !c->have_data) return c->fail(WFM_ERR_STATE, "object and data must be set first");
-    WFM_CK(c, cudaSetDevice(c->device));
+    WFM_ENTER(c);
     ConvArgs<double> a = conv_args(c);
     a.real_in = (const double*)h_dev; a.grad = (double*)grad_dev; a.alpha = alpha; a.clear_grad = clr ? 1 : 0;
     a.cost_part = (double*)c->cost_part.p;
@@ -282,7 +283,7 @@ int wfm_conv_cost_and_gradient_dev(wfm_conv* c, double alpha, const void* h_dev,
 int wfm_conv_cost_and_gradient(wfm_conv* c, double alpha, const void* h_host, void* grad_host, int clr, double* cost) {
     if (!c) return WFM_ERR_INVALID_ARG;
     if (!h_host || !grad_host || !cost) return c->fail(WFM_ERR_INVALID_ARG, "h / grad / cost is NULL");
-    WFM_CK(c, cudaSetDevice(c->device));
+    WFM_ENTER(c);
     const size_t bytes = 8 * c->vox();
     WFM_CK(c, c->hdev.ensure(bytes));
     WFM_CK(c, c->gdev.ensure(bytes));
@@ -301,24 +302,27 @@ int wfm_conv_cost_and_gradient(wfm_conv* c, double alpha, const void* h_host, vo
 // Only x (n doubles) goes to the device and {cost, gX} come back.  param: WFM_DEFOCUS / WFM_PHASE / WFM_MODULUS.
 int wfm_eval_fg(wfm_model* h, wfm_conv* c, int param, const double* x, int n, double alpha, double* cost, double* grad_out) {
     if (!h || !c) return WFM_ERR_INVALID_ARG;
-    if (!x || !cost || !grad_out) return h->fail(WFM_ERR_INVALID_ARG, "x / cost / grad_out is NULL");
+    if (!cost || !grad_out) return h->fail(WFM_ERR_INVALID_ARG, "cost / grad_out is NULL");
     if (h->precision != WFM_F64) return h->fail(WFM_ERR_UNSUPPORTED, "wfm_eval_fg is fp64 only in this revision");
     if (h->N != c->nx || h->nz_global != c->nz || h->z0 != 0 || h->nzl != h->nz_global || h->nbatch != 1)
         return h->fail(WFM_ERR_INVALID_ARG, "model and data term must have the same (unsharded) shape");
     if (h->device != c->device) return h->fail(WFM_ERR_INVALID_ARG, "model and data term live on different devices");
     int rc;
     unsigned kinds;
+    // x == NULL: the caller has already taken the setParam(x) step through the matching setter (the host mirrors do,
+    // so that their parameterCoefs / ni / deltaX / deltaY stay in step, WFM:412-422, 1516-1531)
     switch (param) {                                                           // WFM:412-422
-        case WFM_DEFOCUS: rc = wfm_set_defocus(h, x, n); kinds = WFM_J_DEFOCUS; break;
-        case WFM_PHASE: rc = wfm_set_phase(h, x, n); kinds = WFM_J_PHASE; break;
-        case WFM_MODULUS: rc = wfm_set_modulus(h, x, n); kinds = WFM_J_MODULUS; break;
+        case WFM_DEFOCUS: rc = x ? wfm_set_defocus(h, x, n) : WFM_OK; kinds = WFM_J_DEFOCUS; if (!x) n = h->ndefocus; break;
+        case WFM_PHASE: rc = x ? wfm_set_phase(h, x, n) : WFM_OK; kinds = WFM_J_PHASE; break;
+        case WFM_MODULUS: rc = x ? wfm_set_modulus(h, x, n) : WFM_OK; kinds = WFM_J_MODULUS; break;
         default: return h->fail(WFM_ERR_INVALID_ARG, "DoubleShapedVector param does not belong to any space");
     }
     if (rc) return rc;
+    WFM_ENTER(h);
     if ((rc = compute_psf_impl(h))) return rc;
+    WFM_CK(h, c->gdev.ensure(8 * c->vox()));                // (before the stream swap: no early return while it is swapped)
     cudaStream_t saved = c->stream;
     c->stream = h->stream;                                  // one stream: the steps are ordered
-    WFM_CK(h, c->gdev.ensure(8 * c->vox()));
     rc = wfm_conv_cost_and_gradient_dev(c, alpha, h->psf.p, c->gdev.p, 1, nullptr);
     c->stream = saved;
     if (rc) return h->fail(rc, "%s", c->err.c_str());
@@ -341,6 +345,7 @@ int wfm_get_mtf(wfm_model* h, void* out_host) {
     if (h->precision != WFM_F64) return h->fail(WFM_ERR_UNSUPPORTED, "getMtf is fp64 only in this revision");
     if (h->z0 != 0 || h->nzl != h->nz_global) return h->fail(WFM_ERR_UNSUPPORTED, "getMtf needs the whole stack on one handle");
     if (!supported_n(h->nz_global)) return h->fail(WFM_ERR_UNSUPPORTED, "getMtf needs Nz to be a power of two in [32, 2048]");
+    WFM_ENTER(h);
     int rc = compute_psf_impl(h); if (rc) return rc;
     wfm_conv* c = nullptr;
     rc = conv_create_impl(&c, h->N, h->N, h->nz_global, WFM_F64, h->device, true);

@@ -674,7 +674,11 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ringoff, c
     for (int kk = 0; kk < Cfg::KR; ++kk) {
         if (kk == Cfg::KR - 1) qu.prefetch(ctl, a.g.nzl);             // claim the next item behind the last row
         const int ky = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;     // N % ROWS_PER_ITEM == 0
+#ifdef WFM_PROBE_PSF_L1LD          /* timing probe only (wrong results): ring loads that hit the L1 */
+        const cx<T>* src = a.T1 + (size_t)slot * C;
+#else
         const cx<T>* src = a.T1 + (size_t)ringoff + (size_t)ky * C;
+#endif
         cx<T> v[E];
 #if WFM_ROW_PREFETCH
 #pragma unroll
@@ -688,10 +692,18 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ringoff, c
 #else
 #pragma unroll
         for (int e = 0; e < E; ++e)
+#ifdef WFM_PROBE_PSF_L1LD
+            v[e] = (leg_live<P::R1, NARROW>(e % P::R1) && xis[e] >= 0) ? __ldg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
+#else
             v[e] = (leg_live<P::R1, NARROW>(e % P::R1) && xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
 #endif
+#endif
         fft_inplace<T, P, L, RowSync<TT>, NoHook, NARROW, WFM_PSF_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
+#ifdef WFM_PROBE_PSF_L2ST          /* timing probe only (wrong results): stores that never reach DRAM */
+        const size_t base = (size_t)N * (blockIdx.x * C + slot);
+#else
         const size_t base = (size_t)pl * N * N + (size_t)N * ky;
+#endif
 #pragma unroll
         for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
@@ -809,8 +821,14 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
     for (int kk = 0; kk < Cfg::KR; ++kk) {
         if (kk == Cfg::KR - 1) qu.prefetch(ctl, a.g.nzl);             // claim the next item behind the last row
         const int y = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;      // N % ROWS_PER_ITEM == 0
+#if defined(WFM_PROBE_JAC_L1)      /* timing probes only (wrong results): what if the row loads never left the SM / the L2? */
+        const size_t base = 0;
+#elif defined(WFM_PROBE_JAC_L2)
+        const size_t base = (size_t)N * (blockIdx.x * C + slot);
+#else
         const size_t base = (size_t)pl * N * N + (size_t)N * y;
-#if WFM_L2_PREFETCH
+#endif
+#if WFM_L2_PREFETCH && !defined(WFM_PROBE_JAC_L1) && !defined(WFM_PROBE_JAC_L2)
         if (t == 0 && kk + 1 < Cfg::KR) {              // this group's next row: DRAM -> L2 while this row is transformed
             wfm_prefetch_l2(&a.cpx[base + (size_t)N * C], (unsigned)(N * sizeof(cx<T>)));
             wfm_prefetch_l2(&a.q[base + (size_t)N * C], (unsigned)(N * sizeof(T)));
@@ -837,8 +855,13 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
 #pragma unroll
             for (int r = 0; r < P::R1; ++r) {
                 const int x = (t + TT * u) + P::S1 * r;
+#if defined(WFM_PROBE_JAC_L1) || defined(WFM_PROBE_JAC_L2)
+                const cx<T> av = __ldg(&a.cpx[base + x]);
+                const T qv = __ldg(&a.q[base + x]);
+#else
                 const cx<T> av = __ldcs(&a.cpx[base + x]);
                 const T qv = __ldcs(&a.q[base + x]);
+#endif
                 v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
             }
 #endif

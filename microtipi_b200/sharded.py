@@ -38,6 +38,7 @@ class ShardedWideFieldModel:
             raise ValueError("more ranks than z-planes")
         self.model = WideFieldModel(psfShape, nPhase, nModulus, NA, lambda_, ni, dxy, dz, radial, single,
                                     device=device, z0=self.z0, nz_local=self.nz_local, lib=lib, basis=basis)
+        self._handle_stream_ptr = None      # None: the handle's own (non-blocking) stream
 
     def __getattr__(self, name):           # setters / getters are slab-local and identical on every rank
         return getattr(self.model, name)
@@ -69,12 +70,26 @@ class ShardedWideFieldModel:
         return full[:3], full[3:3 + p.size], full[3 + p.size:]
 
     def applyJacobianDeviceAllReduce(self, kinds, q_tensor, grad_tensor):
-        """Device-resident path: q / grad are torch CUDA tensors; NCCL allreduce of the K-vector on
-        the current torch stream (the handle must run on that stream, see WideFieldModel.setStream)."""
+        """Device-resident path: q / grad are torch CUDA tensors; NCCL allreduce of the K-vector on the current
+        torch stream.  The Jacobian kernels run on the HANDLE's stream; unless that is the current torch stream
+        (WideFieldModel.setStream) the collective is ordered behind them here: an event recorded on the handle's
+        stream after k_jac_final, waited for by the torch stream, so NCCL can never sum a gradient that has not
+        been written yet."""
+        import torch
+        cur = torch.cuda.current_stream()
+        if self.world > 1 and self._handle_stream_ptr != cur.cuda_stream:
+            # q may have been produced on the torch stream: the handle's stream waits for it first
+            self.model.waitForStream(cur.cuda_stream)
         self.model.applyJacobianDevice(kinds, q_tensor.data_ptr(), grad_tensor.data_ptr())
         if self.world > 1:
+            if self._handle_stream_ptr != cur.cuda_stream:
+                self.model.orderStreamAfter(cur.cuda_stream)
             self._dist.all_reduce(grad_tensor, op=self._dist.ReduceOp.SUM, group=self.group)
         return grad_tensor
+
+    def setStream(self, cuda_stream_ptr):
+        self._handle_stream_ptr = int(cuda_stream_ptr or 0) or None
+        self.model.setStream(cuda_stream_ptr)
 
     def gatherPsfDevice(self):
         """NCCL all-gather of the PSF slabs on the device: returns a CUDA tensor (Nz, Ny, Nx) holding the

@@ -235,6 +235,14 @@ class WideFieldModel(MicroscopeModel):
     def synchronize(self):
         self._call("wfm_synchronize")
 
+    def waitForStream(self, cuda_stream_ptr):
+        """The handle's stream waits (on the device) for the work queued on another stream so far."""
+        self._call("wfm_wait_stream", C.c_void_p(cuda_stream_ptr))
+
+    def orderStreamAfter(self, cuda_stream_ptr):
+        """Another stream waits (on the device) for the work queued on the handle's stream so far."""
+        self._call("wfm_fence_stream", C.c_void_p(cuda_stream_ptr))
+
     # -- basis -----------------------------------------------------------------------------------
     def computeZernike(self):                                              # WFM:194-197
         if self._basis_fn is not None:
@@ -294,6 +302,8 @@ class WideFieldModel(MicroscopeModel):
     def apply_J_all(self, q):
         """All three Jacobians from one adjoint FFT pass (they differ only after the FFT)."""
         qh = _as_host(q, self._dtype())
+        if qh.size != self._npix() * self.nz_local:
+            raise ValueError("gradient does not have the shape of the PSF")
         d = np.zeros(3)
         p = np.zeros(max(self.getNPhase(), 1))
         m = np.zeros(self.getNModulus())
@@ -406,7 +416,10 @@ class WideFieldModel(MicroscopeModel):
         if not isinstance(phase, DoubleShapedVector):
             if phase is None or len(phase) == 0:
                 self.nPhase = 0
+                self.parameterSpace[self.PHASE] = None
                 self.parameterCoefs[self.PHASE] = None
+                self._call("wfm_set_phase", None, 0)                       # the device side drops its phase vector too
+                self.freeMem()
                 return
             phase = np.asarray(phase, dtype=np.float64)
             self.setNPhase(phase.size)
@@ -630,5 +643,6 @@ class WideFieldModelBatch(WideFieldModel):
         self._call("wfm_batch_apply_jacobian", int(kinds), qh.ctypes.data_as(C.c_void_p),
                    out.ctypes.data_as(C.c_void_p))
         self.PState = self._lib.wfm_psf_state(self._h)
-        nP = self.getNPhase()
-        return out[:, :3], out[:, 3:3 + nP], out[:, 3 + nP:]
+        nP, nM = C.c_int(), C.c_int()                                      # split by the handle's own counts
+        self._call("wfm_get_info", None, None, None, None, None, None, None, C.byref(nP), C.byref(nM))
+        return out[:, :3], out[:, 3:3 + nP.value], out[:, 3 + nP.value:3 + nP.value + nM.value]

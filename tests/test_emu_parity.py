@@ -352,3 +352,12 @@ def test_randomised_configurations_match_oracle(lib, seed):
     if nPhase:
         assert o.rel_l2(p, ref.apply_J_phase(qz)) <= tj
     m.close()
+
+
+def test_gpu_case_helpers_at_small_sizes(lib):
+    """The bodies of the full-stack / escape-hatch GPU tests, run on the emulated build at sizes it finishes in
+    seconds (a ragged slab across the z wrap, more planes than the intermediate ring holds)."""
+    from tests.test_gpu_parity import escape_hatch_case, full_stack_case
+    full_stack_case(lib, 32, 96, 40, 50, False)
+    full_stack_case(lib, 32, 16, 3, 9, True)
+    escape_hatch_case(lib, ((32, 5, 0.2), (32, 3, 0.4)))

@@ -384,3 +384,138 @@ def test_generic_kernels_when_the_pupil_is_wide(lib):
     for a, b in zip(m.apply_J_all(q), (ref.apply_J_defocus(q), ref.apply_J_phase(q), ref.apply_J_modulus(q))):
         assert o.rel_l2(a, b) <= 1e-12
     m.close()
+
+
+# ---- full-stack parity at the BASELINE shapes (every plane against the oracle) ---------------------------------
+# These are the only cases where the plane index exceeds the intermediate ring of the pipelines (ring = 2*lag + 2
+# planes, ~44 at 512^2), i.e. where ring slots are re-used and the B(p - ring) -> A(p) dependency is live.
+def _oracle_stack(ref, Nz, z0, nzl, q, single=False):
+    """Oracle PSF / cpxPsf / three Jacobians of the slab [z0, z0+nzl) of a global stack of Nz planes."""
+    w = os.cpu_count() or 1
+    rho, phi, psi, mask = ref.rho, ref.phi, ref.psi, ref.maskPupil
+    cpx, psf = o.compute_psf(rho, phi, psi, Nz, P["dz"], single=single, z0=z0, nz_local=nzl, workers=w)
+    gp = o.apply_J_phase(q, cpx, rho, phi, psi, mask, ref.Z, ref.nPhase, Nz, P["dz"], single=single, z0=z0, workers=w)
+    gd = o.apply_J_defocus(q, cpx, rho, phi, psi, mask, Nz, P["dz"], P["dxy"], ref.lambda_ni, ref.deltaX, ref.deltaY,
+                           single=single, z0=z0, workers=w)
+    gm = o.apply_J_modulus(q, cpx, rho, phi, psi, mask, ref.Z, ref.beta, Nz, P["dz"], single=single, z0=z0, workers=w)
+    return cpx, psf, gd, gp, gm
+
+
+@pytest.mark.parametrize("N,Nz,z0,nzl,single", [
+    (512, 256, 0, 256, False),        # BASELINE config 3 / the headline shape: all 256 planes
+    (256, 128, 0, 128, False),        # BASELINE config 2
+    (1024, 512, 448, 64, False),      # BASELINE config 4: the last GPU's slab of the 1024^2 x 512 stack
+    (512, 256, 64, 96, True),         # optional fp32 mode, a slab that straddles the z wrap (Nz/2 = 128)
+])
+def test_full_stack_parity_at_baseline_shapes(lib, N, Nz, z0, nzl, single):
+    full_stack_case(lib, N, Nz, z0, nzl, single)
+
+
+def full_stack_case(lib, N, Nz, z0, nzl, single):
+    ref = o.WideFieldModelOracle((N, N, 2), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], single=single)
+    m = WideFieldModel((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, single, lib=lib,
+                       basis=lambda nz: ref.Z[:nz], z0=z0, nz_local=nzl)
+    alpha = o.synthetic_alpha(10)
+    for mm in (ref, m):
+        mm.setPhase(alpha)
+        mm.setModulus(BETA4)
+    q = o.synthetic_q(N, N, Nz, z0=z0, nz_local=nzl, single=single)
+    cpx, psf, gd, gp, gm = _oracle_stack(ref, Nz, z0, nzl, q, single)
+    t = tol(single)
+    tj = 20 * t if single else t
+    got_psf, got_cpx = m.getPsf(), m.get_cpxPsf()
+    assert o.rel_l2(got_psf, psf) <= t
+    assert o.rel_l2(got_cpx, cpx) <= t
+    worst = max(o.rel_l2(got_psf[l], psf[l]) for l in range(nzl))          # no single plane may hide in the norm
+    assert worst <= t, f"worst plane {worst:.2e}"
+    worst = max(o.rel_l2(got_cpx[l], cpx[l]) for l in range(nzl))
+    assert worst <= t, f"worst cpx plane {worst:.2e}"
+    d, p, mo = m.apply_J_all(q)
+    assert o.rel_l2(d, gd) <= tj and o.rel_l2(p, gp) <= tj and o.rel_l2(mo, gm) <= tj
+    assert o.rel_l2(m.apply_J_phase(q).data, gp) <= tj                    # the single-Jacobian launch (kinds = 2)
+    # a q that is non-zero on one late plane only: an error in that plane's ring slot cannot average out
+    for l in sorted({nzl - 1, nzl // 2 + 1, min(nzl - 1, 47)}):
+        q1 = np.zeros_like(q)
+        q1[l] = q[l]
+        want = o.apply_J_phase(q1[l:l + 1], cpx[l:l + 1], ref.rho, ref.phi, ref.psi, ref.maskPupil, ref.Z, 10, Nz,
+                               P["dz"], single=single, z0=z0 + l)
+        assert o.rel_l2(m.apply_J_phase(q1).data, want) <= tj, f"plane {l}"
+    m.close()
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_config5_batch_of_eight_256x256x64(lib, single):
+    """BASELINE config 5 at its own plane count: 8 of the 64 models (512 planes through one pipeline launch pair)."""
+    from tests.test_emu_parity import _batch_case
+    N, Nz, B = 256, 64, 8
+    m, refs = _batch_case(lib, N, Nz, B, single)
+    t = tol(single)
+    tj = 20 * t if single else t
+    psf, cpx = m.getPsf(), m.get_cpxPsf()
+    q = np.stack([o.synthetic_q(N, N, Nz, seed=42 + b, single=single) for b in range(B)])
+    d, p, mo = m.applyJacobianBatch(q)
+    for b, r in enumerate(refs):
+        assert o.rel_l2(psf[b], r.getPsf()) <= t
+        assert o.rel_l2(cpx[b], r.get_cpxPsf()) <= t
+        assert o.rel_l2(d[b], r.apply_J_defocus(q[b])) <= tj
+        assert o.rel_l2(p[b], r.apply_J_phase(q[b])) <= tj
+        assert o.rel_l2(mo[b], r.apply_J_modulus(q[b])) <= tj
+    m.close()
+
+
+def test_escape_hatch_identical_pupils_on_the_gpu(lib):
+    """wfm_set_pupil_arrays (SURVEY 8 b3 "identical synthetic pupils"): arbitrary rho / phi / psi / mask -- not the
+    output of any setter, support wider than the optical mask -- through the generic and the narrow kernels."""
+    escape_hatch_case(lib, ((128, 40, 0.2), (256, 24, 0.4)))         # 0.2 N < N/4: narrow kernels; 0.4 N: generic
+
+
+def escape_hatch_case(lib, cases):
+    for N, Nz, rad in cases:
+        rng = np.random.default_rng(N)
+        ky, kx = np.meshgrid(o.kappa(N), o.kappa(N), indexing="ij")
+        disk = (kx * kx + ky * ky) < (rad * N) ** 2
+        rho = np.where(disk, rng.uniform(0.2, 1.0, (N, N)), 0.0)
+        rho /= np.sqrt(np.sum(rho * rho))
+        phi = np.where(disk, rng.normal(0.0, 1.0, (N, N)), 0.0)
+        psi = np.where(disk, rng.uniform(1e6, 3e6, (N, N)), 0.0)
+        mask = disk & (rng.random((N, N)) > 0.05)                     # a few support pixels are off the mask
+        ref = o.WideFieldModelOracle((N, N, 2), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"])
+        m = WideFieldModel((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, False, lib=lib,
+                           basis=lambda nz: ref.Z[:nz])
+        m.setPupilArrays(rho, phi, psi, mask)
+        ref.rho, ref.phi, ref.psi, ref.maskPupil = rho, phi, psi, mask
+        ref.nPhase = 10
+        ref.beta = np.array([1.0, 0.0, 0.0, 0.0])                     # what the constructor left on the handle
+        q = o.synthetic_q(N, N, Nz)
+        cpx, psf, gd, gp, gm = _oracle_stack(ref, Nz, 0, Nz, q)
+        np.testing.assert_array_equal(m.getRho(), rho.ravel())
+        np.testing.assert_array_equal(m.getMaskPupil(), mask.ravel())
+        assert o.rel_l2(m.getPsf(), psf) <= 1e-12
+        assert o.rel_l2(m.get_cpxPsf(), cpx) <= 1e-12
+        d, p, mo = m.apply_J_all(q)
+        assert o.rel_l2(d, gd) <= 1e-12 and o.rel_l2(p, gp) <= 1e-12 and o.rel_l2(mo, gm) <= 1e-12
+        m.close()
+
+
+def test_handle_on_a_fresh_thread_keeps_its_device(lib):
+    """Every ABI entry point makes the handle's device current itself (a new host thread starts on device 0) and
+    hands the caller's device back."""
+    import threading
+    import torch
+    dev = torch.cuda.device_count() - 1                               # device 1 when the box has more than one GPU
+    ref, m = make_pair(64, 8, lib, device=dev)
+    q = o.synthetic_q(64, 64, 8)
+    out = {}
+
+    def worker():
+        out["before"] = torch.cuda.current_device()
+        out["psf"] = m.getPsf()
+        out["g"] = m.apply_J_phase(q).data
+        out["after"] = torch.cuda.current_device()
+    torch.cuda.set_device(0)
+    th = threading.Thread(target=worker)
+    th.start(); th.join()
+    assert out["before"] == out["after"] == 0
+    assert o.rel_l2(out["psf"], ref.getPsf()) <= 1e-12
+    assert o.rel_l2(out["g"], ref.apply_J_phase(q)) <= 1e-12
+    m.close()

@@ -6,7 +6,7 @@ for spec in "$@"; do
   name="${spec%%:*}"; rest="${spec#*:}"; flags="${rest%%:*}"; envs=""
   if [[ "$rest" == *:* ]]; then envs="${rest#*:}"; fi
   WFM_BUILD_FLAGS="-DWFM_ONLY_N=${BENCH_N:-512} $flags" python -c "import __graft_entry__ as g; g.build_library(force=True)" > gpurun_out/build_$name.log 2>&1 || { echo "$name: build failed"; tail -5 gpurun_out/build_$name.log; continue; }
-  env $envs timeout 300 python bench.py --nxy ${BENCH_N:-512} --nz ${BENCH_NZ:-256} ${BENCH_EXTRA:-} --steps 50 --warmup 5 --no-cpu-baseline --no-eval-fg --e2e-steps 1 > gpurun_out/bench_$name.log 2>&1
+  env $envs timeout 300 python bench.py --nxy ${BENCH_N:-512} --nz ${BENCH_NZ:-256} ${BENCH_EXTRA:-} --steps 50 --warmup 5 --quick --no-cpu-baseline --no-eval-fg --e2e-steps 1 > gpurun_out/bench_$name.log 2>&1
   python - "$name" <<'PY'
 import json,sys
 name=sys.argv[1]
