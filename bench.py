@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--sustain", type=float, default=2.5, help="seconds of the sustained-roofline loop (0 = skip)")
     ap.add_argument("--no-others", dest="others", action="store_false", help="skip the extra lines of configs 2, 4, 5")
     ap.add_argument("--quick", action="store_true", help="headline numbers only (variant A/B runs)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: how the K-vector is summed over the ranks (peer = inside k_jac_final over CUDA-IPC "
+                         "peer memory; nccl = one all-reduce per step; auto = peer if every rank can map its peers)")
     ap.add_argument("--single", action="store_true", help="optional fp32 mode (not the headline)")
     ap.add_argument("--kinds", type=int, default=2, help="Jacobian bits: 1 defocus, 2 phase, 4 modulus")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
@@ -243,8 +246,8 @@ def describe_config(cfg_id, n, planes_local, planes_global, single, kinds, world
                         f"{planes_local} {'fp32' if single else 'fp64'} planes on each GPU ({planes_global} planes total)",
             "baseline_config": cfg_id, "nphase": 10, "nmodulus": nmod, "NA": 1.4, "jacobian_kinds": kinds,
             "l2_policy": f"inputs larger than L2 ({alg_step / 1e9:.2f} GB streamed per step vs 126 MB L2)",
-            "parallelism": (f"z-slab x{world}, NCCL allreduce of {L} doubles per step" if not models
-                            else f"models split by index x{world}, no collective") if world > 1 else "single GPU"}
+            "parallelism": (f"z-slab x{world}, the K-vector of {L} doubles is summed over the ranks once per step"
+                            if not models else f"models split by index x{world}, no collective") if world > 1 else "single GPU"}
 
 
 def resolve_shape(args, world):
@@ -295,7 +298,15 @@ class Workload:
         self.grad = torch.zeros(self.L * max(models, 1), dtype=torch.float64, device=dev)
         self.x = None if models else self.m.parameterCoefs[self.m.PHASE]      # PSF_Estimation.java:117
         self.reduce = (world > 1 and not models)
-        self.exchange = exchange
+        self.exchange = "none"
+        if self.reduce:
+            from microtipi_b200.sharded import connect_peer_exchange
+            self.exchange = "nccl"
+            if exchange in ("peer", "auto"):
+                if connect_peer_exchange(self.m, dist):
+                    self.exchange = "peer"                                        # k_jac_final sums over the ranks itself
+                elif exchange == "peer":
+                    raise SystemExit("bench.py: --exchange peer could not be set up on every rank")
 
     def step(self, i, kinds=None):
         m = self.m
@@ -306,13 +317,18 @@ class Workload:
             m.setParam(self.x)                                                # PSF_Estimation.java:202 -> setPhase -> freeMem()
         m.computePsf()
         m.applyJacobianDevice(self.kinds if kinds is None else kinds, self.q.data_ptr(), self.grad.data_ptr())
-        if self.reduce:
+        if self.reduce and self.exchange == "nccl":
             self.dist.all_reduce(self.grad)                                   # NCCL sum of the K-vector
 
     def alg_bytes_per_step(self):
         return 6 * self.es * self.n * self.n * self.planes_local              # SURVEY 8 d3, per GPU
 
     def close(self):
+        if self.exchange == "peer":
+            self.m.synchronize()
+            self.dist.barrier()                                               # nobody unmaps while a peer may still store
+            self.m.exchangeStatus()
+            self.m.exchangeClose()
         self.m.close()
         del self.q, self.grad
 
@@ -366,14 +382,15 @@ def run_b200(args):
             cfg["nz"] = nz
         if cfg_id == 5:
             b0, nb = slab_bounds(cfg["models"], world, rank)
-            w = Workload(torch, dist, local, world, rank, cfg["n"], cfg["nz"], b0, cfg["nz"], single, kinds, stream, models=nb)
+            w = Workload(torch, dist, local, world, rank, cfg["n"], cfg["nz"], b0, cfg["nz"], single, kinds, stream, models=nb,
+                         exchange=args.exchange)
             return w, cfg["models"] * cfg["nz"], cfg
         if cfg["mode"] == "weak":
             nzg = cfg["nz"] * world
         else:
             nzg = cfg["nz"]
         z0, nzl = slab_bounds(nzg, world, rank)
-        w = Workload(torch, dist, local, world, rank, cfg["n"], nzg, z0, nzl, single, kinds, stream)
+        w = Workload(torch, dist, local, world, rank, cfg["n"], nzg, z0, nzl, single, kinds, stream, exchange=args.exchange)
         return w, nzg, cfg
 
     def timed(w, steps, warmup, kinds=None):
@@ -390,7 +407,7 @@ def run_b200(args):
         return max_over_ranks(e0.elapsed_time(e1))
 
     # ---- parity before timing: a small sharded run against the oracle (checker only), on every rank ----------
-    parity = None if args.quick else check_parity(torch, dist, local, world, rank, stream)
+    parity = None if args.quick else check_parity(torch, dist, local, world, rank, stream, args.exchange)
 
     cfg_id = args.config
     single = args.single
@@ -472,7 +489,7 @@ def run_b200(args):
     per = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in ktimes.items()}
     alg_step = w.alg_bytes_per_step()
     main_close = w.close
-    main = dict(N=N, nzl=nzl, nzg=nzg, planes_local=w.planes_local, L=w.L, models=w.models)
+    main = dict(N=N, nzl=nzl, nzg=nzg, planes_local=w.planes_local, L=w.L, models=w.models, exchange=w.exchange)
     main_close()
 
     # ---- the other BASELINE configs, a few steps each, as extra keys of the same line ------------------------------
@@ -525,6 +542,8 @@ def run_b200(args):
             "dtype": "f32" if single else "f64", "data": "synthetic",
             "config": describe_config(cfg_id, main["N"], main["planes_local"], planes_global, single, args.kinds, world,
                                       main["models"]),
+            "exchange": {"none": None, "peer": "inside k_jac_final over NVLink peer memory (CUDA IPC landing buffers, flags, fixed "
+                                               "rank order)", "nccl": "one NCCL all-reduce per step"}[main["exchange"]],
             "clocks": clocks,
             "ms_per_step_distribution": dist_ms,
             "e2e": e2e,
@@ -572,7 +591,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def check_parity(torch, dist, local, world, rank, stream):
+def check_parity(torch, dist, local, world, rank, stream, exchange="auto"):
     """128 x 128 x (2*world + 1) planes, sharded like the timed run (ragged slabs), against the oracle: the PSF slab
     of every rank, and the three gradients after the same exchange the timed step uses.  rel-L2, asserted <= 1e-12."""
     import numpy as np
@@ -582,7 +601,7 @@ def check_parity(torch, dist, local, world, rank, stream):
     P = o.DEFAULTS
     ref = o.WideFieldModelOracle((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"])
     m = ShardedWideFieldModel((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], device=local,
-                              basis=lambda nz: ref.Z[:nz])
+                              basis=lambda nz: ref.Z[:nz], exchange=exchange if world > 1 else "nccl")
     alpha, beta = o.synthetic_alpha(10), [1.0, 0.1, -0.05, 0.02]
     for mm in (ref, m):
         mm.setPhase(alpha)
@@ -599,6 +618,7 @@ def check_parity(torch, dist, local, world, rank, stream):
     want = np.concatenate([ref.apply_J_defocus(qf), ref.apply_J_phase(qf), ref.apply_J_modulus(qf)])
     errs = {"psf_slab": o.rel_l2(m.getPsf(), ref.getPsf()[z0:z0 + nzl]), "grad_defocus": o.rel_l2(g[:3], want[:3]),
             "grad_phase": o.rel_l2(g[3:13], want[3:13]), "grad_modulus": o.rel_l2(g[13:], want[13:])}
+    used_exchange = m.exchange
     m.close()
     worst = max(errs.values())
     if world > 1:
@@ -606,7 +626,7 @@ def check_parity(torch, dist, local, world, rank, stream):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         worst = float(t.item())
     assert worst <= 1e-12, f"rank {rank}: sharded parity failure {errs}"
-    return {"shape": f"{N}x{N}x{Nz} over {world} rank(s)", "rel_l2_rank0": {k: float(f"{v:.3e}") for k, v in errs.items()},
+    return {"shape": f"{N}x{N}x{Nz} over {world} rank(s)", "exchange": used_exchange, "rel_l2_rank0": {k: float(f"{v:.3e}") for k, v in errs.items()},
             "worst_over_ranks": float(f"{worst:.3e}"), "tolerance": 1e-12, "checker": "oracle/wfm_oracle.py"}
 
 

@@ -101,6 +101,40 @@ WFM_API int wfm_create_batch(wfm_model** out, int nx, int ny, int nz, int nbatch
                              int precision, int device);
 WFM_API int wfm_batch_size(const wfm_model* h);
 
+/* The whole stack over n_dev GPUs of one box, driven by ONE host thread like the reference's callers
+ * (PSF_Estimation.java:202-217): contiguous z-slabs, one per device (the first nz % n_dev devices hold one extra
+ * plane).  The handle answers every entry point of a plain one with the reference layouts: setters are
+ * broadcast, wfm_get_psf / wfm_get_cpx_psf copy every slab from its device straight to its offset of the caller's
+ * array (one PCIe link per device, in parallel), wfm_apply_j_* split q the same way and add the per-device partial
+ * vectors in device order.  Not available: wfm_set_stream, the rolled PSF / MTF / wfm_eval_fg (they cross slabs), the
+ * batch calls; device-resident entry points go through the children (wfm_multi_part). */
+WFM_API int wfm_create_multi(wfm_model** out, int nx, int ny, int nz, double dxy, double dz, int precision,
+                             const int* devices, int n_dev);
+WFM_API int wfm_multi_parts(const wfm_model* h);                 /* devices of a multi handle, 0 for a plain handle */
+WFM_API int wfm_multi_part_info(const wfm_model* h, int part, int* device, int* z0, int* nz_local);
+/* Borrowed child handle of one device, for device-resident use (wfm_device_psf, wfm_fill_uniform, wfm_synchronize).
+ * It belongs to the parent: never destroy it and never call its setters. */
+WFM_API int wfm_multi_part(wfm_model* h, int part, wfm_model** child);
+/* Device-resident Jacobians of a multi handle.  q_dev[i]: part i's slab of q on device i.  grad_dev: 3 + nPhase +
+ * nModulus doubles on the FIRST device, summed over the devices in device order: every device's k_jac_final stores its
+ * partial vector into a slot on the first device over NVLink (peer mapping) and the first device adds the slots once
+ * the others' events have fired -- no host round trip, no NCCL.  Asynchronous (first device's stream). */
+WFM_API int wfm_multi_apply_jacobian_dev(wfm_model* h, unsigned kinds, const void* const* q_dev, double* grad_dev);
+
+/* One process per GPU (torchrun): the same sum across PROCESSES, through CUDA IPC peer memory instead of an NCCL
+ * all-reduce of ~14 doubles.  Every rank: wfm_exchange_export (allocates its landing buffer, returns the 64-byte IPC
+ * handle) -> all-gather the handles by any means -> wfm_exchange_connect(rank, world, handles[world][64]).  From then
+ * on wfm_apply_jacobian_dev leaves the sum over ALL ranks in grad_dev on every rank (fixed rank order: identical
+ * bits everywhere): k_jac_final stores the partial vector into every peer's buffer over NVLink, raises a flag per
+ * peer and adds the slots when the world's flags have arrived.  It is a collective: every rank issues the same
+ * sequence of Jacobian calls.  wfm_exchange_status: 1 = connected and healthy, 0 = not connected, < 0 = a peer's
+ * flag did not arrive (time-out, never a hang).  Close every rank's exchange before destroying the handles. */
+#define WFM_EXCHANGE_HANDLE_BYTES 64
+WFM_API int wfm_exchange_export(wfm_model* h, int world, void* handle_out);
+WFM_API int wfm_exchange_connect(wfm_model* h, int rank, int world, const void* handles);
+WFM_API int wfm_exchange_status(wfm_model* h);
+WFM_API int wfm_exchange_close(wfm_model* h);
+
 WFM_API int wfm_destroy(wfm_model* h);
 
 /* Text of the last error on this handle (or of the last failed wfm_create* when h == NULL). */

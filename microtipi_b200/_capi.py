@@ -23,6 +23,7 @@ WFM_F64, WFM_F32 = 0, 1
 WFM_DEFOCUS, WFM_PHASE, WFM_MODULUS = 0, 1, 2
 WFM_J_DEFOCUS, WFM_J_PHASE, WFM_J_MODULUS = 1, 2, 4
 WFM_MODULUS_INTENDED, WFM_MODULUS_REFERENCE_LAST_PLANE = 0, 1
+WFM_EXCHANGE_HANDLE_BYTES = 64
 KERNEL_NAMES = ["psf_pipeline", "jac_pipeline", "jac_reduce", "setters"]
 
 _vp = C.c_void_p
@@ -40,6 +41,15 @@ SIGNATURES = {
     "wfm_batch_set_modulus": (C.c_int, [_vp, _vp, C.c_int]),
     "wfm_batch_set_defocus": (C.c_int, [_vp, _vp, C.c_int]),
     "wfm_batch_apply_jacobian": (C.c_int, [_vp, C.c_uint, _vp, _vp]),
+    "wfm_create_multi": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _ip, C.c_int]),
+    "wfm_multi_parts": (C.c_int, [_vp]),
+    "wfm_multi_part_info": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip]),
+    "wfm_multi_part": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "wfm_multi_apply_jacobian_dev": (C.c_int, [_vp, C.c_uint, C.POINTER(_vp), _vp]),
+    "wfm_exchange_export": (C.c_int, [_vp, C.c_int, _vp]),
+    "wfm_exchange_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "wfm_exchange_status": (C.c_int, [_vp]),
+    "wfm_exchange_close": (C.c_int, [_vp]),
     "wfm_destroy": (C.c_int, [_vp]),
     "wfm_last_error": (C.c_char_p, [_vp]),
     "wfm_set_stream": (C.c_int, [_vp, _vp]),

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <string>
 #include <vector>
@@ -97,6 +98,17 @@ struct wfm_model {
     double k_ms[WFM_KERNEL_IDS] = {0};
     uint64_t k_count[WFM_KERNEL_IDS] = {0};
 
+    // multi-device handle (wfm_create_multi): one z-slab child per device, this object holds no device memory of its
+    // own except the landing buffer of the partial gradient vectors on the first device
+    std::vector<wfm_model*> parts;
+    std::vector<int> part_z0;                     // first plane of each child inside the stack
+    DevBuf xslots;                                // [n_dev][glen] doubles on parts[0]'s device, written by the peers
+    std::vector<int> peer_direct;                 // child i can store into xslots over NVLink (peer access enabled)
+    std::vector<cudaEvent_t> part_done;           // one event per child: its Jacobian chain has been queued
+    // cross-process gradient exchange over CUDA IPC peer memory (wfm_exchange_*): see wfm_multi.inl
+    struct Exchange* xchg = nullptr;
+    bool multi() const { return !parts.empty(); }
+
     int npix() const { return N * N; }
     size_t esz() const { return precision == WFM_F64 ? 8 : 4; }
     int glen() const { return 3 + nphase + nmod; }
@@ -139,6 +151,17 @@ struct DeviceScope {
 #define WFM_ENTER(h)                                                                             \
     DeviceScope dev_scope__((h)->device);                                                        \
     if (!dev_scope__.ok) return (h)->fail(WFM_ERR_CUDA, "cudaSetDevice(%d) failed", (h)->device)
+
+// Cross-process gradient exchange state (one process per GPU; wfm_exchange_export / _connect, wfm_multi.inl).
+struct Exchange {
+    int rank = -1, world = 0, glen_cap = 0;
+    void* base = nullptr;                    // this rank's landing buffer (cudaMalloc): slots, then flags
+    size_t slot_bytes = 0;
+    std::vector<void*> mapped;               // every rank's buffer as mapped into this process (own = base)
+    DevBuf local;                            // ticket + err words
+    unsigned epoch = 0;
+    bool connected = false;
+};
 
 namespace {
 
@@ -441,10 +464,23 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
             for (int k = 0; k < h->nmod; ++k) s += h->beta.v[k] * h->beta.v[k];
             nbeta = 1.0 / std::sqrt(s);                                        // WFM:435
         }
+        XchgArgs xc;
+        memset(&xc, 0, sizeof(xc));
+        if (h->xchg && h->xchg->connected) {                 // sum over the ranks inside k_jac_final (peer memory)
+            Exchange* x = h->xchg;
+            if (batch) return h->fail(WFM_ERR_UNSUPPORTED, "the peer-memory gradient exchange needs a single-model handle");
+            if (r.glen > x->glen_cap) return h->fail(WFM_ERR_STATE, "gradient vector longer than the exchange buffer: reconnect");
+            xc.world = x->world; xc.rank = x->rank; xc.epoch = ++x->epoch;
+            for (int k = 0; k < x->world; ++k) {
+                xc.slots[k] = (double*)x->mapped[k];
+                xc.flags[k] = (unsigned*)((char*)x->mapped[k] + x->slot_bytes);
+            }
+            xc.ticket = (unsigned*)x->local.p; xc.err = (unsigned*)x->local.p + 1;
+        }
         auto kfin = &k_jac_final;
         WFM_LAUNCH_PDL(kfin, dim3(r.glen, h->nbatch), dim3(WFM_FINAL_THREADS), 0, h->stream, (const double*)r.block_part,
                    nblocks * r.cpm, r.glen, h->nphase, a.g.psf_norm, h->beta, nbeta, kinds,
-                   batch ? (const double*)h->beta_dev.p : (const double*)nullptr, h->nmod, r.bpar, grad_dev);
+                   batch ? (const double*)h->beta_dev.p : (const double*)nullptr, h->nmod, r.bpar, grad_dev, xc);
         WFM_CK_LAUNCH(h, "k_jac_final");
     }
     return WFM_OK;
@@ -595,6 +631,28 @@ int batch_set_defocus(wfm_model* h, const double* tab, int n, int stride) {
 
 }  // namespace
 
+// ---- multi-device handles (wfm_create_multi; bodies in wfm_multi.inl) ------------------------------------
+namespace wfm_multi {
+int destroy(wfm_model* h);
+int broadcast(wfm_model* h, const std::function<int(wfm_model*)>& fn);
+int sync_meta(wfm_model* h);
+int compute_psf(wfm_model* h);
+int get_stack(wfm_model* h, void* out, bool cpx, bool async);
+int wait_transfers(wfm_model* h);
+int apply_host(wfm_model* h, unsigned kinds, const void* q_host, std::vector<double>& g);
+int synchronize(wfm_model* h);
+int kernel_times(wfm_model* h, double* ms, uint64_t* counts);
+int unsupported(wfm_model* h, const char* what);
+}  // namespace wfm_multi
+#define WFM_MULTI_BCAST(h, call)                                                        \
+    do { if ((h)->multi()) {                                                            \
+        int rc__ = wfm_multi::broadcast((h), [&](wfm_model* c) { return (call); });     \
+        return rc__ ? rc__ : wfm_multi::sync_meta(h); } } while (0)
+#define WFM_MULTI_FIRST(h, call)                                                        \
+    do { if ((h)->multi()) { wfm_model* c = (h)->parts[0]; int rc__ = (call);           \
+        if (rc__) (h)->err = c->err; return rc__; } } while (0)
+#define WFM_MULTI_NO(h, what) do { if ((h)->multi()) return wfm_multi::unsupported((h), what); } while (0)
+
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
@@ -670,6 +728,8 @@ int wfm_create(wfm_model** out, int nx, int ny, int nz, double dxy, double dz, i
 
 int wfm_destroy(wfm_model* h) {
     if (!h) return WFM_OK;
+    if (h->multi()) return wfm_multi::destroy(h);
+    wfm_exchange_close(h);
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->Z, &h->rho, &h->phi, &h->psi, &h->mask, &h->map, &h->support, &h->act_x, &h->inv_x,
@@ -691,6 +751,7 @@ const char* wfm_last_error(const wfm_model* h) { return h ? h->err.c_str() : g_c
 
 int wfm_set_stream(wfm_model* h, void* s) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "wfm_set_stream (every device of a multi handle runs its own stream)");
     WFM_ENTER(h);
     cudaStreamSynchronize(h->stream);
     h->stream = s ? (cudaStream_t)s : h->own_stream;
@@ -707,17 +768,20 @@ static int order_streams(wfm_model* h, cudaStream_t first, cudaStream_t then) {
 }
 int wfm_wait_stream(wfm_model* h, void* s) {          // the handle's stream waits for what `s` holds so far
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "wfm_wait_stream");
     WFM_ENTER(h);
     return order_streams(h, (cudaStream_t)s, h->stream);
 }
 int wfm_fence_stream(wfm_model* h, void* s) {         // `s` waits for what the handle's stream holds so far
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "wfm_fence_stream");
     WFM_ENTER(h);
     return order_streams(h, h->stream, (cudaStream_t)s);
 }
 
 int wfm_synchronize(wfm_model* h) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->multi()) return wfm_multi::synchronize(h);
     WFM_ENTER(h);
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     return check_pipeline(h);
@@ -725,6 +789,7 @@ int wfm_synchronize(wfm_model* h) {
 
 int wfm_set_optics(wfm_model* h, double NA, double lambda, double ni) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_optics(c, NA, lambda, ni));
     if (!(NA > 0) || !(lambda > 0) || !(ni > 0)) return h->fail(WFM_ERR_INVALID_ARG, "NA, lambda and ni must be positive");
     WFM_ENTER(h);
     h->NA = NA; h->lambda = lambda; h->ni = ni;
@@ -748,6 +813,7 @@ int wfm_set_optics(wfm_model* h, double NA, double lambda, double ni) {
 
 int wfm_set_basis(wfm_model* h, const double* Z, int nzern, int radial) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_basis(c, Z, nzern, radial));
     if (!Z || nzern <= 0) return h->fail(WFM_ERR_INVALID_ARG, "Z is NULL or nzern <= 0");
     WFM_ENTER(h);
     const size_t npix = h->npix();
@@ -767,6 +833,7 @@ int wfm_set_basis(wfm_model* h, const double* Z, int nzern, int radial) {
 // computeZernike() WFM:194-197 on the device.
 int wfm_build_basis(wfm_model* h, int nzern, int radial) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_build_basis(c, nzern, radial));
     if (nzern <= 0) return h->fail(WFM_ERR_INVALID_ARG, "nzern <= 0");
     if (!h->have_optics) return h->fail(WFM_ERR_STATE, "optics not set: call wfm_set_optics first");
     WFM_ENTER(h);
@@ -851,6 +918,7 @@ int wfm_build_basis(wfm_model* h, int nzern, int radial) {
 
 int wfm_get_basis(wfm_model* h, double* out, int nzern) {
     if (!h || !out) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_FIRST(h, wfm_get_basis(c, out, nzern));
     WFM_ENTER(h);
     if (nzern <= 0 || nzern > h->nzern) return h->fail(WFM_ERR_INVALID_ARG, "nzern out of range");
     WFM_CK(h, cudaStreamSynchronize(h->stream));
@@ -860,6 +928,7 @@ int wfm_get_basis(wfm_model* h, double* out, int nzern) {
 
 int wfm_set_phase(wfm_model* h, const double* alpha, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_phase(c, alpha, n));
     if (h->nbatch > 1) return batch_set_phase(h, alpha, n, 0);     // batch handle: the same vector for every model
     if (n < 0 || n > WFM_MAX_COEF || (n > 0 && !alpha)) return h->fail(WFM_ERR_INVALID_ARG, "bad phase coefficient vector");
     const int off = h->radial ? 1 : 3;
@@ -879,6 +948,7 @@ int wfm_set_phase(wfm_model* h, const double* alpha, int n) {
 
 int wfm_set_modulus(wfm_model* h, const double* beta, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_modulus(c, beta, n));
     if (h->nbatch > 1) return batch_set_modulus(h, beta, n, 0);
     if (n <= 0 || n > WFM_MAX_COEF || !beta) return h->fail(WFM_ERR_INVALID_ARG, "bad modulus coefficient vector");
     if (h->nzern <= 0) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
@@ -899,6 +969,7 @@ int wfm_set_modulus(wfm_model* h, const double* beta, int n) {
 
 int wfm_set_defocus(wfm_model* h, const double* defoc, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_defocus(c, defoc, n));
     if (h->nbatch > 1) return batch_set_defocus(h, defoc, n, 0);
     if (!defoc || (n != 1 && n != 3)) return h->fail(WFM_ERR_INVALID_ARG, "bad defocus  parameters");   // WFM:1530, Q4
     if (!h->have_optics) return h->fail(WFM_ERR_STATE, "optics not set: call wfm_set_optics first");
@@ -917,22 +988,26 @@ int wfm_set_defocus(wfm_model* h, const double* defoc, int n) {
 // Batch handles: one table row per model.
 int wfm_batch_set_phase(wfm_model* h, const double* alpha, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_phase(c, alpha, n));
     if (h->nbatch <= 1) return wfm_set_phase(h, alpha, n);
     return batch_set_phase(h, alpha, n, n);
 }
 int wfm_batch_set_modulus(wfm_model* h, const double* beta, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_modulus(c, beta, n));
     if (h->nbatch <= 1) return wfm_set_modulus(h, beta, n);
     return batch_set_modulus(h, beta, n, n);
 }
 int wfm_batch_set_defocus(wfm_model* h, const double* defoc, int n) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_defocus(c, defoc, n));
     if (h->nbatch <= 1) return wfm_set_defocus(h, defoc, n);
     return batch_set_defocus(h, defoc, n, n);
 }
 
 int wfm_set_pupil_arrays(wfm_model* h, const double* rho, const double* phi, const double* psi, const uint8_t* mask) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_pupil_arrays(c, rho, phi, psi, mask));
     if (h->nbatch > 1) return h->fail(WFM_ERR_UNSUPPORTED, "wfm_set_pupil_arrays: not available on a batch handle");
     WFM_ENTER(h);
     const size_t npix = h->npix();
@@ -956,6 +1031,7 @@ int wfm_set_pupil_arrays(wfm_model* h, const double* rho, const double* phi, con
 
 int wfm_set_modulus_mode(wfm_model* h, int mode) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_modulus_mode(c, mode));
     if (mode != WFM_MODULUS_INTENDED && mode != WFM_MODULUS_REFERENCE_LAST_PLANE)
         return h->fail(WFM_ERR_INVALID_ARG, "bad modulus mode");
     h->modulus_mode = mode;
@@ -971,21 +1047,32 @@ static int copy_out(wfm_model* h, void* out, const void* dev, size_t bytes) {
 }
 
 // (batch handles: nbatch arrays, model after model)
-int wfm_get_rho(wfm_model* h, double* out) { return h ? copy_out(h, out, h->rho.p, 8 * (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
-int wfm_get_phi(wfm_model* h, double* out) { return h ? copy_out(h, out, h->phi.p, 8 * (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
-int wfm_get_psi(wfm_model* h, double* out) { return h ? copy_out(h, out, h->psi.p, 8 * (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
-int wfm_get_mask(wfm_model* h, uint8_t* out) { return h ? copy_out(h, out, h->mask.p, (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
+int wfm_get_rho(wfm_model* h, double* out) { if (h && h->multi()) h = h->parts[0]; return h ? copy_out(h, out, h->rho.p, 8 * (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
+int wfm_get_phi(wfm_model* h, double* out) { if (h && h->multi()) h = h->parts[0]; return h ? copy_out(h, out, h->phi.p, 8 * (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
+int wfm_get_psi(wfm_model* h, double* out) { if (h && h->multi()) h = h->parts[0]; return h ? copy_out(h, out, h->psi.p, 8 * (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
+int wfm_get_mask(wfm_model* h, uint8_t* out) { if (h && h->multi()) h = h->parts[0]; return h ? copy_out(h, out, h->mask.p, (size_t)h->npix() * h->nbatch) : WFM_ERR_INVALID_ARG; }
 
 int wfm_compute_psf(wfm_model* h) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->multi()) return wfm_multi::compute_psf(h);
     WFM_ENTER(h);
     return compute_psf_impl(h);
 }
-int wfm_invalidate(wfm_model* h) { return h ? invalidate(h) : WFM_ERR_INVALID_ARG; }
-int wfm_psf_state(const wfm_model* h) { return h ? h->pstate : 0; }
+int wfm_invalidate(wfm_model* h) {
+    if (!h) return WFM_ERR_INVALID_ARG;
+    for (wfm_model* c : h->parts) invalidate(c);
+    return invalidate(h);
+}
+int wfm_psf_state(const wfm_model* h) {
+    if (!h) return 0;
+    if (!h->multi()) return h->pstate;
+    for (const wfm_model* c : h->parts) if (c->pstate < 1) return 0;
+    return 1;
+}
 
 int wfm_get_psf(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->multi()) return wfm_multi::get_stack(h, out, false, false);
     WFM_ENTER(h);
     int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1800-1802
     return copy_out(h, out, h->psf.p, (size_t)h->npix() * h->nzl * h->esz());
@@ -996,6 +1083,7 @@ int wfm_get_psf(wfm_model* h, void* out) {
 // computePsf() on this handle is ordered after the copy, so the slab is never overwritten while it is read.
 int wfm_get_psf_async(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->multi()) return wfm_multi::get_stack(h, out, false, true);
     WFM_ENTER(h);
     if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
     int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1800-1802
@@ -1014,6 +1102,7 @@ int wfm_get_psf_async(wfm_model* h, void* out) {
 
 int wfm_wait_transfers(wfm_model* h) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->multi()) return wfm_multi::wait_transfers(h);
     WFM_ENTER(h);
     if (h->copy_stream) WFM_CK(h, cudaStreamSynchronize(h->copy_stream));
     h->copy_pending = false;
@@ -1023,6 +1112,7 @@ int wfm_wait_transfers(wfm_model* h) {
 // ArrayUtils.roll(pupil.getPsf()) (BlindDeconvJob.java:100) -- "next" row f4: the centred PSF, shifted on the device.
 int wfm_roll_psf_dev(wfm_model* h, void* out_dev) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "the rolled PSF (the z roll crosses devices)");
     WFM_ENTER(h);
     if (!out_dev) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
     if (h->z0 != 0 || h->nzl != h->nz_global)
@@ -1043,6 +1133,7 @@ int wfm_roll_psf_dev(wfm_model* h, void* out_dev) {
 
 int wfm_get_psf_rolled(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "the rolled PSF (the z roll crosses devices)");
     if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
     WFM_ENTER(h);
     const size_t bytes = (size_t)h->npix() * h->nzl * h->esz();
@@ -1053,6 +1144,7 @@ int wfm_get_psf_rolled(wfm_model* h, void* out) {
 
 int wfm_get_cpx_psf(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->multi()) return wfm_multi::get_stack(h, out, true, false);
     WFM_ENTER(h);
     int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1857-1859
     return copy_out(h, out, h->cpx.p, (size_t)h->npix() * h->nzl * 2 * h->esz());
@@ -1060,12 +1152,14 @@ int wfm_get_cpx_psf(wfm_model* h, void* out) {
 
 int wfm_device_psf(wfm_model* h, void** p) {
     if (!h || !p) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "wfm_device_psf (use wfm_multi_part and ask the child)");
     WFM_ENTER(h);
     int rc = compute_psf_impl(h); if (rc) return rc;
     *p = h->psf.p; return WFM_OK;
 }
 int wfm_device_cpx_psf(wfm_model* h, void** p) {
     if (!h || !p) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "wfm_device_cpx_psf (use wfm_multi_part and ask the child)");
     WFM_ENTER(h);
     int rc = compute_psf_impl(h); if (rc) return rc;
     *p = h->cpx.p; return WFM_OK;
@@ -1075,6 +1169,7 @@ int wfm_grad_length(const wfm_model* h) { return h ? h->glen() : 0; }
 
 int wfm_apply_jacobian_dev(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "wfm_apply_jacobian_dev (use wfm_multi_apply_jacobian_dev)");
     WFM_ENTER(h);
     if (!q_dev || !grad_dev) return h->fail(WFM_ERR_INVALID_ARG, "q_dev / grad_dev is NULL");
     if (!(kinds & 7u)) return h->fail(WFM_ERR_INVALID_ARG, "no Jacobian selected");
@@ -1088,6 +1183,7 @@ int wfm_apply_jacobian_dev(wfm_model* h, unsigned kinds, const void* q_dev, doub
 
 static int apply_host(wfm_model* h, unsigned kinds, const void* q_host, std::vector<double>& g) {
     if (!q_host) return h->fail(WFM_ERR_INVALID_ARG, "q is NULL");
+    if (h->multi()) return wfm_multi::apply_host(h, kinds, q_host, g);
     WFM_ENTER(h);
     const size_t bytes = (size_t)h->npix() * h->nzl * h->esz();
     WFM_CK(h, h->qdev.ensure(bytes));
@@ -1169,6 +1265,7 @@ int wfm_apply_j_all(wfm_model* h, const void* q, double* d3, double* ph, double*
 
 int wfm_fill_uniform(wfm_model* h, void* dev, int precision, uint64_t seed, uint64_t first, uint64_t count) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "wfm_fill_uniform (use wfm_multi_part and fill on the child's device)");
     if (!dev) return h->fail(WFM_ERR_INVALID_ARG, "dev_ptr is NULL");
     WFM_ENTER(h);
     const unsigned grid = (unsigned)((count + 255) / 256);
@@ -1206,6 +1303,7 @@ int wfm_get_info(const wfm_model* h, int* nx, int* ny, int* nzg, int* z0, int* n
 
 int wfm_active_extent(const wfm_model* h, int* nax, int* nay) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    if (h->multi()) return wfm_active_extent(h->parts[0], nax, nay);
     DeviceScope dev_scope__(h->device);
     int rc = rebuild_activity(const_cast<wfm_model*>(h)); if (rc) return rc;
     if (nax) *nax = h->nax;
@@ -1215,6 +1313,7 @@ int wfm_active_extent(const wfm_model* h, int* nax, int* nay) {
 
 int wfm_set_profiling(wfm_model* h, int on) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_BCAST(h, wfm_set_profiling(c, on));
     WFM_ENTER(h);
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     drain_spans(h);
@@ -1225,6 +1324,7 @@ int wfm_set_profiling(wfm_model* h, int on) {
 
 int wfm_get_kernel_times(wfm_model* h, double* ms, uint64_t* counts, int n) {
     if (!h || !ms || !counts || n < WFM_KERNEL_IDS) return WFM_ERR_INVALID_ARG;
+    if (h->multi()) return wfm_multi::kernel_times(h, ms, counts);
     WFM_ENTER(h);
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     drain_spans(h);
@@ -1251,3 +1351,4 @@ const char* wfm_version(void) {
 }  // extern "C"
 
 #include "wfm_conv_api.inl"
+#include "wfm_multi.inl"

@@ -302,6 +302,7 @@ int wfm_conv_cost_and_gradient(wfm_conv* c, double alpha, const void* h_host, vo
 // Only x (n doubles) goes to the device and {cost, gX} come back.  param: WFM_DEFOCUS / WFM_PHASE / WFM_MODULUS.
 int wfm_eval_fg(wfm_model* h, wfm_conv* c, int param, const double* x, int n, double alpha, double* cost, double* grad_out) {
     if (!h || !c) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "wfm_eval_fg (the 3-D convolution crosses the z-slabs)");
     if (!cost || !grad_out) return h->fail(WFM_ERR_INVALID_ARG, "cost / grad_out is NULL");
     if (h->precision != WFM_F64) return h->fail(WFM_ERR_UNSUPPORTED, "wfm_eval_fg is fp64 only in this revision");
     if (h->N != c->nx || h->nz_global != c->nz || h->z0 != 0 || h->nzl != h->nz_global || h->nbatch != 1)
@@ -341,6 +342,7 @@ int wfm_eval_fg(wfm_model* h, wfm_conv* c, int param, const double* x, int n, do
 // getMtf() WFM:1807-1828 as intended: FFT3 of the PSF (DoubleFFT_3D.complexForward on the zero-imaginary copy).
 int wfm_get_mtf(wfm_model* h, void* out_host) {
     if (!h) return WFM_ERR_INVALID_ARG;
+    WFM_MULTI_NO(h, "getMtf (the 3-D transform crosses the z-slabs)");
     if (!out_host) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
     if (h->precision != WFM_F64) return h->fail(WFM_ERR_UNSUPPORTED, "getMtf is fp64 only in this revision");
     if (h->z0 != 0 || h->nzl != h->nz_global) return h->fail(WFM_ERR_UNSUPPORTED, "getMtf needs the whole stack on one handle");

@@ -22,14 +22,51 @@ def slab_bounds(nz: int, world: int, rank: int):
     return z0, base + (1 if rank < rem else 0)
 
 
+def connect_peer_exchange(model, dist, group=None) -> bool:
+    """Collective: map every rank's landing buffer into every rank (CUDA IPC) so that k_jac_final sums the gradient
+    over the ranks by itself.  Returns True when EVERY rank succeeded; otherwise every rank is left unconnected and
+    the caller falls back to the all-reduce (e.g. IPC unavailable in the container, ranks on different boxes)."""
+    import torch
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ok = 1
+    try:
+        mine = model.exchangeExport(world)
+    except Exception:                                                    # noqa: BLE001
+        ok, mine = 0, b""
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    if ok and all(isinstance(h, (bytes, bytearray)) and len(h) == capi.WFM_EXCHANGE_HANDLE_BYTES for h in handles):
+        try:
+            model.exchangeConnect(rank, world, handles)
+        except Exception:                                                # noqa: BLE001
+            ok = 0
+    else:
+        ok = 0
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    if int(t.item()) == 0:
+        try:
+            model.exchangeClose()
+        except Exception:                                                # noqa: BLE001
+            pass
+        return False
+    dist.barrier(group=group)               # every rank has mapped every buffer before the first store
+    return True
+
+
 class ShardedWideFieldModel:
     """Same call surface as WideFieldModel for the hot path; every rank passes its own slab of q."""
 
     def __init__(self, psfShape, nPhase, nModulus, NA, lambda_, ni, dxy, dz, radial=False, single=False, *,
-                 group=None, device=0, lib=None, basis=None):
+                 group=None, device=0, lib=None, basis=None, exchange="nccl"):
+        """``exchange``: "nccl" = one torch.distributed all-reduce of the K-vector per evaluation (any backend);
+        "peer" = the sum is taken inside k_jac_final over CUDA-IPC peer memory (NVLink; wfm_exchange_*), no collective
+        call at all -- needs one process per GPU on one box; "auto" = peer when every rank can set it up, else nccl."""
         import torch.distributed as dist
         self._dist = dist
         self.group = group
+        self.exchange = exchange
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         nz = psfShape[2] if not hasattr(psfShape, "dimension") else psfShape.dimension(2)
@@ -39,13 +76,31 @@ class ShardedWideFieldModel:
         self.model = WideFieldModel(psfShape, nPhase, nModulus, NA, lambda_, ni, dxy, dz, radial, single,
                                     device=device, z0=self.z0, nz_local=self.nz_local, lib=lib, basis=basis)
         self._handle_stream_ptr = None      # None: the handle's own (non-blocking) stream
+        if exchange not in ("nccl", "peer", "auto"):
+            raise ValueError("exchange must be 'nccl', 'peer' or 'auto'")
+        if exchange in ("peer", "auto") and self.world > 1:
+            if connect_peer_exchange(self.model, dist, group):
+                self.exchange = "peer"
+            elif exchange == "peer":
+                raise RuntimeError("peer-memory gradient exchange could not be set up on every rank")
+            else:
+                self.exchange = "nccl"
+        elif self.world == 1:
+            self.exchange = "nccl"
+
+    def close(self):
+        if self.exchange == "peer" and self.world > 1:
+            self.model.synchronize()
+            self._dist.barrier(group=self.group)   # nobody unmaps while a peer may still store
+            self.model.exchangeClose()
+        self.model.close()
 
     def __getattr__(self, name):           # setters / getters are slab-local and identical on every rank
         return getattr(self.model, name)
 
     # ---- gradient allreduce -----------------------------------------------------------------------
     def _allreduce_host(self, vec: np.ndarray) -> np.ndarray:
-        if self.world == 1:
+        if self.world == 1 or self.exchange == "peer":       # "peer": wfm_apply_j_* already returned the global sum
             return vec
         import torch
         t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64).copy())
@@ -76,6 +131,9 @@ class ShardedWideFieldModel:
         stream after k_jac_final, waited for by the torch stream, so NCCL can never sum a gradient that has not
         been written yet."""
         import torch
+        if self.exchange == "peer":                       # the sum over the ranks happens inside k_jac_final
+            self.model.applyJacobianDevice(kinds, q_tensor.data_ptr(), grad_tensor.data_ptr())
+            return grad_tensor
         cur = torch.cuda.current_stream()
         if self.world > 1 and self._handle_stream_ptr != cur.cuda_stream:
             # q may have been produced on the torch stream: the handle's stream waits for it first

@@ -155,11 +155,13 @@ class WideFieldModel(MicroscopeModel):
     parametersFlag = [0, 1, 2]                   # WFM:123
 
     def __init__(self, psfShape, nPhase=0, nModulus=1, NA=None, lambda_=None, ni=None, dxy=None, dz=None,
-                 radial=False, single=False, *, device=0, z0=0, nz_local=None, lib=None, basis=None, nbatch=1):
+                 radial=False, single=False, *, device=0, z0=0, nz_local=None, lib=None, basis=None, nbatch=1,
+                 devices=None):
         """WFM:154-188.  ``z0/nz_local`` make this object one z-slab of the global stack (SURVEY 8e);
         ``lib`` lets the tests bind another build of the same ABI; ``basis`` (optional
         ``callable(Nzern) -> Z[Nzern, Npix]``) replaces the device-side computeZernike(); ``nbatch`` > 1 makes the
-        handle a batch of independent models (see WideFieldModelBatch)."""
+        handle a batch of independent models (see WideFieldModelBatch); ``devices`` (a list of CUDA device indices)
+        spreads the stack over several GPUs of the box behind the same calls (wfm_create_multi)."""
         super().__init__(psfShape, dxy, dz, single)
         self._lib = lib if lib is not None else capi.load_library()
         self._h = C.c_void_p()
@@ -168,7 +170,14 @@ class WideFieldModel(MicroscopeModel):
         self.z0, self.nz_local = int(z0), int(nzl)
         self.nbatch = int(nbatch)
         prec = capi.WFM_F32 if single else capi.WFM_F64
-        if self.nbatch > 1:
+        self.devices = None if devices is None else [int(d) for d in devices]
+        if self.devices is not None:
+            if self.nbatch > 1 or z0 != 0 or (nz_local is not None and nz_local != self.Nz):
+                raise ValueError("a multi-device model holds the whole stack of one model")
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            rc = self._lib.wfm_create_multi(C.byref(self._h), self.Nx, self.Ny, self.Nz, self.dxy, self.dz, prec, arr,
+                                            len(self.devices))
+        elif self.nbatch > 1:
             rc = self._lib.wfm_create_batch(C.byref(self._h), self.Nx, self.Ny, self.Nz, self.nbatch, self.dxy,
                                             self.dz, prec, int(device))
             self.nz_local = self.Nz * self.nbatch                          # planes held by the handle
@@ -344,6 +353,46 @@ class WideFieldModel(MicroscopeModel):
         v.__cuda_array_interface__ = {"shape": (self.nz_local, self.Ny, self.Nx), "typestr": "<f4" if self.single else "<f8",
                                       "data": (self.devicePsfPointer(), False), "version": 2}
         return torch.as_tensor(v, device="cuda")
+
+    # -- multi-device handles (wfm_create_multi) ------------------------------------------------------------------
+    def parts(self):
+        """[(device, z0, nz_local, child handle)] of a multi-device model ([] for a plain one)."""
+        out = []
+        for i in range(self._lib.wfm_multi_parts(self._h)):
+            d, z, n = C.c_int(), C.c_int(), C.c_int()
+            child = C.c_void_p()
+            self._call("wfm_multi_part_info", i, C.byref(d), C.byref(z), C.byref(n))
+            self._call("wfm_multi_part", i, C.byref(child))
+            out.append((d.value, z.value, n.value, child))
+        return out
+
+    def applyJacobianDeviceMulti(self, kinds, q_dev_ptrs, grad_dev_ptr):
+        """wfm_multi_apply_jacobian_dev: one device pointer per part (its slab of q, on its device); the summed
+        gradient lands on the first device.  Asynchronous."""
+        arr = (C.c_void_p * len(q_dev_ptrs))(*[C.c_void_p(p) for p in q_dev_ptrs])
+        self._call("wfm_multi_apply_jacobian_dev", int(kinds), arr, C.c_void_p(grad_dev_ptr))
+        self.PState = self._lib.wfm_psf_state(self._h)
+
+    # -- cross-process gradient exchange over peer memory (one process per GPU) -------------------------------------
+    def exchangeExport(self, world):
+        buf = (C.c_char * capi.WFM_EXCHANGE_HANDLE_BYTES)()
+        self._call("wfm_exchange_export", int(world), buf)
+        return bytes(buf)
+
+    def exchangeConnect(self, rank, world, handles):
+        blob = b"".join(handles)
+        if len(blob) != world * capi.WFM_EXCHANGE_HANDLE_BYTES:
+            raise ValueError("one 64-byte handle per rank")
+        self._call("wfm_exchange_connect", int(rank), int(world), C.c_char_p(blob))
+
+    def exchangeStatus(self):
+        rc = self._lib.wfm_exchange_status(self._h)
+        if rc < 0:
+            raise RuntimeError(self._lib.wfm_last_error(self._h).decode())
+        return rc
+
+    def exchangeClose(self):
+        self._call("wfm_exchange_close")
 
     def fillUniform(self, dev_ptr, seed, first_index, count, single=None):
         prec = capi.WFM_F32 if (self.single if single is None else single) else capi.WFM_F64

@@ -62,9 +62,20 @@ struct cudaDeviceProp { int multiProcessorCount; size_t sharedMemPerBlockOptin; 
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == 0 ? "no error" : "emulated error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
-static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+// "devices": WFM_EMU_DEVICES of them (default 1); all share the host heap, so peer access and IPC mappings are the
+// identity -- enough to exercise the multi-device / exchange HOST logic and the exchange protocol of the kernels
+static inline int emu_device_count() { const char* e = getenv("WFM_EMU_DEVICES"); const int n = e ? atoi(e) : 1; return n < 1 ? 1 : n; }
+static inline int& emu_current_device() { static thread_local int d = 0; return d; }
+static inline cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= emu_device_count()) return cudaErrorInvalidValue; emu_current_device() = d; return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = emu_current_device(); return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = emu_device_count(); return cudaSuccess; }
+enum { cudaErrorPeerAccessAlreadyEnabled = 704, cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+struct cudaIpcMemHandle_t { char reserved[64]; };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     memset(p, 0, sizeof(*p)); p->multiProcessorCount = 4; p->sharedMemPerBlockOptin = 227 * 1024; p->major = 10; p->minor = 0;
     p->l2CacheSize = 126u << 20; snprintf(p->name, sizeof(p->name), "emulated"); return cudaSuccess; }
@@ -74,6 +85,7 @@ static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return c
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (void*)0x1; return cudaSuccess; }
