@@ -57,6 +57,7 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
     private static FunctionDescriptor ints(java.lang.foreign.MemoryLayout... args) { return FunctionDescriptor.of(JAVA_INT, args); }
 
     private static final MethodHandle CREATE = fn("wfm_create", ints(ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_INT, JAVA_INT));
+    private static final MethodHandle CREATE_MULTI = fn("wfm_create_multi", ints(ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_INT, ADDRESS, JAVA_INT));
     private static final MethodHandle DESTROY = fn("wfm_destroy", ints(ADDRESS));
     private static final MethodHandle LAST_ERROR = fn("wfm_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
     private static final MethodHandle SET_OPTICS = fn("wfm_set_optics", ints(ADDRESS, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE));
@@ -113,7 +114,12 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
         this.radius = NA / lambda;                                                  // WFM:165
         this.lambda_ni = ni / lambda;                                               // WFM:166
         MemorySegment out = arena.allocate(ADDRESS);
-        check(MemorySegment.NULL, call(CREATE, out, Nx, Ny, Nz, dxy, dz, single ? 1 : 0, deviceIndex()));
+        int[] devs = deviceList();
+        if (devs.length > 1)        // the stack over several GPUs behind the SAME calls: one z-slab per device (wfm_create_multi)
+            check(MemorySegment.NULL, call(CREATE_MULTI, out, Nx, Ny, Nz, dxy, dz, single ? 1 : 0,
+                                           arena.allocateFrom(JAVA_INT, devs), devs.length));
+        else
+            check(MemorySegment.NULL, call(CREATE, out, Nx, Ny, Nz, dxy, dz, single ? 1 : 0, devs[0]));
         handle = out.get(ADDRESS, 0);
         vox = (long) Nx * Ny * Nz;
         elemBytes = single ? 4 : 8;
@@ -128,8 +134,13 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
         setDefocus(new double[] {ni / lambda, deltaX, deltaY});                     // WFM:187, 1562-1564
     }
 
-    /** Device this model lives on; one JVM may hold one model per GPU (z-slabs: wfm_create_slab, see INTEGRATION.md). */
-    protected int deviceIndex() { return Integer.getInteger("wfm.device", 0); }
+    /** Devices this model lives on: -Dwfm.devices=0,1,...,7 spreads the z-planes over the GPUs of the box (the caller
+     *  stays one thread, PSF_Estimation.java:202-217: every call below fans out inside the library); default -Dwfm.device=0. */
+    protected int[] deviceList() {
+        String list = System.getProperty("wfm.devices");
+        if (list == null || list.isBlank()) return new int[] {Integer.getInteger("wfm.device", 0)};
+        return java.util.Arrays.stream(list.split(",")).map(String::trim).mapToInt(Integer::parseInt).toArray();
+    }
 
     // ---- the hot path ------------------------------------------------------------------------------------------------
     /** WFM:206-396.  One pipeline launch for all z-planes; no-op when the PSF is valid (WFM:207). */
@@ -230,7 +241,12 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
     }
     /** WFM:1655-1665. */
     public void setPhase(double[] alpha) {
-        if (alpha == null || alpha.length == 0) { nPhase = 0; parameterCoefs[PHASE] = null; return; }
+        if (alpha == null || alpha.length == 0) {
+            nPhase = 0; parameterSpace[PHASE] = null; parameterCoefs[PHASE] = null;
+            check(handle, call(SET_PHASE, handle, MemorySegment.NULL, 0));          // the device side drops its phase vector too
+            freeMem();
+            return;
+        }
         setNPhase(alpha.length);
         setPhase(parameterSpace[PHASE].wrap(alpha));
     }
