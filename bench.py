@@ -415,17 +415,22 @@ def run_b200(args):
     N, nzl, nzg = w.n, w.nzl, w.nzg
     es = w.es
     warm = max(args.warmup, 3)
-    for i in range(warm):
-        w.step(i)
-    fence()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                           # nvidia-smi needs a few hundred ms before its first sample
+    t_w = time.perf_counter()
+    i = 0
+    while i < warm or (not args.quick and time.perf_counter() - t_w < 0.4):
+        w.step(i)
+        i += 1
+        if i % 16 == 0:
+            torch.cuda.synchronize()
+    warm = i
+    fence()
     # ---- timed region: K steps --------------------------------------------------------------------------------
     n0 = lib.wfm_launch_count()
     ms = timed(w, args.steps, 0)
     launches = lib.wfm_launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
     value = planes_global * args.steps / (ms * 1e-3)
     gsum = float(w.grad.abs().sum().item())
     if not os.environ.get("WFM_PIPE_ROLES"):                       # (single-role profiling runs compute garbage)
@@ -449,6 +454,7 @@ def run_b200(args):
             w.step(b * blk + i)
         evs[b + 1].record()
     fence()
+    clocks = sampler.stop() if rank == 0 else None       # sampled over the lead-in, the timed K steps and these two passes
     per_step = sorted(evs[b].elapsed_time(evs[b + 1]) / blk for b in range(nblk))
     dist_ms = {"median": max_over_ranks(per_step[len(per_step) // 2]), "best": max_over_ranks(per_step[0]),
                "worst": max_over_ranks(per_step[-1]), "blocks": nblk, "steps_per_block": blk}

@@ -112,8 +112,10 @@ class WeightedConvolutionCost:
         owner = model.parameterSpace[int(param_flag)]
         if isinstance(x, DoubleShapedVector) and x.getOwner() is owner:
             setter[int(param_flag)](x)
+        elif owner is not None and owner.getNumber() == xv.size:
+            setter[int(param_flag)](owner.wrap(xv.copy()))     # setParam(DoubleShapedVector): no basis rebuild (WFM:412-422)
         else:
-            setter[int(param_flag)](xv.copy())
+            setter[int(param_flag)](xv.copy())                 # a new length: the double[] overloads resize the space first
         g = np.zeros(xv.size)
         cost = C.c_double()
         rc = self._lib.wfm_eval_fg(model.handle, self._h, int(param_flag), None, xv.size,

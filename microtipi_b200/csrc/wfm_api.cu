@@ -450,7 +450,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         r.glen = h->glen();
         const bool batch = h->nbatch > 1;
         r.bpar = batch ? (const double*)h->bpar_dev.p : nullptr;
-        r.cpm = (h->nzm + WFM_RED_PLANES - 1) / WFM_RED_PLANES;
+        r.cpm = (h->nzm + WFM_RED_CHUNK_PLANES - 1) / WFM_RED_CHUNK_PLANES;
         const int nblocks = h->ncells > 0 ? (h->ncells + WFM_RED_THREADS - 1) / WFM_RED_THREADS : 1;
         const int nchunks = r.cpm * h->nbatch;
         WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * nchunks * r.glen));
@@ -668,7 +668,7 @@ static int create_impl(wfm_model** out, int nx, int ny, int nz_global, int z0, i
     }
     // (the model index is a grid.y dimension of the setters and, times the plane chunks per model, of the reduction)
     if (nbatch < 1 || (long long)nbatch * nz_local > (1ll << 24) ||
-        (long long)nbatch * ((nz_local + WFM_RED_PLANES - 1) / WFM_RED_PLANES) > 65535) {
+        (long long)nbatch * ((nz_local + WFM_RED_CHUNK_PLANES - 1) / WFM_RED_CHUNK_PLANES) > 65535) {
         g_create_error = "bad batch size"; return WFM_ERR_INVALID_ARG;
     }
     if (precision != WFM_F64 && precision != WFM_F32) { g_create_error = "bad precision"; return WFM_ERR_INVALID_ARG; }

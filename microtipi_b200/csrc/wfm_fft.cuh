@@ -202,13 +202,21 @@ __host__ __device__ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2
 // ---- barrier scopes --------------------------------------------------------------------------
 // A column tile is transposed through shared memory by all warps of the CTA: CTA-wide barrier.
 struct CtaSync {
+#ifdef WFM_PROBE_NO_CTA_SYNC      /* timing probe only (races, wrong results): what do the exchange barriers of the column items cost? */
+    static WFM_DEVI void sync(int) {}
+#else
     static WFM_DEVI void sync(int) { __syncthreads(); }
+#endif
 };
 // A row transform is private to its TT threads: a named barrier over those warps when TT >= 64,
 // a warp barrier when the transform fits in one warp.  (ncu on the first pipeline revision:
 // barrier stalls dominated with 16-warp CTA barriers; profiles/r01b_*.)
 template <int TT> struct RowSync {
     static WFM_DEVI void sync(int slot) {
+#ifdef WFM_PROBE_NO_ROW_SYNC      /* timing probe only (races, wrong results): what do the 2-warp barriers of the row transforms cost? */
+        (void)slot;
+        return;
+#endif
         if constexpr (TT >= 64) {
 #ifdef WFM_EMU
             emu::named_barrier(1 + slot, TT);

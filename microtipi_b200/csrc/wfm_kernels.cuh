@@ -460,7 +460,9 @@ WFM_DEVI void pipe_wait(const unsigned* cnt, unsigned target, unsigned* err) {
 // CTA barrier (all stores of the item issued), then thread 0 fences at GPU scope and publishes --
 // the arrive half of a cooperative-groups grid barrier.
 WFM_DEVI void pipe_signal(unsigned* cnt) {
+#ifndef WFM_PROBE_NO_ITEM_SYNC    /* timing probe only (races, wrong results): what does the CTA barrier at the item boundary cost? */
     __syncthreads();
+#endif
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(cnt, 1u); }
 }
 
@@ -532,8 +534,16 @@ struct PipeQueue {
     }
     // claim the next item (thread 0, once per item; called from inside the item and again, as a
     // no-op, before the item is published)
-    WFM_DEVI void prefetch(const PipeCtl& c, int P) {
-        if (threadIdx.x == 0 && !pre) { claim(cur ^ 1, c, P); pre = true; }
+    WFM_DEVI bool prefetch(const PipeCtl& c, int P) {
+        if (threadIdx.x == 0 && !pre) { claim(cur ^ 1, c, P); pre = true; return true; }
+        return false;
+    }
+    // (thread 0, right after a claim) the item just claimed
+    WFM_DEVI PipeItem peek_next() const {
+        const int* d = s + (cur ^ 1) * SLOT;
+        PipeItem it;
+        it.type = d[0]; it.plane = d[1]; it.sub = d[2]; it.model = d[3]; it.ringoff = d[5];
+        return it;
     }
     WFM_DEVI void advance() { cur ^= 1; }
 };
@@ -541,9 +551,10 @@ struct PipeQueue {
 // What an item must wait for before it may touch the ring slot (NULL counter: nothing).
 struct PipeDep { const unsigned* cnt; unsigned target; unsigned* err; };
 // hook for fft_inplace: claim the next item after the first stage of a column item
-struct PipePrefetchHook {
-    PipeQueue& qu; const PipeCtl& ctl; int P;
-    WFM_DEVI void operator()() const { qu.prefetch(ctl, P); }
+struct NoClaimAction { WFM_DEVI void operator()(const PipeItem&) const {} };
+template <class OnClaim = NoClaimAction> struct PipePrefetchHook {
+    PipeQueue& qu; const PipeCtl& ctl; int P; OnClaim on_claim;
+    WFM_DEVI void operator()() const { if (qu.prefetch(ctl, P)) on_claim(qu.peek_next()); }
 };
 WFM_DEVI void pipe_wait(const PipeDep& d) { if (d.cnt) pipe_wait(d.cnt, d.target, d.err); }
 
@@ -629,8 +640,8 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int bm, int ri
             v[e] = val;
         }
     }
-    fft_inplace<T, P, L, CtaSync, PipePrefetchHook, NARROW, WFM_PSF_TW_TREE>(v, cells + c, t, tw_s, tw_s + N, 0,
-                                                                             PipePrefetchHook{qu, ctl, a.g.nzl});
+    fft_inplace<T, P, L, CtaSync, PipePrefetchHook<>, NARROW, WFM_PSF_TW_TREE>(v, cells + c, t, tw_s, tw_s + N, 0,
+                                                                               PipePrefetchHook<>{qu, ctl, a.g.nzl, NoClaimAction{}});
     pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
     cx<T>* dst = a.T1 + (size_t)ringoff + (size_t)sub * N * C + c;
 #pragma unroll
@@ -781,6 +792,29 @@ template <typename T> struct JacArgs {
     int last_plane_only;  // quirk Q1 compat mode for the modulus Jacobian
 };
 
+// Claim action of the Jacobian pipeline (thread 0, late in the previous item): when the item just claimed is a row
+// item, its first row of every group -- C consecutive rows of conj(a) and of q -- starts its way from DRAM to L2 now
+// (TMA bulk prefetch), so that the first load of the item is an L2 hit like the later rows, whose prefetch is issued
+// one row ahead by their own group.  (Probe -DWFM_PROBE_JAC_L2: row loads that never miss L2 are worth 6 % of the kernel.)
+#ifndef WFM_CLAIM_PREFETCH
+#define WFM_CLAIM_PREFETCH 1
+#endif
+template <typename T, int N> struct JacClaimPrefetch {
+    const cx<T>* cpx; const T* q;
+    WFM_DEVI void operator()(const PipeItem& it) const {
+#if WFM_CLAIM_PREFETCH && WFM_L2_PREFETCH
+        using Cfg = PipeCfg<T, N>;
+        if (it.type != 0) return;
+        const size_t base = (size_t)it.plane * N * N + (size_t)N * (it.sub * Cfg::ROWS_PER_ITEM);
+#pragma unroll
+        for (int r = 0; r < Cfg::C; ++r) {
+            wfm_prefetch_l2(&cpx[base + (size_t)N * r], (unsigned)(N * sizeof(cx<T>)));
+            wfm_prefetch_l2(&q[base + (size_t)N * r], (unsigned)(N * sizeof(T)));
+        }
+#endif
+    }
+};
+
 // A-item: ROWS_PER_ITEM rows of plane pl (each TT-thread group walks KR of them).  Aq = conj(a)*q
 // fused into the streaming load (WFM:907-914), FFT along x, keep the active kx only.
 template <typename T, int N, bool NARROW>
@@ -819,7 +853,8 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
 #endif
 #pragma unroll 1
     for (int kk = 0; kk < Cfg::KR; ++kk) {
-        if (kk == Cfg::KR - 1) qu.prefetch(ctl, a.g.nzl);             // claim the next item behind the last row
+        if (kk == Cfg::KR - 1 && qu.prefetch(ctl, a.g.nzl))           // claim the next item behind the last row
+            JacClaimPrefetch<T, N>{a.cpx, a.q}(qu.peek_next());
         const int y = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;      // N % ROWS_PER_ITEM == 0
 #if defined(WFM_PROBE_JAC_L1)      /* timing probes only (wrong results): what if the row loads never left the SM / the L2? */
         const size_t base = 0;
@@ -907,8 +942,9 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int bm, int ri
         for (int r = 0; r < P::RL; ++r)
             if (leg_live<P::RL, NARROW>(r))
                 fl |= (unsigned)__ldg(&a.st.flags[sbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
-    fft_inplace<T, P, L, CtaSync, PipePrefetchHook, false, WFM_JAC_TW_TREE>(v, cells + c, t, tw_s, tw_s + N, 0,
-                                                                            PipePrefetchHook{qu, ctl, a.g.nzl});
+    using ClaimHook = PipePrefetchHook<JacClaimPrefetch<T, N>>;
+    fft_inplace<T, P, L, CtaSync, ClaimHook, false, WFM_JAC_TW_TREE>(v, cells + c, t, tw_s, tw_s + N, 0,
+                                                                     ClaimHook{qu, ctl, a.g.nzl, JacClaimPrefetch<T, N>{a.cpx, a.q}});
     const int iz = a.g.z0 + (pl - bm * a.g.nzm);
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
     const bool mod_plane = (a.Gm != nullptr) && (!a.last_plane_only || iz == a.g.nz_global - 1);
@@ -962,14 +998,14 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
                 jac_rows_item<T, N, NARROW>(a, it.plane, it.sub, it.ringoff, cells, tw_s, invx_s, dep, qu, ctl);
             }
-            qu.prefetch(ctl, P);
+            if (qu.prefetch(ctl, P)) JacClaimPrefetch<T, N>{a.cpx, a.q}(qu.peek_next());
             pipe_signal(&ctl.cntA[it.plane]);
         } else {
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
                 jac_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, it.ringoff, cells, tw_s, qu, ctl);
             }
-            qu.prefetch(ctl, P);
+            if (qu.prefetch(ctl, P)) JacClaimPrefetch<T, N>{a.cpx, a.q}(qu.peek_next());
             pipe_signal(&ctl.cntB[it.plane]);
         }
         qu.advance();
@@ -1010,8 +1046,12 @@ struct ReduceArgs {
 #define WFM_RED_THREADS 256
 #define WFM_RED_CHUNK 8
 #ifndef WFM_RED_PLANES
-#define WFM_RED_PLANES 16   // planes summed by one CTA ("chunk"); 4 and 8 measured slower (more basis re-reads)
+#define WFM_RED_PLANES 16   // loads a thread keeps in flight at once; 4 and 8 measured slower
 #endif
+#ifndef WFM_RED_BATCHES
+#define WFM_RED_BATCHES 4   // batches of WFM_RED_PLANES a thread sums one after the other: a CTA owns a chunk of
+#endif                      // 64 planes, so that 512^2 x 256 is ONE wave of 360 CTAs (was 2.4 waves of 1440)
+#define WFM_RED_CHUNK_PLANES (WFM_RED_PLANES * WFM_RED_BATCHES)
 
 // One thread per support cell and per chunk of WFM_RED_PLANES planes.  Sums the planes of the chunk
 // in fixed order (gP = sum jin, gD = sum defoc*jin, gM = sum J), then forms the glen dot products
@@ -1028,31 +1068,36 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     wfm_grid_dep_trigger();
     wfm_grid_dep_wait();                               // Gj / Gm come from the pipeline kernel before us
     const int bm = blockIdx.y / a.cpm;                 // model of a batch handle (0 otherwise); chunks never straddle models
-    const int zl0 = (blockIdx.y - bm * a.cpm) * WFM_RED_PLANES;   // first plane of the chunk inside its model
-    const int p0 = bm * a.g.nzm + zl0;
-    const int p1 = (zl0 + WFM_RED_PLANES < a.g.nzm) ? p0 + WFM_RED_PLANES : (bm + 1) * a.g.nzm;
+    const int zc0 = (blockIdx.y - bm * a.cpm) * WFM_RED_CHUNK_PLANES;   // first plane of the chunk inside its model
+    const int pend = (zc0 + WFM_RED_CHUNK_PLANES < a.g.nzm) ? bm * a.g.nzm + zc0 + WFM_RED_CHUNK_PLANES : (bm + 1) * a.g.nzm;
     const bool m = sup && (a.flags[(size_t)bm * img + cell] & 1u);
     double gP = 0.0, gD = 0.0, gM = 0.0;
-    if (m) {
-        // all loads of the chunk in flight at once (the kernel is latency-bound: one DRAM round trip per thread
-        // instead of four; measured 41 -> 35 us per step at 512^2 x 256), then the fixed-order sums
-        double jin[WFM_RED_PLANES];
+#pragma unroll 1
+    for (int bt = 0; bt < WFM_RED_BATCHES; ++bt) {
+        const int zl0 = zc0 + bt * WFM_RED_PLANES;
+        const int p0 = bm * a.g.nzm + zl0;
+        if (p0 >= pend) break;
+        const int p1 = (p0 + WFM_RED_PLANES < pend) ? p0 + WFM_RED_PLANES : pend;
+        if (m) {
+            // all loads of the batch in flight at once (the kernel is latency-bound), then the fixed-order sums
+            double jin[WFM_RED_PLANES];
 #pragma unroll
-        for (int k = 0; k < WFM_RED_PLANES; ++k) jin[k] = (p0 + k < p1) ? __ldcs(&a.Gj[(size_t)(p0 + k) * img + cell]) : 0.0;
+            for (int k = 0; k < WFM_RED_PLANES; ++k) jin[k] = (p0 + k < p1) ? __ldcs(&a.Gj[(size_t)(p0 + k) * img + cell]) : 0.0;
 #pragma unroll
-        for (int k = 0; k < WFM_RED_PLANES; ++k) {
-            gP += jin[k];
-            gD += defoc_depth_dev(a.g.z0 + zl0 + k, a.g.nz_global, a.g.dz) * jin[k];
+            for (int k = 0; k < WFM_RED_PLANES; ++k) {
+                gP += jin[k];
+                gD += defoc_depth_dev(a.g.z0 + zl0 + k, a.g.nz_global, a.g.dz) * jin[k];
+            }
         }
-    }
-    if (sup && (a.kinds & 4u)) {
-        double jm[WFM_RED_PLANES];
+        if (sup && (a.kinds & 4u)) {
+            double jm[WFM_RED_PLANES];
 #pragma unroll
-        for (int k = 0; k < WFM_RED_PLANES; ++k)
-            jm[k] = (p0 + k < p1 && (!a.last_plane_only || a.g.z0 + zl0 + k == a.g.nz_global - 1))
-                        ? __ldcs(&a.Gm[(size_t)(p0 + k) * img + cell]) : 0.0;
+            for (int k = 0; k < WFM_RED_PLANES; ++k)
+                jm[k] = (p0 + k < p1 && (!a.last_plane_only || a.g.z0 + zl0 + k == a.g.nz_global - 1))
+                            ? __ldcs(&a.Gm[(size_t)(p0 + k) * img + cell]) : 0.0;
 #pragma unroll
-        for (int k = 0; k < WFM_RED_PLANES; ++k) gM += jm[k];
+            for (int k = 0; k < WFM_RED_PLANES; ++k) gM += jm[k];
+        }
     }
     // defocus weights: idef = 1/psi on maskPupil (WFM:1251); rx, ry of the prologue WFM:1040-1061
     double wD = 0.0, rx = 0.0, ry = 0.0;

@@ -187,6 +187,7 @@ def test_full_size_properties_512x512x256(lib):
     L = m.gradLength()
     g = torch.zeros((3, L), dtype=torch.float64, device=dev)
     comb = 2.0 * q1 - 3.0 * q2
+    torch.cuda.synchronize()                     # torch's stream produced the inputs; the handle runs on its own stream
     for i, qq in enumerate((q1, q2, comb)):
         m.applyJacobianDevice(7, qq.data_ptr(), g[i].data_ptr())
     m.synchronize()
@@ -196,6 +197,7 @@ def test_full_size_properties_512x512x256(lib):
     sel = (3, 200)
     for iz in sel:
         qs[iz * N * N:(iz + 1) * N * N] = q1[iz * N * N:(iz + 1) * N * N]
+    torch.cuda.synchronize()
     m.applyJacobianDevice(7, qs.data_ptr(), g[0].data_ptr())
     m.synchronize()
     got = g[0].cpu().numpy()
