@@ -257,6 +257,14 @@ WFM_API int wfm_grad_length(const wfm_model* h);
  * these semantics are restated, parity unpinned.  fp64, nx == ny, nx and nz powers of two in [32, 2048]. */
 typedef struct wfm_conv wfm_conv;
 WFM_API int wfm_conv_create(wfm_conv** out, int nx, int ny, int nz, int precision, int device);
+/* The data term sharded by z-slab over n_dev GPUs (same device list and split as wfm_create_multi): real-space volumes
+ * and the x / y passes in slabs, the z pass in pencils; the two transposes are done by the stores of the y pass and of
+ * the fused z pass over NVLink peer memory (no separate all-to-all).  Answers wfm_conv_set_object / _set_data /
+ * _set_weights / wfm_conv_cost_and_gradient (whole host volumes; every slab uses its own PCIe link) and wfm_eval_fg
+ * together with a wfm_create_multi model: the inner loop of the PSF fit then scales over the box with only the
+ * parameter vector crossing PCIe.  Needs peer access between all the devices. */
+WFM_API int wfm_conv_create_multi(wfm_conv** out, int nx, int ny, int nz, int precision, const int* devices, int n_dev);
+WFM_API int wfm_conv_parts(const wfm_conv* c);
 WFM_API int wfm_conv_destroy(wfm_conv* c);
 WFM_API const char* wfm_conv_last_error(const wfm_conv* c);
 WFM_API int wfm_conv_set_stream(wfm_conv* c, void* cuda_stream);

@@ -89,6 +89,8 @@ SIGNATURES = {
     "wfm_apply_jacobian_dev": (C.c_int, [_vp, C.c_uint, _vp, _vp]),
     "wfm_grad_length": (C.c_int, [_vp]),
     "wfm_conv_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "wfm_conv_create_multi": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int]),
+    "wfm_conv_parts": (C.c_int, [_vp]),
     "wfm_conv_destroy": (C.c_int, [_vp]),
     "wfm_conv_last_error": (C.c_char_p, [_vp]),
     "wfm_conv_set_stream": (C.c_int, [_vp, _vp]),

@@ -18,7 +18,7 @@ from .wide_field_model import DoubleShapedVector, DoubleShapedVectorSpace, Shape
 
 
 class WeightedConvolutionCost:
-    def __init__(self, space, *, device=0, lib=None):
+    def __init__(self, space, *, device=0, lib=None, devices=None):
         self._lib = lib if lib is not None else capi.load_library()
         self.space = space
         shape = space.getShape() if hasattr(space, "getShape") else Shape(space)
@@ -26,7 +26,11 @@ class WeightedConvolutionCost:
             raise ValueError("the data space must be 3D")
         self.Nx, self.Ny, self.Nz = shape.dimension(0), shape.dimension(1), shape.dimension(2)
         self._h = C.c_void_p()
-        rc = self._lib.wfm_conv_create(C.byref(self._h), self.Nx, self.Ny, self.Nz, capi.WFM_F64, int(device))
+        if devices is not None:             # z-slabs over several GPUs (pairs with WideFieldModel(devices=...))
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._lib.wfm_conv_create_multi(C.byref(self._h), self.Nx, self.Ny, self.Nz, capi.WFM_F64, arr, len(devices))
+        else:
+            rc = self._lib.wfm_conv_create(C.byref(self._h), self.Nx, self.Ny, self.Nz, capi.WFM_F64, int(device))
         if rc != capi.WFM_OK:
             msg = self._lib.wfm_conv_last_error(None).decode()
             self._h = C.c_void_p()

@@ -1352,3 +1352,4 @@ const char* wfm_version(void) {
 
 #include "wfm_conv_api.inl"
 #include "wfm_multi.inl"
+#include "wfm_conv_multi.inl"

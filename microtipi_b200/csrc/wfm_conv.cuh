@@ -36,6 +36,33 @@ enum ConvStore {
     CS_SPECTRUM = 5     // X = v                                (FFT3(obj) at set_object time)
 };
 
+// ---- z-slab sharding across GPUs -----------------------------------------------------------------------------
+// Real-space volumes (h, data, weights, residual, gradient) and the x / y passes live in Z-SLABS: device g holds
+// planes [z0_g, z0_g + nzl_g).  The z pass needs every plane of a (ky, kx) column, so it runs in PENCIL layout:
+// device g holds ALL Nz planes of the rows ky in [y0_g, y0_g + nyl_g), Vp_g[z][ky - y0_g][kx].  The all-to-all
+// transposes between the two layouts are not separate collectives: the y pass stores every output row straight into
+// the pencil volume of the device that owns its ky (CW adjacent kx = one 128-byte NVLink store per row and tile),
+// and the fused z pass stores every output plane straight into the slab volume of the device that owns its z.
+// n items over `parts` owners, the first n % parts owners hold one more (the split of wfm_create_multi).
+struct SplitMap {
+    int n, parts;
+    __host__ __device__ int base() const { return n / parts; }
+    __host__ __device__ int rem() const { return n % parts; }
+    __host__ __device__ int first(int o) const { return o * base() + (o < rem() ? o : rem()); }
+    __host__ __device__ int count(int o) const { return base() + (o < rem() ? 1 : 0); }
+    __host__ __device__ int owner(int i) const {
+        const int b = base(), r = rem(), cut = r * (b + 1);
+        return i < cut ? i / (b + 1) : r + (i - cut) / b;
+    }
+};
+template <typename T> struct ConvPeers {
+    cx<T>* vol[WFM_MAX_RANKS];   // destination volume of every device as mapped here (pencil volumes for the y pass,
+                                 // slab volumes for the z pass)
+    SplitMap split;              // how the scattered axis (ky for the y pass, z for the z pass) is divided
+    int src_first;               // this device's first index on the OTHER axis (its z0 for the y pass, its y0 for the z pass)
+    int ny_full;                 // Ny of the whole volume (slab rows per plane)
+};
+
 template <typename T> struct ConvArgs {
     cx<T>* V;             // work volume
     const T* real_in;     // CL_REAL source
@@ -50,6 +77,8 @@ template <typename T> struct ConvArgs {
     int nx, ny, nz;
     double inv_ntot, alpha;
     int clear_grad;       // CS_GRAD: 1 = overwrite, 0 = accumulate (TiPi's `clr` flag)
+    // z-sharded data term (wfm_conv_create_multi): where the y pass / the fused z pass deliver their output
+    ConvPeers<T> peers;
 };
 
 template <typename T, int STORE>
@@ -280,7 +309,9 @@ template <typename T, int LEN> struct ConvColCfg {
     static constexpr int MINB_ZZ = (THREADS <= 256 && LEN <= 256) ? WFM_CONV_ZZ_MINB : 1;
 };
 
-template <typename T, int LEN, int STORE>
+// SCATTER (y pass of a z-sharded volume, STORE == CS_CPLX): output row ky of local plane zl goes to the pencil
+// volume of the device that owns ky, at [z0 + zl][ky - y0_owner][kx].
+template <typename T, int LEN, int STORE, bool SCATTER = false>
 __global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS) k_conv_cols(ConvArgs<T> a, size_t stride, int tiles_per_outer,
                                                                             size_t outer_stride) {
     using P = Plan<LEN>;
@@ -301,19 +332,37 @@ __global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS) k_conv_cols(ConvA
     __syncthreads();
     fft_inplace<T, P, L, CtaSync>(v, cells + c, t, tw_s, tw_s + LEN, 0);
     double cost_acc = 0.0;
+    if constexpr (SCATTER) {
+        static_assert(STORE == CS_CPLX, "scatter stores plain values");
+        const int zl = blockIdx.x / tiles_per_outer;
+        const size_t kx = (size_t)(blockIdx.x % tiles_per_outer) * CW + c;
+        const size_t zg = (size_t)(a.peers.src_first + zl);
 #pragma unroll
-    for (int u = 0; u < E / P::RL; ++u)
+        for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
-        for (int r = 0; r < P::RL; ++r)
-            conv_store<T, STORE>(a, base + (size_t)((t + TT * u) + P::SL * r) * stride, v[u * P::RL + r], cost_acc);
-    if constexpr (STORE == CS_RESID) conv_cost_reduce(cost_acc, &a.cost_part[blockIdx.x]);
+            for (int r = 0; r < P::RL; ++r) {
+                const int ky = (t + TT * u) + P::SL * r;
+                const int o = a.peers.split.owner(ky);
+                const size_t nyl = (size_t)a.peers.split.count(o), kyl = (size_t)(ky - a.peers.split.first(o));
+                a.peers.vol[o][(zg * nyl + kyl) * stride + kx] = v[u * P::RL + r];      // `stride` = row pitch of the volume
+            }
+    } else {
+#pragma unroll
+        for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+            for (int r = 0; r < P::RL; ++r)
+                conv_store<T, STORE>(a, base + (size_t)((t + TT * u) + P::SL * r) * stride, v[u * P::RL + r], cost_acc);
+        if constexpr (STORE == CS_RESID) conv_cost_reduce(cost_acc, &a.cost_part[blockIdx.x]);
+    }
 }
 
 // ---- z pass there and back: FFT_z, spectral product, conjugate, FFT_z again without leaving the SM ---------
 // MUL = CS_MULX_CONJ: V <- FFT_z(conj(FFT_z(V) * X));  CS_MULCX_CONJ: V <- FFT_z(conj(FFT_z(V) * conj(X))).
 // Saves one write + read of the work volume per transform pair; the only extra cost is one exchange through the
 // tile's shared cells (the first transform leaves its output in output-slot order, the second wants input-slot order).
-template <typename T, int LEN, int MUL>
+// SCATTER (z-sharded volume): the kernel works on this device's pencil volume [Nz][nyl][P]; output plane z of
+// pencil row kyl goes to the slab volume of the device that owns z, at [z - z0_owner][y0 + kyl][kx].
+template <typename T, int LEN, int MUL, bool SCATTER = false>
 __global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS, ConvColCfg<T, LEN>::MINB_ZZ) k_conv_cols_zz(ConvArgs<T> a, size_t stride, int tiles_per_outer,
                                                                                size_t outer_stride) {
     using P = Plan<LEN>;
@@ -357,10 +406,26 @@ __global__ void __launch_bounds__(ConvColCfg<T, LEN>::THREADS, ConvColCfg<T, LEN
         for (int r = 0; r < P::R1; ++r) v[u * P::R1 + r] = sm[L::at((t + TT * u) + P::S1 * r)];
     __syncthreads();                                   // everybody holds its inputs: the cells may be overwritten
     fft_inplace<T, P, L, CtaSync>(v, sm, t, tw_s, tw_s + LEN, 0);
+    if constexpr (SCATTER) {
+        const size_t pitch = (size_t)conv_pitch(a.nx);
+        const size_t cell = (size_t)(blockIdx.x % tiles_per_outer) * CW + c;     // (kyl, kx) inside the pencil plane
+        const size_t kyl = cell / pitch, kx = cell - kyl * pitch;
+        const size_t row = ((size_t)a.peers.src_first + kyl) * pitch + kx;       // the same entry inside a slab plane
+        const size_t plane = (size_t)a.peers.ny_full * pitch;
 #pragma unroll
-    for (int u = 0; u < E / P::RL; ++u)
+        for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
-        for (int r = 0; r < P::RL; ++r) a.V[base + (size_t)((t + TT * u) + P::SL * r) * stride] = v[u * P::RL + r];
+            for (int r = 0; r < P::RL; ++r) {
+                const int z = (t + TT * u) + P::SL * r;
+                const int o = a.peers.split.owner(z);
+                a.peers.vol[o][(size_t)(z - a.peers.split.first(o)) * plane + row] = v[u * P::RL + r];
+            }
+    } else {
+#pragma unroll
+        for (int u = 0; u < E / P::RL; ++u)
+#pragma unroll
+            for (int r = 0; r < P::RL; ++r) a.V[base + (size_t)((t + TT * u) + P::SL * r) * stride] = v[u * P::RL + r];
+    }
 }
 
 // fixed-order sum of the per-CTA partials: cost = alpha/2 * sum

@@ -11,6 +11,16 @@ struct wfm_conv {
     bool lite = false;                  // full complex work volume only (wfm_get_mtf)
     bool have_obj = false, have_data = false, have_w = false;
     std::string err;
+    // ---- z-sharded data term (wfm_conv_create_multi) ----------------------------------------------------------
+    // A PARENT (parts non-empty) owns one child per device; a CHILD holds the z-slab [z0, z0 + nz) of the real-space
+    // volumes (its nz is the slab's) plus the pencil volume Vp / Xp = all nz_all planes of its rows [y0, y0 + nyl).
+    std::vector<wfm_conv*> parts;
+    wfm_conv* parent = nullptr;
+    int part = 0, nz_all = 0, z0 = 0, y0 = 0, nyl = 0;
+    DevBuf Vp, Xp;
+    cudaEvent_t ev_pass = nullptr;      // "my scatter pass has been queued" (cross-device barrier, one per child)
+    bool multi() const { return !parts.empty(); }
+    size_t pvox() const { return (size_t)pitch() * nyl * nz_all; }   // entries of the pencil volume
     size_t vox() const { return (size_t)nx * ny * nz; }
     int pitch() const { return conv_pitch(nx); }
     size_t hvox() const { return (size_t)pitch() * ny * nz; }      // entries of the half-spectrum volume
@@ -92,6 +102,30 @@ template <typename T, int LEN, int STORE> int conv_cols(wfm_conv* c, ConvArgs<T>
     return WFM_OK;
 }
 
+// y pass of a z-sharded volume: the outputs land in the pencil volumes of their owners (ConvArgs::peers)
+template <typename T, int LEN> int conv_cols_scatter(wfm_conv* c, ConvArgs<T> a, int pitch) {
+    using Cfg = ConvColCfg<T, LEN>;
+    auto kfn = &k_conv_cols<T, LEN, CS_CPLX, true>;
+    if (Cfg::SMEM > 48 * 1024) WFM_CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    const size_t npix = (size_t)pitch * a.ny;
+    a.tw = (const cx<T>*)c->twx.p;
+    const unsigned grid = (unsigned)((size_t)a.nz * (pitch / Cfg::CW));
+    WFM_LAUNCH(kfn, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, c->stream, a, (size_t)pitch, pitch / Cfg::CW, npix);
+    WFM_CK_LAUNCH(c, "k_conv_cols (scatter)");
+    return WFM_OK;
+}
+// fused z pass on this device's pencil volume; the outputs land in the slab volumes of their owners
+template <typename T, int LEN, int MUL> int conv_cols_zz_scatter(wfm_conv* c, ConvArgs<T> a, int pitch) {
+    using Cfg = ConvColCfg<T, LEN>;
+    auto kfn = &k_conv_cols_zz<T, LEN, MUL, true>;
+    if (Cfg::SMEM > 48 * 1024) WFM_CK(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    const size_t npix = (size_t)pitch * a.ny;                 // a.ny = rows of the pencil volume (nyl)
+    a.tw = (const cx<T>*)c->twz.p;
+    WFM_LAUNCH(kfn, dim3((unsigned)(npix / Cfg::CW)), dim3(Cfg::THREADS), Cfg::SMEM, c->stream, a, npix, (int)(npix / Cfg::CW), (size_t)0);
+    WFM_CK_LAUNCH(c, "k_conv_cols_zz (scatter)");
+    return WFM_OK;
+}
+
 #define WFM_CONV_SWITCH(len, CALL)                                              \
     switch (len) {                                                              \
         case 32: { constexpr int L_ = 32; return CALL; }                        \
@@ -121,8 +155,17 @@ template <typename T, int LEN, int MUL> int conv_cols_zz(wfm_conv* c, ConvArgs<T
 template <int MUL> int conv_cols_zz_n(wfm_conv* c, const ConvArgs<double>& a, int pitch) {
     WFM_CONV_SWITCH(c->nz, (conv_cols_zz<double, L_, MUL>(c, a, pitch)))
 }
+int conv_cols_scatter_n(wfm_conv* c, const ConvArgs<double>& a, int pitch) {
+    WFM_CONV_SWITCH(c->ny, (conv_cols_scatter<double, L_>(c, a, pitch)))
+}
+template <int MUL> int conv_cols_zz_scatter_n(wfm_conv* c, const ConvArgs<double>& a, int pitch) {
+    WFM_CONV_SWITCH(c->nz_all, (conv_cols_zz_scatter<double, L_, MUL>(c, a, pitch)))
+}
 template <int STORE> int conv_cols_n(wfm_conv* c, const ConvArgs<double>& a, int axis, int pitch) {
     WFM_CONV_SWITCH(axis == 1 ? c->ny : c->nz, (conv_cols<double, L_, STORE>(c, a, axis, pitch)))
+}
+template <int STORE> int conv_cols_zall_n(wfm_conv* c, const ConvArgs<double>& a, int pitch) {      // z pass of length nz_all
+    WFM_CONV_SWITCH(c->nz_all, (conv_cols<double, L_, STORE>(c, a, 2, pitch)))
 }
 template <int STORE> int conv_r2c_n(wfm_conv* c, const ConvArgs<double>& a) {
     WFM_CONV_SWITCH(c->nx, (conv_rows_r2c<double, L_, STORE>(c, a)))
@@ -144,20 +187,30 @@ ConvArgs<double> conv_args(wfm_conv* c) {
 
 }  // namespace
 
+namespace wfm_multi {
+int conv_destroy(wfm_conv* p);
+int conv_scatter_host(wfm_conv* p, const void* host, DevBuf wfm_conv::*buf);
+int conv_set_object(wfm_conv* p, const void* obj_host);
+int conv_cost_and_gradient_host(wfm_conv* p, double alpha, const void* h_host, void* grad_host, int clr, double* cost);
+int eval_fg(wfm_model* h, wfm_conv* p, int param, int n, double alpha, double* cost, double* grad_out, unsigned kinds);
+}  // namespace wfm_multi
+
 extern "C" {
 
-static int conv_create_impl(wfm_conv** out, int nx, int ny, int nz, int precision, int device, bool lite);
+static int conv_create_impl(wfm_conv** out, int nx, int ny, int nz, int precision, int device, bool lite, int slab_of = 0);
 
 int wfm_conv_create(wfm_conv** out, int nx, int ny, int nz, int precision, int device) {
     return conv_create_impl(out, nx, ny, nz, precision, device, false);
 }
 
 // lite: only the work volume and the twiddles (3-D transform helper of wfm_get_mtf)
-static int conv_create_impl(wfm_conv** out, int nx, int ny, int nz, int precision, int device, bool lite) {
+// slab_of > 0: a child of a z-sharded data term -- nz is the slab's plane count, slab_of the length of the z transform
+static int conv_create_impl(wfm_conv** out, int nx, int ny, int nz, int precision, int device, bool lite, int slab_of) {
     if (!out) { g_create_error = "out is NULL"; return WFM_ERR_INVALID_ARG; }
     *out = nullptr;
     if (nx != ny) { g_create_error = "Nx should equal Ny"; return WFM_ERR_INVALID_ARG; }
-    if (!supported_n(nx) || !supported_n(nz)) { g_create_error = "Nx and Nz must be powers of two in [32, 2048]"; return WFM_ERR_UNSUPPORTED; }
+    const int nz_fft = slab_of > 0 ? slab_of : nz;
+    if (!supported_n(nx) || !supported_n(nz_fft) || nz < 1) { g_create_error = "Nx and Nz must be powers of two in [32, 2048]"; return WFM_ERR_UNSUPPORTED; }
     if (precision != WFM_F64) { g_create_error = "the convolution data term is fp64 only in this revision"; return WFM_ERR_UNSUPPORTED; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -166,7 +219,7 @@ static int conv_create_impl(wfm_conv** out, int nx, int ny, int nz, int precisio
     if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return WFM_ERR_INVALID_ARG; }
     wfm_conv* c = new (std::nothrow) wfm_conv();
     if (!c) { g_create_error = "out of host memory"; return WFM_ERR_NOMEM; }
-    c->nx = nx; c->ny = ny; c->nz = nz; c->precision = precision; c->device = device; c->lite = lite;
+    c->nx = nx; c->ny = ny; c->nz = nz; c->nz_all = nz_fft; c->precision = precision; c->device = device; c->lite = lite;
     auto bail = [&](int code, const char* what) { g_create_error = what; wfm_conv_destroy(c); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(WFM_ERR_CUDA, "cudaSetDevice failed");
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(WFM_ERR_CUDA, "cudaStreamCreate failed");
@@ -175,7 +228,7 @@ static int conv_create_impl(wfm_conv** out, int nx, int ny, int nz, int precisio
     if (c->V.ensure(16 * (lite ? vox : c->hvox())) || c->cost_dev.ensure(8) || c->cost_part.ensure(8 * ((size_t)ny * nz + 8)) ||
         (!lite && (c->X.ensure(16 * c->hvox()) || c->y.ensure(8 * vox) || c->R.ensure(8 * vox))))
         return bail(WFM_ERR_NOMEM, "device allocation failed");
-    if (conv_upload_twiddles(c, c->twx, nx) != WFM_OK || conv_upload_twiddles(c, c->twz, nz) != WFM_OK ||
+    if (conv_upload_twiddles(c, c->twx, nx) != WFM_OK || conv_upload_twiddles(c, c->twz, nz_fft) != WFM_OK ||
         conv_upload_twiddles(c, c->twh, nx / 2) != WFM_OK || conv_upload_twiddles(c, c->twn, nx / 2, nx) != WFM_OK)
         return bail(WFM_ERR_CUDA, "twiddle upload failed");
     *out = c;
@@ -184,6 +237,7 @@ static int conv_create_impl(wfm_conv** out, int nx, int ny, int nz, int precisio
 
 int wfm_conv_destroy(wfm_conv* c) {
     if (!c) return WFM_OK;
+    if (c->multi()) return wfm_multi::conv_destroy(c);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->V, &c->X, &c->y, &c->w, &c->R, &c->hdev, &c->gdev, &c->cost_part, &c->cost_dev, &c->twx, &c->twz,
@@ -198,6 +252,7 @@ const char* wfm_conv_last_error(const wfm_conv* c) { return c ? c->err.c_str() :
 
 int wfm_conv_set_stream(wfm_conv* c, void* s) {
     if (!c) return WFM_ERR_INVALID_ARG;
+    if (c->multi()) return c->fail(WFM_ERR_UNSUPPORTED, "a z-sharded data term runs every device on its own stream");
     WFM_ENTER(c);
     cudaStreamSynchronize(c->stream);
     c->stream = s ? (cudaStream_t)s : c->own_stream;
@@ -208,6 +263,7 @@ int wfm_conv_set_stream(wfm_conv* c, void* s) {
 int wfm_conv_set_object(wfm_conv* c, const void* obj_host) {
     if (!c) return WFM_ERR_INVALID_ARG;
     if (!obj_host) return c->fail(WFM_ERR_INVALID_ARG, "object is NULL");
+    if (c->multi()) return wfm_multi::conv_set_object(c, obj_host);
     WFM_ENTER(c);
     WFM_CK(c, c->hdev.ensure(8 * c->vox()));
     WFM_CK(c, cudaMemcpyAsync(c->hdev.p, obj_host, 8 * c->vox(), cudaMemcpyHostToDevice, c->stream));
@@ -224,6 +280,11 @@ int wfm_conv_set_object(wfm_conv* c, const void* obj_host) {
 int wfm_conv_set_data(wfm_conv* c, const void* y_host) {          // fdata.setData(data)  PSF_Estimation.java:149
     if (!c) return WFM_ERR_INVALID_ARG;
     if (!y_host) return c->fail(WFM_ERR_INVALID_ARG, "data is NULL");
+    if (c->multi()) {
+        int rc = wfm_multi::conv_scatter_host(c, y_host, &wfm_conv::y);
+        if (!rc) { c->have_data = true; for (wfm_conv* k : c->parts) k->have_data = true; }
+        return rc;
+    }
     WFM_ENTER(c);
     WFM_CK(c, cudaMemcpyAsync(c->y.p, y_host, 8 * c->vox(), cudaMemcpyHostToDevice, c->stream));
     WFM_CK(c, cudaStreamSynchronize(c->stream));
@@ -233,6 +294,12 @@ int wfm_conv_set_data(wfm_conv* c, const void* y_host) {          // fdata.setDa
 
 int wfm_conv_set_weights(wfm_conv* c, const void* w_host) {       // fdata.setWeights(weights, true)  :150
     if (!c) return WFM_ERR_INVALID_ARG;
+    if (c->multi()) {
+        if (!w_host) { c->have_w = false; for (wfm_conv* k : c->parts) k->have_w = false; return WFM_OK; }
+        int rc = wfm_multi::conv_scatter_host(c, w_host, &wfm_conv::w);
+        if (!rc) { c->have_w = true; for (wfm_conv* k : c->parts) k->have_w = true; }
+        return rc;
+    }
     WFM_ENTER(c);
     if (!w_host) { c->have_w = false; return WFM_OK; }
     WFM_CK(c, c->w.ensure(8 * c->vox()));
@@ -247,6 +314,7 @@ int wfm_conv_set_weights(wfm_conv* c, const void* w_host) {       // fdata.setWe
 int wfm_conv_cost_and_gradient_dev(wfm_conv* c, double alpha, const void* h_dev, void* grad_dev, int clr, double* cost_dev) {
     if (!c) return WFM_ERR_INVALID_ARG;
     if (!h_dev || !grad_dev) return c->fail(WFM_ERR_INVALID_ARG, "h_dev / grad_dev is NULL");
+    if (c->multi() || c->parent) return c->fail(WFM_ERR_UNSUPPORTED, "z-sharded data term: use the host-buffer call or wfm_eval_fg");
     if (!c->have_obj || !c->have_data) return c->fail(WFM_ERR_STATE, "object and data must be set first");
     WFM_ENTER(c);
     ConvArgs<double> a = conv_args(c);
@@ -283,6 +351,10 @@ int wfm_conv_cost_and_gradient_dev(wfm_conv* c, double alpha, const void* h_dev,
 int wfm_conv_cost_and_gradient(wfm_conv* c, double alpha, const void* h_host, void* grad_host, int clr, double* cost) {
     if (!c) return WFM_ERR_INVALID_ARG;
     if (!h_host || !grad_host || !cost) return c->fail(WFM_ERR_INVALID_ARG, "h / grad / cost is NULL");
+    if (c->multi()) {
+        if (!c->have_obj || !c->have_data) return c->fail(WFM_ERR_STATE, "object and data must be set first");
+        return wfm_multi::conv_cost_and_gradient_host(c, alpha, h_host, grad_host, clr, cost);
+    }
     WFM_ENTER(c);
     const size_t bytes = 8 * c->vox();
     WFM_CK(c, c->hdev.ensure(bytes));
@@ -302,8 +374,21 @@ int wfm_conv_cost_and_gradient(wfm_conv* c, double alpha, const void* h_host, vo
 // Only x (n doubles) goes to the device and {cost, gX} come back.  param: WFM_DEFOCUS / WFM_PHASE / WFM_MODULUS.
 int wfm_eval_fg(wfm_model* h, wfm_conv* c, int param, const double* x, int n, double alpha, double* cost, double* grad_out) {
     if (!h || !c) return WFM_ERR_INVALID_ARG;
-    WFM_MULTI_NO(h, "wfm_eval_fg (the 3-D convolution crosses the z-slabs)");
     if (!cost || !grad_out) return h->fail(WFM_ERR_INVALID_ARG, "cost / grad_out is NULL");
+    if (h->multi() != c->multi()) return h->fail(WFM_ERR_INVALID_ARG, "model and data term must both be multi-device handles, or neither");
+    if (h->multi()) {                 // z-slabs on every device, transposes over NVLink peer memory (wfm_conv_multi.inl)
+        if (h->precision != WFM_F64) return h->fail(WFM_ERR_UNSUPPORTED, "wfm_eval_fg is fp64 only in this revision");
+        if (h->N != c->nx || h->nz_global != c->nz) return h->fail(WFM_ERR_INVALID_ARG, "model and data term must have the same shape");
+        int rcm; unsigned km;
+        switch (param) {
+            case WFM_DEFOCUS: rcm = x ? wfm_set_defocus(h, x, n) : WFM_OK; km = WFM_J_DEFOCUS; if (!x) n = h->ndefocus; break;
+            case WFM_PHASE: rcm = x ? wfm_set_phase(h, x, n) : WFM_OK; km = WFM_J_PHASE; break;
+            case WFM_MODULUS: rcm = x ? wfm_set_modulus(h, x, n) : WFM_OK; km = WFM_J_MODULUS; break;
+            default: return h->fail(WFM_ERR_INVALID_ARG, "DoubleShapedVector param does not belong to any space");
+        }
+        if (rcm) return rcm;
+        return wfm_multi::eval_fg(h, c, param, n, alpha, cost, grad_out, km);
+    }
     if (h->precision != WFM_F64) return h->fail(WFM_ERR_UNSUPPORTED, "wfm_eval_fg is fp64 only in this revision");
     if (h->N != c->nx || h->nz_global != c->nz || h->z0 != 0 || h->nzl != h->nz_global || h->nbatch != 1)
         return h->fail(WFM_ERR_INVALID_ARG, "model and data term must have the same (unsharded) shape");

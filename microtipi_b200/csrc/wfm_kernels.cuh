@@ -460,9 +460,7 @@ WFM_DEVI void pipe_wait(const unsigned* cnt, unsigned target, unsigned* err) {
 // CTA barrier (all stores of the item issued), then thread 0 fences at GPU scope and publishes --
 // the arrive half of a cooperative-groups grid barrier.
 WFM_DEVI void pipe_signal(unsigned* cnt) {
-#ifndef WFM_PROBE_NO_ITEM_SYNC    /* timing probe only (races, wrong results): what does the CTA barrier at the item boundary cost? */
     __syncthreads();
-#endif
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(cnt, 1u); }
 }
 

@@ -543,3 +543,13 @@ def test_multi_device_handle(lib):
     want = np.concatenate([ref.apply_J_defocus(q), ref.apply_J_phase(q), ref.apply_J_modulus(q)])
     assert o.rel_l2(grad.cpu().numpy(), want) <= 1e-12
     m.close()
+
+
+def test_z_sharded_data_term_and_inner_loop(lib):
+    """Row f1 across GPUs: wfm_conv_create_multi + wfm_eval_fg on min(2, device_count) devices (slabs <-> pencils
+    through peer stores) against the oracle."""
+    import torch
+    from tests.test_multi_device import conv_multi_case
+    n = min(2, torch.cuda.device_count())
+    conv_multi_case(lib, 128, 64, list(range(n)))
+    conv_multi_case(lib, 64, 128, list(range(n)))

@@ -166,3 +166,64 @@ def test_peer_memory_gradient_exchange_between_ranks(lib):
         m.exchangeClose()
     for m in models:
         m.close()
+
+
+def conv_multi_case(lib, N, Nz, devices):
+    """Body shared with the GPU test: the z-sharded data term against the oracle, and the one-call inner loop
+    (wfm_eval_fg on a multi model + multi data term) against the explicit oracle chain."""
+    from microtipi_b200 import WeightedConvolutionCost, DoubleShapedVectorSpace
+    rng = np.random.default_rng(5)
+    shp = (Nz, N, N)
+    obj, h, y = rng.normal(size=shp), rng.normal(size=shp), rng.normal(size=shp)
+    w = rng.uniform(0.0, 2.0, size=shp)
+    f = WeightedConvolutionCost.build(DoubleShapedVectorSpace(N, N, Nz), lib=lib, devices=devices)
+    assert lib.wfm_conv_parts(f.handle) == len(devices)
+    f.setPSF(obj); f.setData(y); f.setWeights(w, True)
+    g = np.zeros(h.size)
+    c = f.computeCostAndGradient(0.7, h, g, True)
+    c_ref, g_ref = o.weighted_convolution_cost(h, obj, y, w, 0.7)
+    assert abs(c - c_ref) <= 1e-12 * abs(c_ref)
+    assert o.rel_l2(g, g_ref) <= 1e-12
+    c2 = f.computeCostAndGradient(0.7, h, g, False)                      # accumulate (clr = false)
+    assert abs(c2 - c) <= 1e-14 * abs(c) and o.rel_l2(g, 2 * g_ref) <= 1e-12
+    f.setWeights(None)
+    c3 = f.computeCostAndGradient(1.0, h, g, True)
+    c3_ref, g3_ref = o.weighted_convolution_cost(h, obj, y)
+    assert abs(c3 - c3_ref) <= 1e-12 * abs(c3_ref) and o.rel_l2(g, g3_ref) <= 1e-12
+    # the inner loop of the PSF fit on the same devices
+    ref = o.WideFieldModelOracle((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"])
+    m = WideFieldModel((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, False, lib=lib,
+                       basis=oracle_basis(N), devices=devices)
+    for mm in (ref, m):
+        mm.setModulus(BETA4)
+    for flag, x, refset, refj in (
+            (m.PHASE, o.synthetic_alpha(10) + 0.01, ref.setPhase, ref.apply_J_phase),
+            (m.DEFOCUS, np.array([P["ni"] / P["lam"], 1e4, -1e4]), ref.setDefocus, ref.apply_J_defocus),
+            (m.MODULUS, np.array([1.0, 0.12, -0.04, 0.03]), ref.setModulus, ref.apply_J_modulus)):
+        cost, gx = f.evalFG(m, flag, x)
+        refset(x)
+        c_ref, q_ref = o.weighted_convolution_cost(ref.getPsf(), obj, y)
+        assert abs(cost - c_ref) <= 1e-11 * abs(c_ref)
+        assert o.rel_l2(gx, refj(q_ref)) <= 1e-10
+    f.close(); m.close()
+
+
+@pytest.mark.parametrize("N,Nz,devices", [(32, 32, [0, 1]), (32, 64, [1, 3, 0]), (64, 32, [0, 1, 2, 3]), (32, 32, [2])])
+def test_z_sharded_data_term_and_inner_loop(lib, N, Nz, devices):
+    conv_multi_case(lib, N, Nz, devices)
+
+
+def test_z_sharded_data_term_errors(lib):
+    from microtipi_b200 import WeightedConvolutionCost, DoubleShapedVectorSpace
+    with pytest.raises(ValueError):
+        WeightedConvolutionCost.build(DoubleShapedVectorSpace(32, 32, 32), lib=lib, devices=[0, 0])
+    f = WeightedConvolutionCost.build(DoubleShapedVectorSpace(32, 32, 32), lib=lib, devices=[0, 1])
+    m1 = WideFieldModel((32, 32, 32), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib, basis=oracle_basis(32))
+    f.setPSF(np.ones((32, 32, 32))); f.setData(np.zeros((32, 32, 32)))
+    with pytest.raises(ValueError, match="multi-device"):
+        f.evalFG(m1, m1.PHASE, np.zeros(10))                                # single-device model, sharded data term
+    m3 = WideFieldModel((32, 32, 32), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib, basis=oracle_basis(32),
+                        devices=[0, 1, 2])
+    with pytest.raises(ValueError, match="different device lists"):
+        f.evalFG(m3, m3.PHASE, np.zeros(10))
+    f.close(); m1.close(); m3.close()

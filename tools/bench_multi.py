@@ -27,6 +27,8 @@ ap.add_argument("--nxy", type=int, default=512)
 ap.add_argument("--nz-per-device", type=int, default=256)
 ap.add_argument("--steps", type=int, default=30)
 ap.add_argument("--e2e-steps", type=int, default=5)
+ap.add_argument("--eval-fg", action="store_true", help="also time wfm_eval_fg with the z-sharded data term")
+ap.add_argument("--strong", action="store_true", help="keep the TOTAL stack at --nz-per-device planes (strong scaling)")
 a = ap.parse_args()
 P = dict(NA=1.4, lam=542e-9, ni=1.518, dxy=64.5e-9, dz=160e-9)
 lib = capi.load_library()
@@ -35,7 +37,7 @@ ndev = a.devices or ndev_all
 
 
 def run(n_dev):
-    N, nz = a.nxy, a.nz_per_device * n_dev
+    N, nz = a.nxy, (a.nz_per_device if a.strong else a.nz_per_device * n_dev)
     m = WideFieldModel((N, N, nz), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, False,
                        devices=list(range(n_dev)))
     parts = m.parts()
@@ -95,9 +97,28 @@ def run(n_dev):
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / a.e2e_steps
     lib.wfm_host_free(hq); lib.wfm_host_free(hp)
+    out = {"n_dev": n_dev, "planes": nz, "device_ms_per_step": dev_ms, "device_planes_per_s": nz / (dev_ms * 1e-3),
+           "e2e_ms_per_step": e2e_ms, "e2e_planes_per_s": nz / (e2e_ms * 1e-3), "e2e_bytes_per_step": 2 * vox * 8}
+    # config 3 inner loop on the same devices: PSF + z-sharded FFT-convolution data term + Jacobian, one call
+    if a.eval_fg and nz in (32, 64, 128, 256, 512, 1024, 2048):
+        from microtipi_b200 import WeightedConvolutionCost, DoubleShapedVectorSpace
+        f = WeightedConvolutionCost.build(DoubleShapedVectorSpace(N, N, nz), devices=list(range(n_dev)))
+        obj = np.zeros((nz, N, N))
+        obj[:3, :3, :3] = 1.0
+        f.setPSF(obj)
+        del obj
+        f.setData(np.random.default_rng(7).random((nz, N, N)) * 1e-6)
+        f.evalFG(m, m.PHASE, alpha)
+        t0 = time.perf_counter()
+        for i in range(a.e2e_steps):
+            cost, g = f.evalFG(m, m.PHASE, alpha + 1e-3 * (i % 7))
+        fg_ms = (time.perf_counter() - t0) * 1e3 / a.e2e_steps
+        assert np.isfinite(cost) and np.all(np.isfinite(g))
+        out["eval_fg_ms"] = fg_ms
+        out["eval_fg_planes_per_s"] = nz / (fg_ms * 1e-3)
+        f.close()
     m.close()
-    return {"n_dev": n_dev, "planes": nz, "device_ms_per_step": dev_ms, "device_planes_per_s": nz / (dev_ms * 1e-3),
-            "e2e_ms_per_step": e2e_ms, "e2e_planes_per_s": nz / (e2e_ms * 1e-3), "e2e_bytes_per_step": 2 * vox * 8}
+    return out
 
 
 one = run(1)
@@ -108,4 +129,6 @@ if ndev > 1:
     res["all_devices"] = many
     res["device_efficiency"] = many["device_planes_per_s"] / (ndev * one["device_planes_per_s"])
     res["e2e_efficiency"] = many["e2e_planes_per_s"] / (ndev * one["e2e_planes_per_s"])
+    if "eval_fg_ms" in many and "eval_fg_ms" in one:
+        res["eval_fg_efficiency"] = many["eval_fg_planes_per_s"] / (ndev * one["eval_fg_planes_per_s"])
 print(json.dumps(res))
