@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -411,21 +411,15 @@ def run_b200(args):
 
     cfg_id = args.config
     single = args.single
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()       # nvidia-smi needs a few hundred ms before its first sample: started before the set-up
     w, planes_global, cfg = make(cfg_id, args.n, args.nz, single, args.kinds)
     N, nzl, nzg = w.n, w.nzl, w.nzg
     es = w.es
     warm = max(args.warmup, 3)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()                           # nvidia-smi needs a few hundred ms before its first sample
-    t_w = time.perf_counter()
-    i = 0
-    while i < warm or (not args.quick and time.perf_counter() - t_w < 0.4):
+    for i in range(warm):
         w.step(i)
-        i += 1
-        if i % 16 == 0:
-            torch.cuda.synchronize()
-    warm = i
     fence()
     # ---- timed region: K steps --------------------------------------------------------------------------------
     n0 = lib.wfm_launch_count()

@@ -51,8 +51,11 @@ def run(n_dev):
     alpha = np.random.default_rng(1234).normal(0.0, 0.3, 10)
     qptrs = [q.data_ptr() for q in qs]
 
+    x = m.parameterCoefs[m.PHASE]                                    # PSF_Estimation.java:117
+
     def step(i):
-        m.setPhase(alpha + 1e-3 * (i % 7))
+        x.data[:] = alpha + 1e-3 * (i % 7)
+        m.setParam(x)                                                  # PSF_Estimation.java:202 (no basis rebuild)
         m.computePsf()
         m.applyJacobianDeviceMulti(2, qptrs, grad.data_ptr())
 
