@@ -78,9 +78,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, window=None):
+        """Summary of the samples taken inside `window` = (t0, t1) on the perf_counter clock (widened by 60 ms on both
+        sides, one sampling period plus nvidia-smi's own latency; all samples when no window is given)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         self.proc.terminate()
@@ -90,17 +92,18 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
             try:
-                clk, cmax, util = float(f[0]), float(f[1]), float(f[2])
+                clk, cmax = float(f[0]), float(f[1])
             except ValueError:
                 continue
             mx.append(cmax)
-            if util > 0:
-                sm.append(clk)
+            if window is not None and not (window[0] - 0.06 <= ts <= window[1] + 0.06):
+                continue
+            sm.append(clk)
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
@@ -418,6 +421,7 @@ def run_b200(args):
     N, nzl, nzg = w.n, w.nzl, w.nzg
     es = w.es
     warm = max(args.warmup, 3)
+    t_clock0 = time.perf_counter()
     for i in range(warm):
         w.step(i)
     fence()
@@ -448,7 +452,8 @@ def run_b200(args):
             w.step(b * blk + i)
         evs[b + 1].record()
     fence()
-    clocks = sampler.stop() if rank == 0 else None       # sampled over the lead-in, the timed K steps and these two passes
+    # clocks: the samples that fall between the first warm-up step and the end of this pass (same kernels throughout)
+    clocks = sampler.stop((t_clock0, time.perf_counter())) if rank == 0 else None
     per_step = sorted(evs[b].elapsed_time(evs[b + 1]) / blk for b in range(nblk))
     dist_ms = {"median": max_over_ranks(per_step[len(per_step) // 2]), "best": max_over_ranks(per_step[0]),
                "worst": max_over_ranks(per_step[-1]), "blocks": nblk, "steps_per_block": blk}
@@ -471,8 +476,9 @@ def run_b200(args):
             w.step(i)
         if rank == 0:
             s2.start()
+        t_s0 = time.perf_counter()
         ms_s = timed(w, nsteps, 0)
-        c2 = s2.stop() if rank == 0 else None
+        c2 = s2.stop((t_s0 + 0.1, time.perf_counter())) if rank == 0 else None
         sustained = {"steps": nsteps, "seconds": ms_s * 1e-3, "ms_per_step": ms_s / nsteps,
                      "value": planes_global * nsteps / (ms_s * 1e-3), "clocks": c2}
 
