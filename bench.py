@@ -431,7 +431,7 @@ def run_b200(args):
     launches = lib.wfm_launch_count() - n0
     value = planes_global * args.steps / (ms * 1e-3)
     gsum = float(w.grad.abs().sum().item())
-    if not os.environ.get("WFM_PIPE_ROLES"):                       # (single-role profiling runs compute garbage)
+    if not os.environ.get("WFM_PIPE_ROLES") and not os.environ.get("WFM_BENCH_NO_CHECK"):   # (timing probes compute garbage)
         assert np.isfinite(gsum) and gsum > 0.0, "gradient is not finite / zero"
 
     # ---- per-kernel durations (roofline): the same K steps with an event pair around every kernel group ---------

@@ -4,7 +4,9 @@
 // IllegalArgumentException sites) plus the kernel launches.  WFM = WideFieldModel.java.
 #include "../../include/wfm_b200.h"
 #include "wfm_kernels.cuh"
+#include "wfm_generic.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -79,6 +81,8 @@ struct wfm_model {
     int ncells = 0;
     // FFT twiddles
     DevBuf tw;
+    bool generic = false;                         // N is not one of the pipeline plans: any-N path (wfm_generic.cuh)
+    DevBuf tw64;                                  // any-N path: W_N^m in double (also in fp32 mode)
     // outputs + PState (MicroscopeModel.java:42)
     DevBuf cpx, psf;
     int pstate = 0;
@@ -214,6 +218,16 @@ template <typename T> int col_tile(int N) {
 
 int upload_twiddles(wfm_model* h) {
     const int N = h->N;
+    if (h->generic) {
+        std::vector<double2> t(N);
+        for (int m = 0; m < N; ++m) {
+            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)N;
+            t[m].x = (double)cosl(a); t[m].y = (double)(-sinl(a));
+        }
+        WFM_CK(h, h->tw64.ensure(sizeof(double2) * N));
+        WFM_CK(h, cudaMemcpy(h->tw64.p, t.data(), sizeof(double2) * N, cudaMemcpyHostToDevice));
+        return WFM_OK;
+    }
     if (h->precision == WFM_F64) {
         std::vector<double2> t(N);
         for (int m = 0; m < N; ++m) {
@@ -256,7 +270,7 @@ int rebuild_activity(wfm_model* h) {
     h->narrow = getenv("WFM_NO_NARROW") == nullptr;
     for (int x : ax) if (x >= N / 4 && x < N - N / 4) h->narrow = false;
     for (int y : ay) if (y >= N / 4 && y < N - N / 4) h->narrow = false;
-    const int C = h->precision == WFM_F64 ? col_tile<double>(N) : col_tile<float>(N);
+    const int C = h->generic ? 4 : (h->precision == WFM_F64 ? col_tile<double>(N) : col_tile<float>(N));
     h->pitch = (h->nax + C - 1) / C * C;
     h->ctile = C;
     WFM_CK(h, h->act_x.ensure(sizeof(int) * ax.size()));
@@ -392,6 +406,65 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
     return WFM_OK;
 }
 
+// z-sums and basis contractions of the per-plane integrands (shared by the pipelines and the any-N path)
+int launch_jac_reduce(wfm_model* h, unsigned kinds, const Geom& g, const double* Gj, const double* Gm, int last_plane_only,
+                      double* grad_dev) {
+    {
+        KernelSpan span(h, WFM_K_JAC_REDUCE);
+        if (!h->basis_packed && h->nzern > 0 && h->ncells > 0) {
+            WFM_CK(h, h->Zs.ensure(sizeof(double) * (size_t)h->nzern * h->ncells));
+            auto kpk = &k_pack_basis;
+            WFM_LAUNCH(kpk, dim3((h->ncells + 255) / 256), dim3(256), 0, h->stream, (double*)h->Zs.p,
+                       (const double*)h->Z.p, (const int*)h->in_list.p, h->ncells, h->nzern, h->npix());
+            WFM_CK_LAUNCH(h, "k_pack_basis");
+            h->basis_packed = true;
+        }
+        ReduceArgs r;
+        r.g = g; r.Gj = Gj; r.Gm = Gm; r.pitch = h->pitch;
+        r.Zs = (const double*)h->Zs.p; r.psi = (const double*)h->psi.p; r.flags = (const uint8_t*)h->s_flags.p;
+        r.cell_list = (const int*)h->cell_list.p; r.in_list = (const int*)h->in_list.p; r.ncells = h->ncells;
+        r.nphase = h->nphase; r.nmod = h->nmod; r.phase_off = h->radial ? 1 : 3;
+        r.kinds = kinds; r.last_plane_only = last_plane_only;
+        r.dxy = h->dxy; r.lambda_ni = h->lambda_ni; r.deltaX = h->deltaX; r.deltaY = h->deltaY;
+        r.glen = h->glen();
+        const bool batch = h->nbatch > 1;
+        r.bpar = batch ? (const double*)h->bpar_dev.p : nullptr;
+        r.cpm = (h->nzm + WFM_RED_CHUNK_PLANES - 1) / WFM_RED_CHUNK_PLANES;
+        const int nblocks = h->ncells > 0 ? (h->ncells + WFM_RED_THREADS - 1) / WFM_RED_THREADS : 1;
+        const int nchunks = r.cpm * h->nbatch;
+        WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * nchunks * r.glen));
+        r.block_part = (double*)h->block_part.p;
+        auto kred = &k_jac_reduce;
+        WFM_LAUNCH_PDL(kred, dim3(nblocks, nchunks), dim3(WFM_RED_THREADS), 0, h->stream, r);
+        WFM_CK_LAUNCH(h, "k_jac_reduce");
+        double nbeta = 0.0;
+        if (h->nmod > 0) {
+            double s = 0.0;
+            for (int k = 0; k < h->nmod; ++k) s += h->beta.v[k] * h->beta.v[k];
+            nbeta = 1.0 / std::sqrt(s);                                        // WFM:435
+        }
+        XchgArgs xc;
+        memset(&xc, 0, sizeof(xc));
+        if (h->xchg && h->xchg->connected) {                 // sum over the ranks inside k_jac_final (peer memory)
+            Exchange* x = h->xchg;
+            if (batch) return h->fail(WFM_ERR_UNSUPPORTED, "the peer-memory gradient exchange needs a single-model handle");
+            if (r.glen > x->glen_cap) return h->fail(WFM_ERR_STATE, "gradient vector longer than the exchange buffer: reconnect");
+            xc.world = x->world; xc.rank = x->rank; xc.epoch = ++x->epoch;
+            for (int k = 0; k < x->world; ++k) {
+                xc.slots[k] = (double*)x->mapped[k];
+                xc.flags[k] = (unsigned*)((char*)x->mapped[k] + x->slot_bytes);
+            }
+            xc.ticket = (unsigned*)x->local.p; xc.err = (unsigned*)x->local.p + 1;
+        }
+        auto kfin = &k_jac_final;
+        WFM_LAUNCH_PDL(kfin, dim3(r.glen, h->nbatch), dim3(WFM_FINAL_THREADS), 0, h->stream, (const double*)r.block_part,
+                   nblocks * r.cpm, r.glen, h->nphase, g.psf_norm, h->beta, nbeta, kinds,
+                   batch ? (const double*)h->beta_dev.p : (const double*)nullptr, h->nmod, r.bpar, grad_dev, xc);
+        WFM_CK_LAUNCH(h, "k_jac_final");
+    }
+    return WFM_OK;
+}
+
 // ---- apply_J_* ------------------------------------------------------------------------------------
 template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev) {
     using Cfg = PipeCfg<T, N>;
@@ -430,60 +503,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         WFM_CK_LAUNCH(h, "k_jac_pipeline");
         h->pipe_checks++;
     }
-    {
-        KernelSpan span(h, WFM_K_JAC_REDUCE);
-        if (!h->basis_packed && h->nzern > 0 && h->ncells > 0) {
-            WFM_CK(h, h->Zs.ensure(sizeof(double) * (size_t)h->nzern * h->ncells));
-            auto kpk = &k_pack_basis;
-            WFM_LAUNCH(kpk, dim3((h->ncells + 255) / 256), dim3(256), 0, h->stream, (double*)h->Zs.p,
-                       (const double*)h->Z.p, (const int*)h->in_list.p, h->ncells, h->nzern, h->npix());
-            WFM_CK_LAUNCH(h, "k_pack_basis");
-            h->basis_packed = true;
-        }
-        ReduceArgs r;
-        r.g = a.g; r.Gj = a.Gj; r.Gm = a.Gm; r.pitch = h->pitch;
-        r.Zs = (const double*)h->Zs.p; r.psi = (const double*)h->psi.p; r.flags = (const uint8_t*)h->s_flags.p;
-        r.cell_list = (const int*)h->cell_list.p; r.in_list = (const int*)h->in_list.p; r.ncells = h->ncells;
-        r.nphase = h->nphase; r.nmod = h->nmod; r.phase_off = h->radial ? 1 : 3;
-        r.kinds = kinds; r.last_plane_only = a.last_plane_only;
-        r.dxy = h->dxy; r.lambda_ni = h->lambda_ni; r.deltaX = h->deltaX; r.deltaY = h->deltaY;
-        r.glen = h->glen();
-        const bool batch = h->nbatch > 1;
-        r.bpar = batch ? (const double*)h->bpar_dev.p : nullptr;
-        r.cpm = (h->nzm + WFM_RED_CHUNK_PLANES - 1) / WFM_RED_CHUNK_PLANES;
-        const int nblocks = h->ncells > 0 ? (h->ncells + WFM_RED_THREADS - 1) / WFM_RED_THREADS : 1;
-        const int nchunks = r.cpm * h->nbatch;
-        WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * nchunks * r.glen));
-        r.block_part = (double*)h->block_part.p;
-        auto kred = &k_jac_reduce;
-        WFM_LAUNCH_PDL(kred, dim3(nblocks, nchunks), dim3(WFM_RED_THREADS), 0, h->stream, r);
-        WFM_CK_LAUNCH(h, "k_jac_reduce");
-        double nbeta = 0.0;
-        if (h->nmod > 0) {
-            double s = 0.0;
-            for (int k = 0; k < h->nmod; ++k) s += h->beta.v[k] * h->beta.v[k];
-            nbeta = 1.0 / std::sqrt(s);                                        // WFM:435
-        }
-        XchgArgs xc;
-        memset(&xc, 0, sizeof(xc));
-        if (h->xchg && h->xchg->connected) {                 // sum over the ranks inside k_jac_final (peer memory)
-            Exchange* x = h->xchg;
-            if (batch) return h->fail(WFM_ERR_UNSUPPORTED, "the peer-memory gradient exchange needs a single-model handle");
-            if (r.glen > x->glen_cap) return h->fail(WFM_ERR_STATE, "gradient vector longer than the exchange buffer: reconnect");
-            xc.world = x->world; xc.rank = x->rank; xc.epoch = ++x->epoch;
-            for (int k = 0; k < x->world; ++k) {
-                xc.slots[k] = (double*)x->mapped[k];
-                xc.flags[k] = (unsigned*)((char*)x->mapped[k] + x->slot_bytes);
-            }
-            xc.ticket = (unsigned*)x->local.p; xc.err = (unsigned*)x->local.p + 1;
-        }
-        auto kfin = &k_jac_final;
-        WFM_LAUNCH_PDL(kfin, dim3(r.glen, h->nbatch), dim3(WFM_FINAL_THREADS), 0, h->stream, (const double*)r.block_part,
-                   nblocks * r.cpm, r.glen, h->nphase, a.g.psf_norm, h->beta, nbeta, kinds,
-                   batch ? (const double*)h->beta_dev.p : (const double*)nullptr, h->nmod, r.bpar, grad_dev, xc);
-        WFM_CK_LAUNCH(h, "k_jac_final");
-    }
-    return WFM_OK;
+    return launch_jac_reduce(h, kinds, a.g, a.Gj, a.Gm, a.last_plane_only, grad_dev);
 }
 
 #ifdef WFM_ONLY_512
@@ -509,8 +529,87 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     }
 #endif
 
-template <typename T> int dispatch_psf(wfm_model* h) { WFM_DISPATCH_N(launch_psf, h) }
+// ---- any-N path (wfm_generic.cuh): the same pruned row-column transform as plain DFT sums ------------------
+struct GenPlan { int chunk; size_t s_elems, t_elems; };
+GenPlan plan_generic(const wfm_model* h) {
+    GenPlan p;
+    p.s_elems = (size_t)h->nay * h->nax;                 // active rows x columns
+    p.t_elems = (size_t)h->N * h->nax;                   // all rows x active columns
+    const size_t per_plane = 16 * (p.s_elems + p.t_elems);
+    size_t c = (256u << 20) / (per_plane ? per_plane : 1);
+    if (c < 1) c = 1;
+    if (c > (size_t)h->nzl) c = (size_t)h->nzl;
+    if (c > 4096) c = 4096;
+    p.chunk = (int)c;
+    return p;
+}
+dim3 gen_grid(int nx, int ny, int nz) { return dim3((nx + WFM_GEN_BX - 1) / WFM_GEN_BX, (ny + WFM_GEN_BY - 1) / WFM_GEN_BY, nz); }
+
+template <typename T> int launch_psf_generic(wfm_model* h) {
+    const GenPlan gp = plan_generic(h);
+    WFM_CK(h, h->scratch.ensure(16 * (gp.s_elems + gp.t_elems) * gp.chunk));
+    double2* S = (double2*)h->scratch.p;
+    double2* Tm = S + gp.s_elems * gp.chunk;
+    const Geom g = geom_of(h);
+    const dim3 blk(WFM_GEN_BX, WFM_GEN_BY);
+    if (h->copy_pending) WFM_CK(h, cudaStreamWaitEvent(h->stream, h->ev_copied, 0));
+    KernelSpan span(h, WFM_K_PSF);
+    for (int p0 = 0; p0 < h->nzl; p0 += gp.chunk) {
+        const int nb = std::min(gp.chunk, h->nzl - p0);
+        auto k1 = &k_gen_synth;
+        WFM_LAUNCH(k1, gen_grid(h->nax, h->nay, nb), blk, 0, h->stream, S, (const double*)h->rho.p, (const double*)h->phi.p,
+                   (const double*)h->psi.p, (const int*)h->act_x.p, (const int*)h->act_y.p, h->nax, h->nay, g, p0,
+                   h->precision == WFM_F32 ? 1 : 0);
+        auto k2 = &k_gen_dft_slow;
+        WFM_LAUNCH(k2, gen_grid(h->nax, h->N, nb), blk, 0, h->stream, Tm, (const double2*)S, (const double2*)h->tw64.p, h->N,
+                   h->nay, (const int*)h->act_y.p, h->N, (const int*)nullptr, h->nax);
+        auto k3 = &k_gen_psf_rows<T>;
+        WFM_LAUNCH(k3, gen_grid(h->N, h->N, nb), blk, 0, h->stream, (cx<T>*)h->cpx.p, (T*)h->psf.p, (const double2*)Tm,
+                   (const double2*)h->tw64.p, (const int*)h->act_x.p, h->nax, g, p0);
+    }
+    WFM_CK_LAUNCH(h, "any-N PSF kernels");
+    return WFM_OK;
+}
+
+template <typename T> int launch_jac_generic(wfm_model* h, unsigned kinds, const void* q_dev, double* grad_dev) {
+    int rc = pack_strip(h); if (rc) return rc;
+    const GenPlan gp = plan_generic(h);
+    WFM_CK(h, h->scratch.ensure(16 * (gp.s_elems + gp.t_elems) * gp.chunk));
+    double2* B = (double2*)h->scratch.p;
+    double2* U = B + gp.s_elems * gp.chunk;
+    const size_t img = (size_t)h->N * h->pitch;
+    WFM_CK(h, h->Gj.ensure(sizeof(double) * img * h->nzl));
+    if (kinds & WFM_J_MODULUS) WFM_CK(h, h->Gm.ensure(sizeof(double) * img * h->nzl));
+    const Geom g = geom_of(h);
+    const int last_plane_only = (h->modulus_mode == WFM_MODULUS_REFERENCE_LAST_PLANE) ? 1 : 0;
+    double* Gm = (kinds & WFM_J_MODULUS) ? (double*)h->Gm.p : nullptr;
+    const dim3 blk(WFM_GEN_BX, WFM_GEN_BY);
+    {
+        KernelSpan span(h, WFM_K_JAC);
+        for (int p0 = 0; p0 < h->nzl; p0 += gp.chunk) {
+            const int nb = std::min(gp.chunk, h->nzl - p0);
+            auto k1 = &k_gen_jac_rows<T>;
+            WFM_LAUNCH(k1, gen_grid(h->nax, h->N, nb), blk, 0, h->stream, U, (const cx<T>*)h->cpx.p, (const T*)q_dev,
+                       (const double2*)h->tw64.p, (const int*)h->act_x.p, h->nax, g, p0);
+            auto k2 = &k_gen_dft_slow;
+            WFM_LAUNCH(k2, gen_grid(h->nax, h->nay, nb), blk, 0, h->stream, B, (const double2*)U, (const double2*)h->tw64.p,
+                       h->N, h->N, (const int*)nullptr, h->nay, (const int*)h->act_y.p, h->nax);
+            auto k3 = &k_gen_jac_trig;
+            WFM_LAUNCH(k3, gen_grid(h->nax, h->nay, nb), blk, 0, h->stream, (double*)h->Gj.p, Gm, (const double2*)B, strip_of(h),
+                       (const int*)h->act_y.p, h->nax, h->nay, h->pitch, h->ctile, g, p0, last_plane_only,
+                       h->precision == WFM_F32 ? 1 : 0);
+        }
+        WFM_CK_LAUNCH(h, "any-N Jacobian kernels");
+    }
+    return launch_jac_reduce(h, kinds, g, (const double*)h->Gj.p, Gm, last_plane_only, grad_dev);
+}
+
+template <typename T> int dispatch_psf(wfm_model* h) {
+    if (h->generic) return launch_psf_generic<T>(h);
+    WFM_DISPATCH_N(launch_psf, h)
+}
 template <typename T> int dispatch_jac(wfm_model* h, unsigned kinds, const void* q, double* g) {
+    if (h->generic) return launch_jac_generic<T>(h, kinds, q, g);
     WFM_DISPATCH_N(launch_jac, h, kinds, q, g)
 }
 
@@ -672,8 +771,11 @@ static int create_impl(wfm_model** out, int nx, int ny, int nz_global, int z0, i
         g_create_error = "bad batch size"; return WFM_ERR_INVALID_ARG;
     }
     if (precision != WFM_F64 && precision != WFM_F32) { g_create_error = "bad precision"; return WFM_ERR_INVALID_ARG; }
-    if (!supported_n(nx)) {
-        g_create_error = "Nx must be a power of two in [32, 2048]"; return WFM_ERR_UNSUPPORTED;
+    const bool generic = !supported_n(nx);
+    if (generic && (nx < 2 || nx > 4096 || nbatch > 1)) {
+        g_create_error = nbatch > 1 ? "a batch handle needs Nx to be a power of two in [32, 2048]"
+                                    : "Nx must lie in [2, 4096] (powers of two in [32, 2048] take the fast pipelines)";
+        return WFM_ERR_UNSUPPORTED;
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -684,7 +786,7 @@ static int create_impl(wfm_model** out, int nx, int ny, int nz_global, int z0, i
     if (!h) { g_create_error = "out of host memory"; return WFM_ERR_NOMEM; }
     h->N = nx; h->nz_global = nz_global; h->z0 = z0; h->nzm = nz_local; h->nbatch = nbatch; h->nzl = nbatch * nz_local;
     h->dxy = dxy; h->dz = dz;
-    h->precision = precision; h->device = device;
+    h->precision = precision; h->device = device; h->generic = generic;
     if (nbatch > 1) h->bpar_h.assign(4 * (size_t)nbatch, 0.0);
     auto bail = [&](int code, const char* what) { g_create_error = what; wfm_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(WFM_ERR_CUDA, "cudaSetDevice failed");
@@ -734,7 +836,7 @@ int wfm_destroy(wfm_model* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->Z, &h->rho, &h->phi, &h->psi, &h->mask, &h->map, &h->support, &h->act_x, &h->inv_x,
                       &h->act_y, &h->inv_y, &h->cell_list, &h->in_list, &h->Zs, &h->s_rho, &h->s_phi, &h->s_psi, &h->s_flags, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gj, &h->Gm, &h->ctl, &h->block_part,
-                      &h->grad, &h->qdev, &h->alpha_dev, &h->beta_dev, &h->bpar_dev})
+                      &h->grad, &h->qdev, &h->alpha_dev, &h->beta_dev, &h->bpar_dev, &h->tw64})
         b->release();
     drain_spans(h);
     for (cudaEvent_t e : h->free_events) cudaEventDestroy(e);

@@ -35,7 +35,7 @@ def test_create_rejects_bad_arguments_like_the_reference(lib):
     h = C.c_void_p()
     assert lib.wfm_create(C.byref(h), 64, 32, 8, 1e-7, 1e-7, 0, 0) == capi.WFM_ERR_INVALID_ARG   # WFM:158
     assert b"Nx should equal Ny" in lib.wfm_last_error(None)
-    assert lib.wfm_create(C.byref(h), 96, 96, 8, 1e-7, 1e-7, 0, 0) == capi.WFM_ERR_UNSUPPORTED
+    assert lib.wfm_create(C.byref(h), 5000, 5000, 8, 1e-7, 1e-7, 0, 0) == capi.WFM_ERR_UNSUPPORTED   # any-N path: N <= 4096
     assert lib.wfm_create(C.byref(h), 64, 64, 0, 1e-7, 1e-7, 0, 0) == capi.WFM_ERR_INVALID_ARG
     assert lib.wfm_create_slab(C.byref(h), 64, 64, 8, 6, 4, 1e-7, 1e-7, 0, 0) == capi.WFM_ERR_INVALID_ARG
 

@@ -106,8 +106,8 @@ def test_escape_hatch_identical_pupils(lib):
 def test_error_behaviour_mirrors_reference(lib):
     with pytest.raises(ValueError, match="Nx should equal Ny"):       # WFM:158
         WideFieldModel((32, 64, 4), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib)
-    with pytest.raises(ValueError):                                   # not a supported power of two
-        WideFieldModel((48, 48, 4), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib)
+    with pytest.raises(ValueError):                                   # beyond the any-N path (N <= 4096)
+        WideFieldModel((5000, 5000, 4), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib)
     ref, m = make_pair(32, 2, lib)
     with pytest.raises(ValueError):                                   # quirk Q4: length-2 defocus
         m.setDefocus([1.0, 2.0])
@@ -361,3 +361,28 @@ def test_gpu_case_helpers_at_small_sizes(lib):
     full_stack_case(lib, 32, 96, 40, 50, False)
     full_stack_case(lib, 32, 16, 3, 9, True)
     escape_hatch_case(lib, ((32, 5, 0.2), (32, 3, 0.4)))
+
+
+@pytest.mark.parametrize("N,Nz,single", [(48, 3, False), (100, 2, False), (30, 4, True), (36, 2, False)])
+def test_any_n_path_matches_oracle(lib, N, Nz, single):
+    """Nx = Ny that is not a power of two in [32, 2048] (the reference's JTransforms takes any N, WFM:319): the
+    any-N kernels of wfm_generic.cuh against the oracle, all three Jacobians, both modulus modes, a z-slab."""
+    ref, m = make_pair(N, Nz, lib, single=single)
+    t = tol(single)
+    tj = 20 * t if single else t
+    np.testing.assert_array_equal(m.getRho(), ref.rho.ravel())
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= t
+    assert o.rel_l2(m.get_cpxPsf(), ref.get_cpxPsf()) <= t
+    q = o.synthetic_q(N, N, Nz, single=single)
+    d, p, mo = m.apply_J_all(q)
+    want = np.concatenate([ref.apply_J_defocus(q), ref.apply_J_phase(q), ref.apply_J_modulus(q)])
+    assert o.rel_l2(np.concatenate([d, p, mo]), want) <= tj
+    assert o.rel_l2(m.apply_J_phase(q).data, ref.apply_J_phase(q)) <= tj
+    m.setModulusMode(True)
+    ref.modulus_mode = o.MODULUS_REFERENCE_LAST_PLANE
+    assert o.rel_l2(m.apply_J_modulus(q).data, ref.apply_J_modulus(q)) <= tj
+    m.close()
+    if Nz >= 3:                                                         # z-slab of the any-N path (shard invariance)
+        _, part = make_pair(N, Nz, lib, single=single, z0=1, nz_local=Nz - 1)
+        assert o.rel_l2(part.getPsf(), ref.getPsf()[1:]) <= t
+        part.close()

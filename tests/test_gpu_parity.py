@@ -148,7 +148,7 @@ def test_errors(lib):
     with pytest.raises(ValueError, match="Nx should equal Ny"):
         WideFieldModel((64, 32, 4), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib)
     with pytest.raises(ValueError):
-        WideFieldModel((100, 100, 4), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib)
+        WideFieldModel((5000, 5000, 4), 10, 1, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], lib=lib)
     ref, m = make_pair(32, 2, lib)
     with pytest.raises(ValueError):
         m.setDefocus([1.0, 2.0])
@@ -553,3 +553,11 @@ def test_z_sharded_data_term_and_inner_loop(lib):
     n = min(2, torch.cuda.device_count())
     conv_multi_case(lib, 128, 64, list(range(n)))
     conv_multi_case(lib, 64, 128, list(range(n)))
+
+
+@pytest.mark.parametrize("N,Nz,single", [(100, 9, False), (384, 5, False), (48, 6, True), (1000, 2, False)])
+def test_any_n_path_matches_oracle(lib, N, Nz, single):
+    """Sizes off the pipeline plans (the reference's JTransforms takes any Nx == Ny, WFM:319): wfm_generic.cuh."""
+    ref, m = make_pair(N, Nz, lib, single=single)
+    _check_all(ref, m, N, Nz, single)
+    m.close()
