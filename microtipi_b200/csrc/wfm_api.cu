@@ -81,6 +81,7 @@ struct wfm_model {
     int ncells = 0;
     // FFT twiddles
     DevBuf tw;
+    DevBuf cis_tab;                               // (cos, sin)(2 pi k/64), k < 64: table of wfm_cis
     bool generic = false;                         // N is not one of the pipeline plans: any-N path (wfm_generic.cuh)
     DevBuf tw64;                                  // any-N path: W_N^m in double (also in fp32 mode)
     // outputs + PState (MicroscopeModel.java:42)
@@ -218,6 +219,15 @@ template <typename T> int col_tile(int N) {
 
 int upload_twiddles(wfm_model* h) {
     const int N = h->N;
+    {
+        std::vector<double2> e(WFM_CIS_ENTRIES);
+        for (int k = 0; k < WFM_CIS_ENTRIES; ++k) {
+            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)WFM_CIS_ENTRIES;
+            e[k].x = (double)cosl(a); e[k].y = (double)sinl(a);
+        }
+        WFM_CK(h, h->cis_tab.ensure(sizeof(double2) * WFM_CIS_ENTRIES));
+        WFM_CK(h, cudaMemcpy(h->cis_tab.p, e.data(), sizeof(double2) * WFM_CIS_ENTRIES, cudaMemcpyHostToDevice));
+    }
     if (h->generic) {
         std::vector<double2> t(N);
         for (int m = 0; m < N; ++m) {
@@ -395,6 +405,7 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
     a.inv_x = (const int*)h->inv_x.p;
     a.nax = h->nax; a.pitch = h->pitch;
     a.tw = (const cx<T>*)h->tw.p;
+    a.cis = (const double2*)h->cis_tab.p;
     a.T1 = (cx<T>*)h->scratch.p; a.cpx = (cx<T>*)h->cpx.p; a.psf = (T*)h->psf.p;
     PipeCtl ctl;
     rc = prepare_ctl(h, pp, ctl, pipe_roles()); if (rc) return rc;
@@ -491,6 +502,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     a.st = strip_of(h);
     a.inv_x = (const int*)h->inv_x.p; a.nax = h->nax; a.pitch = h->pitch;
     a.tw = (const cx<T>*)h->tw.p;
+    a.cis = (const double2*)h->cis_tab.p;
     a.T2 = (cx<T>*)h->scratch.p;
     a.Gj = (double*)h->Gj.p;
     a.Gm = (kinds & WFM_J_MODULUS) ? (double*)h->Gm.p : nullptr;
@@ -836,7 +848,7 @@ int wfm_destroy(wfm_model* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->Z, &h->rho, &h->phi, &h->psi, &h->mask, &h->map, &h->support, &h->act_x, &h->inv_x,
                       &h->act_y, &h->inv_y, &h->cell_list, &h->in_list, &h->Zs, &h->s_rho, &h->s_phi, &h->s_psi, &h->s_flags, &h->tw, &h->cpx, &h->psf, &h->scratch, &h->Gj, &h->Gm, &h->ctl, &h->block_part,
-                      &h->grad, &h->qdev, &h->alpha_dev, &h->beta_dev, &h->bpar_dev, &h->tw64})
+                      &h->grad, &h->qdev, &h->alpha_dev, &h->beta_dev, &h->bpar_dev, &h->tw64, &h->cis_tab})
         b->release();
     drain_spans(h);
     for (cudaEvent_t e : h->free_events) cudaEventDestroy(e);

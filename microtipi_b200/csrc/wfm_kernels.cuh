@@ -49,8 +49,42 @@ WFM_DEVI double defoc_depth_dev(int iz, int Nz, double dz) {
     return __dmul_rn((double)zi, dz);
 }
 WFM_DEVI int kappa_dev(int n, int N) { return (n > N / 2) ? n - N : n; }
+// ---- pupil trig ------------------------------------------------------------------------------------------
+// sin / cos of ph = phi + defoc_scale*psi (|ph| up to ~1e3 rad) for every active pixel of every plane, in both
+// pipelines.  CUDA's sincos(double) spends ~30 FP64 instructions plus ~30 UMOV / IMAD that materialise its 64-bit
+// polynomial coefficients (4.3 % of all issued instructions of k_psf_pipeline, profiles/r01p).  Here: e^{i ph} =
+// e^{i 2 pi k/64} * e^{i r} with k from a 64-entry table in shared memory (exact values, computed by the host in long
+// double) and |r| <= pi/64, where degree-9 / degree-8 Taylor polynomials are exact to 1e-20; the reduction
+// r = ph - n*(2 pi/64) is a two-term Cody-Waite with a 33-bit head (n*C1 exact for |n| < 2^20), so r carries
+// no rounding error of its own.  ~19 FP64 instructions and one LDS.128.  |ph| >= 2^20*(2 pi/64) falls back to sincos().
+#ifndef WFM_TABLE_CIS
+#define WFM_TABLE_CIS 1
+#endif
+#define WFM_CIS_ENTRIES 64
+WFM_DEVI void wfm_cis(double x, const double2* __restrict__ tab, double* s, double* c) {
+    const double t = x * 10.185916357881302;                 // 64 / (2 pi)
+    if (!(fabs(t) < 1048576.0)) { sincos(x, s, c); return; }
+    const double n = rint(t);
+    // 2 pi/64 = C1 + C2, C1 = the leading 33 bits
+    double r = fma(-n, 0x1.921fb54400000p-4 /* 0.09817477042088285 */, x);
+    r = fma(-n, 0x1.0b4611a626331p-38 /* 3.79818781656637e-12 */, r);
+    const double r2 = r * r;
+    double ps = fma(r2, 2.7557319223985893e-06, -1.984126984126984e-04);     // 1/9!, -1/7!
+    ps = fma(ps, r2, 8.333333333333333e-03);                                  // 1/5!
+    ps = fma(ps, r2, -1.6666666666666666e-01);                                // -1/3!
+    const double sr = fma(ps * r2, r, r);
+    double pc = fma(r2, 2.48015873015873e-05, -1.388888888888889e-03);       // 1/8!, -1/6!
+    pc = fma(pc, r2, 4.1666666666666664e-02);                                 // 1/4!
+    pc = fma(pc, r2, -0.5);
+    const double cr = fma(pc, r2, 1.0);
+    const double2 e = tab[(int)n & (WFM_CIS_ENTRIES - 1)];                    // (cos, sin) of 2 pi k/64
+    *c = fma(e.x, cr, -(e.y * sr));
+    *s = fma(e.x, sr, e.y * cr);
+}
 #ifdef WFM_FAKE_TRIG   /* profiling experiment only: how much of an item is the trig? */
 #define WFM_SINCOS(x, s, c) do { *(s) = (x) * 0.5; *(c) = 1.0 - (x); } while (0)
+#elif WFM_TABLE_CIS
+#define WFM_SINCOS(x, s, c) wfm_cis((x), cis_s, (s), (c))
 #else
 #define WFM_SINCOS(x, s, c) sincos((x), (s), (c))
 #endif
@@ -394,7 +428,8 @@ template <typename T, int N> struct PipeCfg {
     static constexpr int COLLEN = ColL::pad_c(N - 1) + 1;
     static constexpr int CELLS = C * (ROWLEN > COLLEN ? ROWLEN : COLLEN);
     static constexpr int TW2 = 16;                      // stage-2 base twiddles (R3 <= 16 entries)
-    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N + TW2) + sizeof(int) * (size_t)N;
+    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N + TW2) + sizeof(int) * (size_t)N +
+                                   sizeof(double2) * WFM_CIS_ENTRIES;         // + the e^{i 2 pi k/64} table of wfm_cis
     // resident CTAs per SM the register allocation is tuned for: 1024 threads (64 registers each)
     static constexpr int BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
     static constexpr int BY_SMEM = (int)((220 * 1024) / SMEM) < 1 ? 1 : (int)((220 * 1024) / SMEM);
@@ -589,6 +624,7 @@ template <typename T> struct PsfArgs {
     int nax;
     int pitch;          // nax rounded up to a multiple of the column tile
     const cx<T>* tw;    // W_N table (global; copied to shared memory once per CTA)
+    const double2* cis; // [64] (cos, sin)(2 pi k/64) for wfm_cis
     cx<T>* T1;          // ring: [ring][N][pitch]
     cx<T>* cpx;
     T* psf;
@@ -604,7 +640,7 @@ template <int R, bool NARROW> WFM_DEVI constexpr bool leg_live(int r) { return !
 
 template <typename T, int N, bool NARROW>
 WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int bm, int ringoff, cx<T>* cells, const cx<T>* tw_s,
-                            const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
+                            const double2* cis_s, const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
@@ -736,7 +772,9 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     cx<T>* tw_s = cells + Cfg::CELLS;
     cx<T>* tw2_s = tw_s + N;
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
+    double2* cis_s = reinterpret_cast<double2*>(invx_s + N);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
+    if (threadIdx.x < WFM_CIS_ENTRIES) cis_s[threadIdx.x] = a.cis[threadIdx.x];
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
     wfm_grid_dep_trigger();  // the next kernel's CTAs may take the place of ours as we exit
     wfm_grid_dep_wait();     // the tables above are constants; everything below depends on the previous kernel
@@ -755,7 +793,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                psf_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, it.ringoff, cells, tw_s, dep, qu, ctl);
+                psf_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, it.ringoff, cells, tw_s, cis_s, dep, qu, ctl);
             }
             qu.prefetch(ctl, P);
             pipe_signal(&ctl.cntA[it.plane]);
@@ -784,6 +822,7 @@ template <typename T> struct JacArgs {
     int nax;
     int pitch;         // nax rounded up to a multiple of the column tile
     const cx<T>* tw;
+    const double2* cis; // [64] (cos, sin)(2 pi k/64) for wfm_cis
     cx<T>* T2;         // ring: [ring][N][pitch]
     double* Gj;        // [nzl][N][pitch]  jin  = rho*(B_re sin ph + B_im cos ph)  on maskPupil
     double* Gm;        // [nzl][N][pitch]  J    = B_re cos ph - B_im sin ph        on the support (or NULL)
@@ -913,7 +952,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
 //   J   = B_re cos ph - B_im sin ph         on the support (WFM:607-611)
 template <typename T, int N, bool NARROW>
 WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int bm, int ringoff, cx<T>* cells, const cx<T>* tw_s,
-                            PipeQueue& qu, const PipeCtl& ctl) {
+                            const double2* cis_s, PipeQueue& qu, const PipeCtl& ctl) {
     using P = Plan<N>;
     constexpr int C = PipeCfg<T, N>::C, TT = P::T, E = P::E;
     using L = typename PipeCfg<T, N>::ColL;
@@ -975,7 +1014,9 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
     cx<T>* tw_s = cells + Cfg::CELLS;
     cx<T>* tw2_s = tw_s + N;
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
+    double2* cis_s = reinterpret_cast<double2*>(invx_s + N);
     for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
+    if (threadIdx.x < WFM_CIS_ENTRIES) cis_s[threadIdx.x] = a.cis[threadIdx.x];
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
     wfm_grid_dep_trigger();  // the next kernel's CTAs may take the place of ours as we exit
     wfm_grid_dep_wait();     // the tables above are constants; everything below depends on the previous kernel
@@ -1001,7 +1042,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
         } else {
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
-                jac_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, it.ringoff, cells, tw_s, qu, ctl);
+                jac_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, it.ringoff, cells, tw_s, cis_s, qu, ctl);
             }
             if (qu.prefetch(ctl, P)) JacClaimPrefetch<T, N>{a.cpx, a.q}(qu.peek_next());
             pipe_signal(&ctl.cntB[it.plane]);
