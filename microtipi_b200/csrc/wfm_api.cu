@@ -347,6 +347,7 @@ struct PipePlan { int ring, lag, nA, nB, grid; };
 PipePlan plan_pipeline(const wfm_model* h, int nA, int nB, size_t plane_bytes, int ctas_per_sm) {
     PipePlan p;
     p.nA = nA; p.nB = nB;
+    if (const char* e = getenv("WFM_PIPE_CTAS")) { int v = atoi(e); if (v >= 1 && v < ctas_per_sm) ctas_per_sm = v; }   // experiment knob
     const int nctas = h->num_sms * ctas_per_sm;
     // A CTA holds its current item plus, for the last part of it, the next one: ~1.3*nctas consecutive queue
     // entries are in flight, and B(p) must be queued about twice that far behind A(p) or its CTA stalls on
@@ -487,7 +488,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
             ctas_per_sm = Cfg::template minb_jac<true>();
         }
     }
-    int rc = set_smem(h, kfn, Cfg::SMEM); if (rc) return rc;
+    int rc = set_smem(h, kfn, Cfg::SMEM_JAC); if (rc) return rc;
     rc = pack_strip(h); if (rc) return rc;
     const int nA = N / Cfg::ROWS_PER_ITEM, nB = h->pitch / Cfg::C;
     const size_t plane_bytes = sizeof(cx<T>) * (size_t)N * h->pitch;
@@ -511,7 +512,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         PipeCtl ctl;
         rc = prepare_ctl(h, pp, ctl, pipe_roles()); if (rc) return rc;
         KernelSpan span(h, WFM_K_JAC);
-        WFM_LAUNCH_PDL(kfn, dim3(pp.grid), dim3(Cfg::THREADS), Cfg::SMEM, h->stream, a, ctl);
+        WFM_LAUNCH_PDL(kfn, dim3(pp.grid), dim3(Cfg::THREADS), Cfg::SMEM_JAC, h->stream, a, ctl);
         WFM_CK_LAUNCH(h, "k_jac_pipeline");
         h->pipe_checks++;
     }

@@ -35,6 +35,31 @@ template <typename T> using cx = typename Vec2<T>::type;
 template <typename T> WFM_DEVI cx<T> mkc(T a, T b) { cx<T> r; r.x = a; r.y = b; return r; }
 template <typename C> WFM_DEVI C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 template <typename C> WFM_DEVI C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+// fp32 mode: a complex add / subtract is ONE packed instruction on sm_100 (add.rn.f32x2 -> FADD2); the butterflies
+// are 52 of the 56 arithmetic instructions of a radix-8 transform
+#ifndef WFM_F32X2
+#define WFM_F32X2 1
+#endif
+#if WFM_F32X2 && !defined(WFM_EMU)
+template <> WFM_DEVI float2 cadd<float2>(float2 a, float2 b) {
+    unsigned long long ra, rb, rr;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rr) : "l"(ra), "l"(rb));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rr));
+    return r;
+}
+template <> WFM_DEVI float2 csub<float2>(float2 a, float2 b) {
+    unsigned long long ra, rb, rr;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rr) : "l"(ra), "l"(rb));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rr));
+    return r;
+}
+#endif
 template <typename C> WFM_DEVI C cmul(C a, C w) { C r; r.x = a.x * w.x - a.y * w.y; r.y = a.x * w.y + a.y * w.x; return r; }
 // x * (-i)
 template <typename C> WFM_DEVI C mul_neg_i(C a) { C r; r.x = a.y; r.y = -a.x; return r; }

@@ -58,7 +58,7 @@ WFM_DEVI int kappa_dev(int n, int N) { return (n > N / 2) ? n - N : n; }
 // r = ph - n*(2 pi/64) is a two-term Cody-Waite with a 33-bit head (n*C1 exact for |n| < 2^20), so r carries
 // no rounding error of its own.  ~19 FP64 instructions and one LDS.128.  |ph| >= 2^20*(2 pi/64) falls back to sincos().
 #ifndef WFM_TABLE_CIS
-#define WFM_TABLE_CIS 1
+#define WFM_TABLE_CIS 0   /* measured neutral against sincos() (0.8224 / 0.8290 vs 0.8204 / 0.8178 ms per step, A/B/A/B): kept as a knob */
 #endif
 #define WFM_CIS_ENTRIES 64
 WFM_DEVI void wfm_cis(double x, const double2* __restrict__ tab, double* s, double* c) {
@@ -428,8 +428,16 @@ template <typename T, int N> struct PipeCfg {
     static constexpr int COLLEN = ColL::pad_c(N - 1) + 1;
     static constexpr int CELLS = C * (ROWLEN > COLLEN ? ROWLEN : COLLEN);
     static constexpr int TW2 = 16;                      // stage-2 base twiddles (R3 <= 16 entries)
-    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + N + TW2) + sizeof(int) * (size_t)N +
+    // the engine reads tw[b] for b < N/R1 only (stage-1 base twiddles): the shared copy holds just those S1 entries
+    static constexpr int TW1 = P::S1;
+    static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + TW1 + TW2) + sizeof(int) * (size_t)N +
                                    sizeof(double2) * WFM_CIS_ENTRIES;         // + the e^{i 2 pi k/64} table of wfm_cis
+    // Jacobian row items: conj(a) rows arrive by bulk-async copy (TMA) in a per-group landing buffer, one row ahead
+    // (JAC_TMA); enabled where the landing buffers still fit beside MINB_JAC resident CTAs
+#ifndef WFM_JAC_TMA
+#define WFM_JAC_TMA 1
+#endif
+    static constexpr size_t LANDING = sizeof(cx<T>) * (size_t)C * N + 64;
     // resident CTAs per SM the register allocation is tuned for: 1024 threads (64 registers each)
     static constexpr int BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
     static constexpr int BY_SMEM = (int)((220 * 1024) / SMEM) < 1 ? 1 : (int)((220 * 1024) / SMEM);
@@ -452,6 +460,10 @@ template <typename T, int N> struct PipeCfg {
 #else
     template <bool NARROW> static constexpr int minb_jac() { return MINB_JAC; }
 #endif
+    // (N <= 512: at 1024 the landing buffers would cost a resident CTA)
+    static constexpr bool JAC_TMA = WFM_JAC_TMA && N >= 256 && N <= 512 &&
+                                    (SMEM + LANDING + 1024) * (size_t)MINB_JAC <= 233472;
+    static constexpr size_t SMEM_JAC = SMEM + (JAC_TMA ? LANDING : 0);
 };
 
 // type 0 = A, 1 = B, -1 = done; model = plane / nzm (batch handles: which model's pupil; 0 otherwise);
@@ -674,7 +686,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int bm, int ri
             v[e] = val;
         }
     }
-    fft_inplace<T, P, L, CtaSync, PipePrefetchHook<>, NARROW, WFM_PSF_TW_TREE>(v, cells + c, t, tw_s, tw_s + N, 0,
+    fft_inplace<T, P, L, CtaSync, PipePrefetchHook<>, NARROW, WFM_PSF_TW_TREE>(v, cells + c, t, tw_s, tw_s + PipeCfg<T, N>::TW1, 0,
                                                                                PipePrefetchHook<>{qu, ctl, a.g.nzl, NoClaimAction{}});
     pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
     cx<T>* dst = a.T1 + (size_t)ringoff + (size_t)sub * N * C + c;
@@ -743,7 +755,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ringoff, c
             v[e] = (leg_live<P::R1, NARROW>(e % P::R1) && xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
 #endif
 #endif
-        fft_inplace<T, P, L, RowSync<TT>, NoHook, NARROW, WFM_PSF_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
+        fft_inplace<T, P, L, RowSync<TT>, NoHook, NARROW, WFM_PSF_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
 #ifdef WFM_PROBE_PSF_L2ST          /* timing probe only (wrong results): stores that never reach DRAM */
         const size_t base = (size_t)N * (blockIdx.x * C + slot);
 #else
@@ -770,10 +782,10 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     using Cfg = PipeCfg<T, N>;
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
-    cx<T>* tw2_s = tw_s + N;
+    cx<T>* tw2_s = tw_s + Cfg::TW1;
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     double2* cis_s = reinterpret_cast<double2*>(invx_s + N);
-    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
+    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { if (i < Cfg::TW1) tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
     if (threadIdx.x < WFM_CIS_ENTRIES) cis_s[threadIdx.x] = a.cis[threadIdx.x];
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
     wfm_grid_dep_trigger();  // the next kernel's CTAs may take the place of ours as we exit
@@ -854,15 +866,32 @@ template <typename T, int N> struct JacClaimPrefetch {
 
 // A-item: ROWS_PER_ITEM rows of plane pl (each TT-thread group walks KR of them).  Aq = conj(a)*q
 // fused into the streaming load (WFM:907-914), FFT along x, keep the active kx only.
+// Hook of the row transforms of the TMA variant: right after the first exchange barrier every thread of the group has
+// consumed the landing buffer (its stage-1 loads fed the stores that precede the barrier), so the group's elected
+// thread posts the next row's bulk copy into it; the copy then has the rest of the transform to arrive.
+struct RowBulkLoadHook {
+    void* dst; const void* src; unsigned bytes; uint64_t* bar; bool issue;
+    WFM_DEVI void operator()() const { if (issue) wfm_bulk_load(dst, src, bytes, bar); }
+};
+
 template <typename T, int N, bool NARROW>
 WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, cx<T>* cells, const cx<T>* tw_s,
-                            const int* invx_s, const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl) {
+                            const int* invx_s, const PipeDep& dep, PipeQueue& qu, const PipeCtl& ctl,
+                            cx<T>* landing, uint64_t* mbar, unsigned& row_phase) {
     using P = Plan<N>;
     using L = RowLayout<T, N>;
     using Cfg = PipeCfg<T, N>;
     constexpr int C = Cfg::C, TT = P::T, E = P::E;
     int slot, t;
     row_thread_map<C, TT>(slot, t);
+    if constexpr (Cfg::JAC_TMA) {
+        // first row of the item: nothing of this group is in flight any more (its previous item is complete), so the
+        // landing buffer is free; the copy is an L2 hit when the claim-time prefetch was in time
+        if (t == 0) {
+            const size_t base0 = (size_t)pl * N * N + (size_t)N * (sub * Cfg::ROWS_PER_ITEM + slot);
+            wfm_bulk_load(landing + (size_t)slot * N, &a.cpx[base0], (unsigned)(N * sizeof(cx<T>)), &mbar[slot]);
+        }
+    }
     pipe_wait(dep);                                    // ring slot free? (rarely taken: probed at claim time)
     int xis[E];                                        // strip offset of column kx (without the y term) or -1
 #pragma unroll
@@ -902,7 +931,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
 #endif
 #if WFM_L2_PREFETCH && !defined(WFM_PROBE_JAC_L1) && !defined(WFM_PROBE_JAC_L2)
         if (t == 0 && kk + 1 < Cfg::KR) {              // this group's next row: DRAM -> L2 while this row is transformed
-            wfm_prefetch_l2(&a.cpx[base + (size_t)N * C], (unsigned)(N * sizeof(cx<T>)));
+            if constexpr (!Cfg::JAC_TMA) wfm_prefetch_l2(&a.cpx[base + (size_t)N * C], (unsigned)(N * sizeof(cx<T>)));
             wfm_prefetch_l2(&a.q[base + (size_t)N * C], (unsigned)(N * sizeof(T)));
         }
 #endif
@@ -922,22 +951,49 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
                 }
         }
 #else
+        if constexpr (Cfg::JAC_TMA) {
+            // q straight from global (its row was prefetched into L2 one row ahead); conj(a) from the landing buffer
+            T qv[E];
 #pragma unroll
-        for (int u = 0; u < E / P::R1; ++u)
+            for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
-            for (int r = 0; r < P::R1; ++r) {
-                const int x = (t + TT * u) + P::S1 * r;
+                for (int r = 0; r < P::R1; ++r) qv[u * P::R1 + r] = __ldcs(&a.q[base + (t + TT * u) + P::S1 * r]);
+            wfm_mbar_wait(&mbar[slot], row_phase);
+            ++row_phase;
+            const cx<T>* land = landing + (size_t)slot * N;
+#pragma unroll
+            for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+                for (int r = 0; r < P::R1; ++r) {
+                    const cx<T> av = land[(t + TT * u) + P::S1 * r];
+                    v[u * P::R1 + r] = mkc<T>(av.x * qv[u * P::R1 + r], av.y * qv[u * P::R1 + r]);
+                }
+        } else {
+#pragma unroll
+            for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+                for (int r = 0; r < P::R1; ++r) {
+                    const int x = (t + TT * u) + P::S1 * r;
 #if defined(WFM_PROBE_JAC_L1) || defined(WFM_PROBE_JAC_L2)
-                const cx<T> av = __ldg(&a.cpx[base + x]);
-                const T qv = __ldg(&a.q[base + x]);
+                    const cx<T> av = __ldg(&a.cpx[base + x]);
+                    const T qv = __ldg(&a.q[base + x]);
 #else
-                const cx<T> av = __ldcs(&a.cpx[base + x]);
-                const T qv = __ldcs(&a.q[base + x]);
+                    const cx<T> av = __ldcs(&a.cpx[base + x]);
+                    const T qv = __ldcs(&a.q[base + x]);
 #endif
-                v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
-            }
+                    v[u * P::R1 + r] = mkc<T>(av.x * qv, av.y * qv);
+                }
+        }
 #endif
-        fft_inplace<T, P, L, RowSync<TT>, NoHook, false, WFM_JAC_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + N, slot);
+        if constexpr (Cfg::JAC_TMA) {
+            const bool more = kk + 1 < Cfg::KR;
+            RowBulkLoadHook hk{landing + (size_t)slot * N, &a.cpx[base + (more ? (size_t)N * C : 0)],
+                               (unsigned)(N * sizeof(cx<T>)), &mbar[slot], more && t == 0};
+            fft_inplace<T, P, L, RowSync<TT>, RowBulkLoadHook, false, WFM_JAC_TW_TREE>(v, cells + slot * L::LEN, t, tw_s,
+                                                                                     tw_s + PipeCfg<T, N>::TW1, slot, hk);
+        } else {
+            fft_inplace<T, P, L, RowSync<TT>, NoHook, false, WFM_JAC_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
+        }
         cx<T>* dst = a.T2 + (size_t)ringoff + (size_t)y * C;
 #pragma unroll
         for (int e = 0; e < E; ++e)
@@ -980,7 +1036,7 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int bm, int ri
             if (leg_live<P::RL, NARROW>(r))
                 fl |= (unsigned)__ldg(&a.st.flags[sbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
     using ClaimHook = PipePrefetchHook<JacClaimPrefetch<T, N>>;
-    fft_inplace<T, P, L, CtaSync, ClaimHook, false, WFM_JAC_TW_TREE>(v, cells + c, t, tw_s, tw_s + N, 0,
+    fft_inplace<T, P, L, CtaSync, ClaimHook, false, WFM_JAC_TW_TREE>(v, cells + c, t, tw_s, tw_s + PipeCfg<T, N>::TW1, 0,
                                                                      ClaimHook{qu, ctl, a.g.nzl, JacClaimPrefetch<T, N>{a.cpx, a.q}});
     const int iz = a.g.z0 + (pl - bm * a.g.nzm);
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
@@ -1012,11 +1068,19 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
     using Cfg = PipeCfg<T, N>;
     WFM_DYN_SMEM(cx<T>, cells);
     cx<T>* tw_s = cells + Cfg::CELLS;
-    cx<T>* tw2_s = tw_s + N;
+    cx<T>* tw2_s = tw_s + Cfg::TW1;
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     double2* cis_s = reinterpret_cast<double2*>(invx_s + N);
-    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
+    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { if (i < Cfg::TW1) tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
     if (threadIdx.x < WFM_CIS_ENTRIES) cis_s[threadIdx.x] = a.cis[threadIdx.x];
+    // landing buffers of the row items (bulk-async copies of conj(a) rows) and their barriers
+    cx<T>* landing = reinterpret_cast<cx<T>*>(cis_s + WFM_CIS_ENTRIES);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(landing + (Cfg::JAC_TMA ? (size_t)Cfg::C * N : 0));
+    unsigned row_phase = 0;                      // rows this thread's group has received so far (= barrier phase)
+    if constexpr (Cfg::JAC_TMA) {
+        if (threadIdx.x < Cfg::C) wfm_mbar_init(&mbar[threadIdx.x], 1);
+        wfm_mbar_init_fence();
+    }
     if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
     wfm_grid_dep_trigger();  // the next kernel's CTAs may take the place of ours as we exit
     wfm_grid_dep_wait();     // the tables above are constants; everything below depends on the previous kernel
@@ -1035,7 +1099,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
             if (ctl.roles & 1) {
                 PipeDep dep;
                 dep.cnt = ready ? nullptr : &ctl.cntB[it.plane - ctl.ring]; dep.target = (unsigned)ctl.nB; dep.err = ctl.err;
-                jac_rows_item<T, N, NARROW>(a, it.plane, it.sub, it.ringoff, cells, tw_s, invx_s, dep, qu, ctl);
+                jac_rows_item<T, N, NARROW>(a, it.plane, it.sub, it.ringoff, cells, tw_s, invx_s, dep, qu, ctl, landing, mbar, row_phase);
             }
             if (qu.prefetch(ctl, P)) JacClaimPrefetch<T, N>{a.cpx, a.q}(qu.peek_next());
             pipe_signal(&ctl.cntA[it.plane]);

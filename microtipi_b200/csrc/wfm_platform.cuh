@@ -29,6 +29,31 @@ __device__ __forceinline__ void wfm_prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// ---- mbarrier + 1-D bulk-async copy (TMA engine; SASS: UBLKCP + SYNCS) ---------------------------------------
+// One elected thread posts the expected byte count on the shared-memory barrier and issues the copy; the data moves
+// global -> shared without passing through registers or the LSU; every consumer waits on the barrier's phase.
+#include <stdint.h>
+__device__ __forceinline__ void wfm_mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void wfm_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// bytes: multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void wfm_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+// wait until phase number `phase` (0, 1, 2, ... since the init) of the barrier has completed
+__device__ __forceinline__ void wfm_mbar_wait(uint64_t* bar, unsigned phase) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), parity = phase & 1u;
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 // Programmatic dependent launch: a kernel launched with WFM_LAUNCH_PDL may become resident while its
 // predecessor on the stream is still draining; it must execute wfm_grid_dep_wait() before its first access
 // to anything the predecessor reads or writes (everything before that point -- twiddle tables into shared

@@ -313,6 +313,16 @@ static inline int atomicAdd(int* addr, int v) { return __atomic_fetch_add(addr, 
 #define WFM_SPIN_PAUSE() std::this_thread::sleep_for(std::chrono::microseconds(50))
 
 static inline void wfm_prefetch_l2(const void*, unsigned) {}
+// mbarrier + bulk-async copy: the copy is done on the spot by the issuing fiber; the barrier word counts completed phases
+static inline void wfm_mbar_init(uint64_t* bar, unsigned) { __atomic_store_n(bar, (uint64_t)0, __ATOMIC_SEQ_CST); }
+static inline void wfm_mbar_init_fence() {}
+static inline void wfm_bulk_load(void* d, const void* s, unsigned n, uint64_t* bar) {
+    memcpy(d, s, n);
+    __atomic_fetch_add(bar, (uint64_t)1, __ATOMIC_SEQ_CST);
+}
+static inline void wfm_mbar_wait(uint64_t* bar, unsigned phase) {
+    while (__atomic_load_n(bar, __ATOMIC_SEQ_CST) <= (uint64_t)phase) emu::yield_fiber();
+}
 static inline void wfm_grid_dep_wait() {}
 static inline void wfm_grid_dep_trigger() {}
 
