@@ -290,9 +290,11 @@ struct NoHook { WFM_DEVI void operator()() const {} };
 // for R1 == 8, 4..11 for R1 == 16); their slots in v are ignored.
 // TWTREE: 0 = sequential chain w, w^2, ... (2 live twiddles), 1 = tree (depth log2 R, up to R/2 live),
 //         2 = two interleaved chains stepping by w^2 (depth R/2, 3 live)
-template <typename T, class P, class L, class S, class Hook = NoHook, bool SPARSE1 = false, int TWTREE = 0>
+// Hook2: callable run once by every thread right after the SECOND exchange barrier of a three-stage plan, i.e. before
+// the last (twiddle-free, lowest register pressure) stage: the place to put loads for the NEXT transform in flight.
+template <typename T, class P, class L, class S, class Hook = NoHook, bool SPARSE1 = false, int TWTREE = 0, class Hook2 = NoHook>
 WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* tw, const cx<T>* tw2,
-                          const int sync_id, const Hook& hook = Hook()) {
+                          const int sync_id, const Hook& hook = Hook(), const Hook2& hook2 = Hook2()) {
     static_assert(!SPARSE1 || P::R1 == 8 || P::R1 == 16, "sparse first stage: radix 8 or 16");
     constexpr int E = P::E, R1 = P::R1, R2 = P::R2, R3 = P::R3, TT = P::T, S1 = P::S1;
     // AFF: the layout is affine over the S1-blocks (see RowLayout::affine): every stage then needs ONE address per
@@ -399,6 +401,7 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
         }
         S::sync(sync_id);
 #endif
+        hook2();
         // stage 3: radix R3 over adjacent cells; butterfly b = k1 + R1*k2 -> X[b + (N/R3)*r]
 #pragma unroll
         for (int u = 0; u < E / R3; ++u) {

@@ -437,7 +437,10 @@ template <typename T, int N> struct PipeCfg {
 #ifndef WFM_JAC_TMA
 #define WFM_JAC_TMA 1
 #endif
-    static constexpr size_t LANDING = sizeof(cx<T>) * (size_t)C * N + 64;
+    // WFM_JAC_TMA: 0 = register loads; 1 = conj(a) rows by bulk copy, q by register loads one row ahead; 2 = conj(a) AND q
+    // rows by bulk copy (12 KB of landing buffer per row group at 512^2 fp64: two resident CTAs instead of three)
+    static constexpr bool JAC_TMA_Q = (WFM_JAC_TMA == 2);
+    static constexpr size_t LANDING = (sizeof(cx<T>) + (JAC_TMA_Q ? sizeof(T) : 0)) * (size_t)C * N + 64;
     // resident CTAs per SM the register allocation is tuned for: 1024 threads (64 registers each)
     static constexpr int BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
     static constexpr int BY_SMEM = (int)((220 * 1024) / SMEM) < 1 ? 1 : (int)((220 * 1024) / SMEM);
@@ -451,7 +454,8 @@ template <typename T, int N> struct PipeCfg {
 #ifdef WFM_PIPE_MINB_JAC
     static constexpr int MINB_JAC = WFM_PIPE_MINB_JAC;
 #else
-    static constexpr int MINB_JAC = (sizeof(T) == 8 && MINB >= 4) ? (3 * MINB) / 4 : MINB;
+    static constexpr int MINB_JAC0 = (sizeof(T) == 8 && MINB >= 4) ? (3 * MINB) / 4 : MINB;
+    static constexpr int MINB_JAC = (JAC_TMA_Q && N == 512 && sizeof(T) == 8) ? 2 : MINB_JAC0;
 #endif
     // The narrow Jacobian kernel (4 instead of 8 strip offsets and output predicates per thread) would fit 64
     // registers with 8 bytes of spill, but the full CTA count measured slower (0.841 vs 0.832 ms/step, A/B/A/B).
@@ -871,7 +875,29 @@ template <typename T, int N> struct JacClaimPrefetch {
 // thread posts the next row's bulk copy into it; the copy then has the rest of the transform to arrive.
 struct RowBulkLoadHook {
     void* dst; const void* src; unsigned bytes; uint64_t* bar; bool issue;
-    WFM_DEVI void operator()() const { if (issue) wfm_bulk_load(dst, src, bytes, bar); }
+    void* dst2; const void* src2; unsigned bytes2;     // second copy on the same barrier phase (the q row), bytes2 = 0: none
+    WFM_DEVI void operator()() const {
+        if (!issue) return;
+        wfm_mbar_expect(bar, bytes + bytes2);
+        wfm_bulk_copy(dst, src, bytes, bar);
+        if (bytes2) wfm_bulk_copy(dst2, src2, bytes2, bar);
+        wfm_mbar_complete_emu(bar);
+    }
+};
+// Second hook of the same transforms (before the last stage): the NEXT row's q values start their way into registers,
+// so that their L2 latency is covered by the last stage, the stores and the row barrier of this row.
+#ifndef WFM_JAC_Q_AHEAD
+#define WFM_JAC_Q_AHEAD 1
+#endif
+template <typename T, int E, int R1, int TT, int S1> struct RowQAheadHook {
+    T (&qn)[E]; const T* src; int t; bool issue;
+    WFM_DEVI void operator()() const {
+        if (!issue) return;
+#pragma unroll
+        for (int u = 0; u < E / R1; ++u)
+#pragma unroll
+            for (int r = 0; r < R1; ++r) qn[u * R1 + r] = __ldcs(&src[(t + TT * u) + S1 * r]);
+    }
 };
 
 template <typename T, int N, bool NARROW>
@@ -884,13 +910,14 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
     constexpr int C = Cfg::C, TT = P::T, E = P::E;
     int slot, t;
     row_thread_map<C, TT>(slot, t);
+    T* const landq = reinterpret_cast<T*>(landing + (size_t)C * N);      // (JAC_TMA_Q) q rows land behind the conj(a) rows
     if constexpr (Cfg::JAC_TMA) {
         // first row of the item: nothing of this group is in flight any more (its previous item is complete), so the
         // landing buffer is free; the copy is an L2 hit when the claim-time prefetch was in time
-        if (t == 0) {
-            const size_t base0 = (size_t)pl * N * N + (size_t)N * (sub * Cfg::ROWS_PER_ITEM + slot);
-            wfm_bulk_load(landing + (size_t)slot * N, &a.cpx[base0], (unsigned)(N * sizeof(cx<T>)), &mbar[slot]);
-        }
+        const size_t base0 = (size_t)pl * N * N + (size_t)N * (sub * Cfg::ROWS_PER_ITEM + slot);
+        RowBulkLoadHook first{landing + (size_t)slot * N, &a.cpx[base0], (unsigned)(N * sizeof(cx<T>)), &mbar[slot], t == 0,
+                              landq + (size_t)slot * N, &a.q[base0], Cfg::JAC_TMA_Q ? (unsigned)(N * sizeof(T)) : 0u};
+        first();
     }
     pipe_wait(dep);                                    // ring slot free? (rarely taken: probed at claim time)
     int xis[E];                                        // strip offset of column kx (without the y term) or -1
@@ -917,6 +944,9 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
             }
     }
 #endif
+    T qn[E];                                           // (TMA variant) the next row's q, loaded one row ahead
+#pragma unroll
+    for (int e = 0; e < E; ++e) qn[e] = (T)0;
 #pragma unroll 1
     for (int kk = 0; kk < Cfg::KR; ++kk) {
         if (kk == Cfg::KR - 1 && qu.prefetch(ctl, a.g.nzl))           // claim the next item behind the last row
@@ -932,7 +962,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
 #if WFM_L2_PREFETCH && !defined(WFM_PROBE_JAC_L1) && !defined(WFM_PROBE_JAC_L2)
         if (t == 0 && kk + 1 < Cfg::KR) {              // this group's next row: DRAM -> L2 while this row is transformed
             if constexpr (!Cfg::JAC_TMA) wfm_prefetch_l2(&a.cpx[base + (size_t)N * C], (unsigned)(N * sizeof(cx<T>)));
-            wfm_prefetch_l2(&a.q[base + (size_t)N * C], (unsigned)(N * sizeof(T)));
+            if constexpr (!Cfg::JAC_TMA_Q) wfm_prefetch_l2(&a.q[base + (size_t)N * C], (unsigned)(N * sizeof(T)));
         }
 #endif
         cx<T> v[E];
@@ -952,15 +982,24 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
         }
 #else
         if constexpr (Cfg::JAC_TMA) {
-            // q straight from global (its row was prefetched into L2 one row ahead); conj(a) from the landing buffer
+            // q straight from global (its row was prefetched into L2 one row ahead): already in registers for every row
+            // but the first of an item (RowQAheadHook); conj(a) from the landing buffer
             T qv[E];
 #pragma unroll
             for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
-                for (int r = 0; r < P::R1; ++r) qv[u * P::R1 + r] = __ldcs(&a.q[base + (t + TT * u) + P::S1 * r]);
+                for (int r = 0; r < P::R1; ++r)
+                    if constexpr (!Cfg::JAC_TMA_Q)
+                        qv[u * P::R1 + r] = (WFM_JAC_Q_AHEAD && kk > 0) ? qn[u * P::R1 + r] : __ldcs(&a.q[base + (t + TT * u) + P::S1 * r]);
             wfm_mbar_wait(&mbar[slot], row_phase);
             ++row_phase;
             const cx<T>* land = landing + (size_t)slot * N;
+            if constexpr (Cfg::JAC_TMA_Q) {
+#pragma unroll
+                for (int u = 0; u < E / P::R1; ++u)
+#pragma unroll
+                    for (int r = 0; r < P::R1; ++r) qv[u * P::R1 + r] = landq[(size_t)slot * N + (t + TT * u) + P::S1 * r];
+            }
 #pragma unroll
             for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
@@ -988,9 +1027,13 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
         if constexpr (Cfg::JAC_TMA) {
             const bool more = kk + 1 < Cfg::KR;
             RowBulkLoadHook hk{landing + (size_t)slot * N, &a.cpx[base + (more ? (size_t)N * C : 0)],
-                               (unsigned)(N * sizeof(cx<T>)), &mbar[slot], more && t == 0};
-            fft_inplace<T, P, L, RowSync<TT>, RowBulkLoadHook, false, WFM_JAC_TW_TREE>(v, cells + slot * L::LEN, t, tw_s,
-                                                                                     tw_s + PipeCfg<T, N>::TW1, slot, hk);
+                               (unsigned)(N * sizeof(cx<T>)), &mbar[slot], more && t == 0,
+                               landq + (size_t)slot * N, &a.q[base + (more ? (size_t)N * C : 0)],
+                               Cfg::JAC_TMA_Q ? (unsigned)(N * sizeof(T)) : 0u};
+            using QHook = RowQAheadHook<T, E, P::R1, TT, P::S1>;
+            QHook qh{qn, &a.q[base + (more ? (size_t)N * C : 0)], t, WFM_JAC_Q_AHEAD && more && !Cfg::JAC_TMA_Q};
+            fft_inplace<T, P, L, RowSync<TT>, RowBulkLoadHook, false, WFM_JAC_TW_TREE, QHook>(v, cells + slot * L::LEN, t, tw_s,
+                                                                                            tw_s + PipeCfg<T, N>::TW1, slot, hk, qh);
         } else {
             fft_inplace<T, P, L, RowSync<TT>, NoHook, false, WFM_JAC_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
         }
@@ -1075,7 +1118,7 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
     if (threadIdx.x < WFM_CIS_ENTRIES) cis_s[threadIdx.x] = a.cis[threadIdx.x];
     // landing buffers of the row items (bulk-async copies of conj(a) rows) and their barriers
     cx<T>* landing = reinterpret_cast<cx<T>*>(cis_s + WFM_CIS_ENTRIES);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(landing + (Cfg::JAC_TMA ? (size_t)Cfg::C * N : 0));
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(landing) + (Cfg::JAC_TMA ? Cfg::LANDING - 64 : 0));
     unsigned row_phase = 0;                      // rows this thread's group has received so far (= barrier phase)
     if constexpr (Cfg::JAC_TMA) {
         if (threadIdx.x < Cfg::C) wfm_mbar_init(&mbar[threadIdx.x], 1);

@@ -44,6 +44,17 @@ __device__ __forceinline__ void wfm_bulk_load(void* smem_dst, const void* gsrc, 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
 }
+// the same in two steps, for several copies completing on one barrier phase
+__device__ __forceinline__ void wfm_mbar_expect(uint64_t* bar, unsigned bytes) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wfm_bulk_copy(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void wfm_mbar_complete_emu(uint64_t*) {}   // (the hardware completes the phase by byte count)
 // wait until phase number `phase` (0, 1, 2, ... since the init) of the barrier has completed
 __device__ __forceinline__ void wfm_mbar_wait(uint64_t* bar, unsigned phase) {
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar), parity = phase & 1u;

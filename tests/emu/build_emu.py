@@ -17,12 +17,15 @@ DEPS = SRCS + [os.path.join(ROOT, "microtipi_b200", "csrc", f) for f in
 
 def build(force=False, sanitize=False):
     out = OUT.replace(".so", "_asan.so") if sanitize else OUT
+    extra = os.environ.get("WFM_EMU_FLAGS", "").split()       # experiment knobs (-DWFM_...=...): a separate library
+    if extra:
+        out = out.replace(".so", "_" + "".join(ch if ch.isalnum() else "_" for ch in "".join(extra)) + ".so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
         return out
     cmd = ["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-fvisibility=hidden", "-Wl,-Bsymbolic",
            "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable",
-           "-DWFM_EMU", "-include", os.path.join(HERE, "cuda_emu.h"), "-x", "c++"] + SRCS + \
+           "-DWFM_EMU", "-include", os.path.join(HERE, "cuda_emu.h")] + extra + ["-x", "c++"] + SRCS + \
           ["-o", out, "-lpthread"]
     if sanitize:
         cmd[1:1] = ["-fsanitize=address", "-fno-omit-frame-pointer"]

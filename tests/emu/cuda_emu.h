@@ -320,6 +320,10 @@ static inline void wfm_bulk_load(void* d, const void* s, unsigned n, uint64_t* b
     memcpy(d, s, n);
     __atomic_fetch_add(bar, (uint64_t)1, __ATOMIC_SEQ_CST);
 }
+static inline void wfm_mbar_expect(uint64_t*, unsigned) {}
+// (emulation: the LAST copy of a phase completes it -- callers pass `last`)
+static inline void wfm_bulk_copy(void* d, const void* s, unsigned n, uint64_t*) { memcpy(d, s, n); }
+static inline void wfm_mbar_complete_emu(uint64_t* bar) { __atomic_fetch_add(bar, (uint64_t)1, __ATOMIC_SEQ_CST); }
 static inline void wfm_mbar_wait(uint64_t* bar, unsigned phase) {
     while (__atomic_load_n(bar, __ATOMIC_SEQ_CST) <= (uint64_t)phase) emu::yield_fiber();
 }
