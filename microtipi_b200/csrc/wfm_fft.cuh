@@ -165,7 +165,9 @@ template <> struct Plan<32> : PlanBase<32, 8, 8, 4, 1> {};
 template <> struct Plan<64> : PlanBase<64, 8, 8, 8, 1> {};
 template <> struct Plan<128> : PlanBase<128, 8, 8, 4, 4> {};
 template <> struct Plan<256> : PlanBase<256, 8, 8, 8, 4> {};
-#ifdef WFM_PLAN512_E16   /* experiment: one warp per transform (T = 32), 16 values per thread */
+#if defined(WFM_PLAN512_W32)   /* experiment: one warp per transform (T = 32), two radix-8 butterflies per lane and stage */
+template <> struct Plan<512> : PlanBase<512, 16, 8, 8, 8> {};
+#elif defined(WFM_PLAN512_E16)   /* experiment: one warp per transform (T = 32), 16 values per thread */
 template <> struct Plan<512> : PlanBase<512, 16, 16, 8, 4> {};
 #else
 template <> struct Plan<512> : PlanBase<512, 8, 8, 8, 8> {};

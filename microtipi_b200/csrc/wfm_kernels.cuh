@@ -435,7 +435,7 @@ template <typename T, int N> struct PipeCfg {
     // Jacobian row items: conj(a) rows arrive by bulk-async copy (TMA) in a per-group landing buffer, one row ahead
     // (JAC_TMA); enabled where the landing buffers still fit beside MINB_JAC resident CTAs
 #ifndef WFM_JAC_TMA
-#define WFM_JAC_TMA 1
+#define WFM_JAC_TMA 0   /* measured slower than register loads at 512^2 fp64 (0.842-0.92 vs 0.810 ms per step, profiles/r02g_tma_variants.md): kept as a knob */
 #endif
     // WFM_JAC_TMA: 0 = register loads; 1 = conj(a) rows by bulk copy, q by register loads one row ahead; 2 = conj(a) AND q
     // rows by bulk copy (12 KB of landing buffer per row group at 512^2 fp64: two resident CTAs instead of three)
@@ -496,12 +496,22 @@ WFM_DEVI PipeItem pipe_decode(unsigned idx, int P, const PipeCtl& c) {
     return it;
 }
 
+#ifndef WFM_WAIT_LIMIT_NS
+#define WFM_WAIT_LIMIT_NS 20000000000ull
+#endif
 // thread 0 polls a counter (L2, volatile) until it reaches `target`; everybody then passes a barrier
 WFM_DEVI void pipe_wait(const unsigned* cnt, unsigned target, unsigned* err) {
     if (threadIdx.x == 0) {
         unsigned spins = 0;
+        unsigned long long t0 = 0;
         while (*(volatile const unsigned*)cnt < target) {
-            if (++spins > (1u << 22)) { *(volatile unsigned*)err = 1u; break; }   // ~seconds: never a hang
+            // a dependency is produced by items dequeued earlier, whose CTAs are running: microseconds.  The limit is
+            // wall-clock time (WFM_WAIT_LIMIT_NS, 20 s), read every 4096 polls: an error flag, never a hang
+            if ((++spins & 4095u) == 0u) {
+                const unsigned long long now = wfm_now_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > WFM_WAIT_LIMIT_NS || *(volatile unsigned*)err) { *(volatile unsigned*)err = 1u; break; }
+            }
             WFM_SPIN_PAUSE();
         }
         __threadfence();
@@ -1382,8 +1392,13 @@ __global__ void __launch_bounds__(WFM_FINAL_THREADS) k_jac_final(const double* _
         *(volatile unsigned*)&xc.flags[r][half * xc.world + xc.rank] = xc.epoch;           // raise my flag on rank r
         const volatile unsigned* mine = xc.flags[xc.rank] + half * xc.world;
         unsigned spins = 0;
+        unsigned long long t0 = 0;
         while ((int)(mine[r] - xc.epoch) < 0) {                                            // ... and wait for rank r's flag here
-            if (++spins > (1u << 24)) { *(volatile unsigned*)xc.err = 1u; break; }         // seconds: an error, never a hang
+            if ((++spins & 4095u) == 0u) {                                                 // wall-clock limit: an error, never a hang
+                const unsigned long long now = wfm_now_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 3 * WFM_WAIT_LIMIT_NS) { *(volatile unsigned*)xc.err = 1u; break; }
+            }
             WFM_SPIN_PAUSE();
         }
         wfm_fence_system();

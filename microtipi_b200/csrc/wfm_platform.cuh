@@ -22,6 +22,13 @@ inline std::atomic<unsigned long long>& launch_counter() {
     T* name = reinterpret_cast<T*>(wfm_dyn_smem_raw)
 
 #define WFM_SPIN_PAUSE() __nanosleep(40)
+// wall clock of the device in nanoseconds (%globaltimer): the dependency waits time out on TIME, not on a spin
+// count, so that a slow neighbour (co-tenancy, a debugger) cannot turn a long wait into a false error
+__device__ __forceinline__ unsigned long long wfm_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // TMA bulk prefetch of a contiguous global range into L2 (no registers, no shared memory, one
 // instruction per row): bytes must be a multiple of 16, the address 16-byte aligned.

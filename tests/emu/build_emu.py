@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "_build", "libwfm_emu.so")
 SRCS = [os.path.join(ROOT, "microtipi_b200", "csrc", "wfm_api.cu")]
-DEPS = SRCS + [os.path.join(ROOT, "microtipi_b200", "csrc", f) for f in
-               ("wfm_kernels.cuh", "wfm_fft.cuh", "wfm_platform.cuh", "wfm_conv.cuh", "wfm_conv_api.inl")] + [
+CSRC = os.path.join(ROOT, "microtipi_b200", "csrc")
+DEPS = SRCS + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".inl"))] + [
     os.path.join(HERE, "cuda_emu.h"), os.path.join(ROOT, "include", "wfm_b200.h")]
 
 

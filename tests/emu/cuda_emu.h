@@ -311,6 +311,9 @@ static inline int atomicAdd(int* addr, int v) { return __atomic_fetch_add(addr, 
 // polling back-off of the pipeline kernels: let the producer CTA's OS thread run
 #include <chrono>
 #define WFM_SPIN_PAUSE() std::this_thread::sleep_for(std::chrono::microseconds(50))
+static inline unsigned long long wfm_now_ns() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static inline void wfm_prefetch_l2(const void*, unsigned) {}
 // mbarrier + bulk-async copy: the copy is done on the spot by the issuing fiber; the barrier word counts completed phases
