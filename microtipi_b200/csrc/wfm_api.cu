@@ -57,6 +57,12 @@ struct wfm_model {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_copied = nullptr, ev_order = nullptr;
     bool copy_pending = false;
+    // host-buffer entry points (wfm_get_psf_async, wfm_apply_j_* with host q): the slab moves in plane chunks so that
+    // the PCIe copies overlap the kernels -- a launch then covers the plane window [win0, win0 + winN) only
+    // (winN == 0: the whole slab); in_stream carries the H2D chunks of q, ev_chunk[c] marks chunk c
+    int win0 = 0, winN = 0;
+    cudaStream_t in_stream = nullptr;
+    std::vector<cudaEvent_t> ev_chunk, ev_in;
     // optics (WFM:161-166)
     bool have_optics = false;
     double NA = 0, lambda = 0, ni = 0, lambda_ni = 0, radius = 0, deltaX = 0, deltaY = 0;
@@ -344,7 +350,7 @@ Strip strip_of(const wfm_model* h) {
 // ring kept within ~48 MB so that it stays L2-resident (126 MB L2 shared with the streaming traffic).
 struct PipePlan { int ring, lag, nA, nB, grid; };
 
-PipePlan plan_pipeline(const wfm_model* h, int nA, int nB, size_t plane_bytes, int ctas_per_sm) {
+PipePlan plan_pipeline(const wfm_model* h, int nA, int nB, size_t plane_bytes, int ctas_per_sm, int planes) {
     PipePlan p;
     p.nA = nA; p.nB = nB;
     if (const char* e = getenv("WFM_PIPE_CTAS")) { int v = atoi(e); if (v >= 1 && v < ctas_per_sm) ctas_per_sm = v; }   // experiment knob
@@ -359,10 +365,10 @@ PipePlan plan_pipeline(const wfm_model* h, int nA, int nB, size_t plane_bytes, i
     if (const char* e = getenv("WFM_PIPE_LAG")) { int v = atoi(e); if (v >= 1) lag = v; }
     while (lag > 2 && (size_t)(2 * lag + 2) * plane_bytes > budget) --lag;
     int ring = 2 * lag + 2;
-    if (ring > h->nzl) ring = h->nzl;
+    if (ring > planes) ring = planes;
     if (lag >= ring) lag = ring > 1 ? ring - 1 : 1;
     p.ring = ring; p.lag = lag;
-    const long items = (long)h->nzl * (nA + nB);
+    const long items = (long)planes * (nA + nB);
     p.grid = (int)(items < nctas ? items : nctas);
     return p;
 }
@@ -398,16 +404,20 @@ template <typename T, int N> int launch_psf(wfm_model* h) {
     rc = pack_strip(h); if (rc) return rc;
     const int nA = h->pitch / Cfg::C, nB = N / Cfg::ROWS_PER_ITEM;
     const size_t plane_bytes = sizeof(cx<T>) * (size_t)N * h->pitch;
-    const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, Cfg::MINB);
+    // plane window of this launch (chunked host paths; single-model handles only)
+    const int P0 = h->winN ? h->win0 : 0, PN = h->winN ? h->winN : h->nzl;
+    const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, Cfg::MINB, PN);
     WFM_CK(h, h->scratch.ensure(plane_bytes * pp.ring));
     PsfArgs<T> a;
     a.g = geom_of(h);
+    if (h->winN) { a.g.z0 += P0; a.g.nzl = PN; a.g.nzm = PN; }
     a.st = strip_of(h);
     a.inv_x = (const int*)h->inv_x.p;
     a.nax = h->nax; a.pitch = h->pitch;
     a.tw = (const cx<T>*)h->tw.p;
     a.cis = (const double2*)h->cis_tab.p;
-    a.T1 = (cx<T>*)h->scratch.p; a.cpx = (cx<T>*)h->cpx.p; a.psf = (T*)h->psf.p;
+    a.T1 = (cx<T>*)h->scratch.p;
+    a.cpx = (cx<T>*)h->cpx.p + (size_t)P0 * N * N; a.psf = (T*)h->psf.p + (size_t)P0 * N * N;
     PipeCtl ctl;
     rc = prepare_ctl(h, pp, ctl, pipe_roles()); if (rc) return rc;
     if (h->copy_pending) WFM_CK(h, cudaStreamWaitEvent(h->stream, h->ev_copied, 0));   // psf is still being read out
@@ -492,21 +502,24 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     rc = pack_strip(h); if (rc) return rc;
     const int nA = N / Cfg::ROWS_PER_ITEM, nB = h->pitch / Cfg::C;
     const size_t plane_bytes = sizeof(cx<T>) * (size_t)N * h->pitch;
-    const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, ctas_per_sm);
+    // plane window of this launch (chunked host path): the z-sums run once, after the last window (win0 + winN == nzl)
+    const int P0 = h->winN ? h->win0 : 0, PN = h->winN ? h->winN : h->nzl;
+    const PipePlan pp = plan_pipeline(h, nA, nB, plane_bytes, ctas_per_sm, PN);
     WFM_CK(h, h->scratch.ensure(plane_bytes * pp.ring));
     const size_t img = (size_t)N * h->pitch;
     WFM_CK(h, h->Gj.ensure(sizeof(double) * img * h->nzl));
     if (kinds & WFM_J_MODULUS) WFM_CK(h, h->Gm.ensure(sizeof(double) * img * h->nzl));
     JacArgs<T> a;
     a.g = geom_of(h);
-    a.cpx = (const cx<T>*)h->cpx.p; a.q = (const T*)q_dev;
+    if (h->winN) { a.g.z0 += P0; a.g.nzl = PN; a.g.nzm = PN; }
+    a.cpx = (const cx<T>*)h->cpx.p + (size_t)P0 * N * N; a.q = (const T*)q_dev + (size_t)P0 * N * N;
     a.st = strip_of(h);
     a.inv_x = (const int*)h->inv_x.p; a.nax = h->nax; a.pitch = h->pitch;
     a.tw = (const cx<T>*)h->tw.p;
     a.cis = (const double2*)h->cis_tab.p;
     a.T2 = (cx<T>*)h->scratch.p;
-    a.Gj = (double*)h->Gj.p;
-    a.Gm = (kinds & WFM_J_MODULUS) ? (double*)h->Gm.p : nullptr;
+    a.Gj = (double*)h->Gj.p + (size_t)P0 * img;
+    a.Gm = (kinds & WFM_J_MODULUS) ? (double*)h->Gm.p + (size_t)P0 * img : nullptr;
     a.last_plane_only = (h->modulus_mode == WFM_MODULUS_REFERENCE_LAST_PLANE) ? 1 : 0;
     {
         PipeCtl ctl;
@@ -516,7 +529,9 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
         WFM_CK_LAUNCH(h, "k_jac_pipeline");
         h->pipe_checks++;
     }
-    return launch_jac_reduce(h, kinds, a.g, a.Gj, a.Gm, a.last_plane_only, grad_dev);
+    if (h->winN && P0 + PN < h->nzl) return WFM_OK;          // more windows to come
+    return launch_jac_reduce(h, kinds, geom_of(h), (const double*)h->Gj.p,
+                             (kinds & WFM_J_MODULUS) ? (const double*)h->Gm.p : nullptr, a.last_plane_only, grad_dev);
 }
 
 #ifdef WFM_ONLY_512
@@ -626,18 +641,58 @@ template <typename T> int dispatch_jac(wfm_model* h, unsigned kinds, const void*
     WFM_DISPATCH_N(launch_jac, h, kinds, q, g)
 }
 
-int compute_psf_impl(wfm_model* h) {
-    if (h->pstate > 0) return WFM_OK;                                          // WFM:207
+// Planes per chunk of the host-buffer paths (wfm_get_psf_async, wfm_apply_j_* with a host q); 0 = one piece.
+// A chunk is a plane window of the pipelines: chunk c's kernel runs while chunk c+1 (q, host -> device) or chunk c-1
+// (psf, device -> host) is on the PCIe link, so that only one chunk's kernel time is left outside the copies.
+int host_chunk_planes(const wfm_model* h) {
+    if (h->generic || h->nbatch > 1 || h->multi()) return 0;
+    int nch = 8;
+    if (const char* e = getenv("WFM_HOST_CHUNKS")) nch = atoi(e);
+    if (nch <= 1) return 0;
+    const size_t plane = (size_t)h->npix() * h->esz();
+    int cp = (h->nzl + nch - 1) / nch;
+    size_t min_bytes = (size_t)32 << 20;                                         // at least 32 MB per copy
+    if (const char* e = getenv("WFM_HOST_CHUNK_MIN_BYTES")) min_bytes = (size_t)atoll(e);   // (tests: chunk small stacks too)
+    const int min_planes = (int)((min_bytes + plane - 1) / plane) > 0 ? (int)((min_bytes + plane - 1) / plane) : 1;
+    if (cp < min_planes) cp = min_planes;
+    if (cp * 2 > h->nzl) return 0;
+    return cp;
+}
+
+int ensure_chunk_events(wfm_model* h, std::vector<cudaEvent_t>& ev, int n) {
+    while ((int)ev.size() < n) {
+        cudaEvent_t e = nullptr;
+        WFM_CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ev.push_back(e);
+    }
+    return WFM_OK;
+}
+
+// computePsf().  cp > 0: in plane windows of cp planes; after_window(p0, np) is called right after window [p0, p0+np)
+// has been queued on the handle's stream (the asynchronous read-back queues that window's device -> host copy there).
+template <class F> int compute_psf_windows(wfm_model* h, int cp, F after_window) {
     if (!h->have_rho) return h->fail(WFM_ERR_STATE, "pupil modulus not set: call wfm_set_modulus or wfm_set_pupil_arrays first");
     WFM_ENTER(h);
     int rc = rebuild_activity(h); if (rc) return rc;
     const size_t vox = (size_t)h->npix() * h->nzl;
     WFM_CK(h, h->cpx.ensure(vox * 2 * h->esz()));
     WFM_CK(h, h->psf.ensure(vox * h->esz()));
-    rc = (h->precision == WFM_F64) ? dispatch_psf<double>(h) : dispatch_psf<float>(h);
-    if (rc) return rc;
+    if (cp <= 0) cp = h->nzl;
+    for (int p0 = 0; p0 < h->nzl; p0 += cp) {
+        const int np = std::min(cp, h->nzl - p0);
+        if (np < h->nzl) { h->win0 = p0; h->winN = np; }
+        rc = (h->precision == WFM_F64) ? dispatch_psf<double>(h) : dispatch_psf<float>(h);
+        h->win0 = 0; h->winN = 0;
+        if (rc) return rc;
+        rc = after_window(p0, np); if (rc) return rc;
+    }
     h->pstate = 1;                                                             // WFM:395
     return WFM_OK;
+}
+
+int compute_psf_impl(wfm_model* h) {
+    if (h->pstate > 0) return WFM_OK;                                          // WFM:207
+    return compute_psf_windows(h, 0, [](int, int) { return WFM_OK; });
 }
 
 int invalidate(wfm_model* h) { h->pstate = 0; h->strip_dirty = true; return WFM_OK; }
@@ -765,6 +820,14 @@ int unsupported(wfm_model* h, const char* what);
         if (rc__) (h)->err = c->err; return rc__; } } while (0)
 #define WFM_MULTI_NO(h, what) do { if ((h)->multi()) return wfm_multi::unsupported((h), what); } while (0)
 
+static int jacobian_preconditions(wfm_model* h, unsigned kinds) {
+    if (!(kinds & 7u)) return h->fail(WFM_ERR_INVALID_ARG, "no Jacobian selected");
+    if ((kinds & WFM_J_PHASE) && h->nphase <= 0) return h->fail(WFM_ERR_STATE, "phase space is empty (nPhase = 0)");
+    if ((kinds & WFM_J_MODULUS) && h->nmod <= 0) return h->fail(WFM_ERR_STATE, "modulus coefficients not set");
+    if ((kinds & (WFM_J_PHASE | WFM_J_MODULUS)) && h->nzern <= 0) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
+    return WFM_OK;
+}
+
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
@@ -854,6 +917,9 @@ int wfm_destroy(wfm_model* h) {
     drain_spans(h);
     for (cudaEvent_t e : h->free_events) cudaEventDestroy(e);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->in_stream) { cudaStreamSynchronize(h->in_stream); cudaStreamDestroy(h->in_stream); }
+    for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
     if (h->ev_ready) cudaEventDestroy(h->ev_ready);
     if (h->ev_copied) cudaEventDestroy(h->ev_copied);
     if (h->ev_order) cudaEventDestroy(h->ev_order);
@@ -1201,15 +1267,31 @@ int wfm_get_psf_async(wfm_model* h, void* out) {
     if (h->multi()) return wfm_multi::get_stack(h, out, false, true);
     WFM_ENTER(h);
     if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
-    int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1800-1802
     if (!h->copy_stream) {
         WFM_CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         WFM_CK(h, cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
         WFM_CK(h, cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
     }
-    WFM_CK(h, cudaEventRecord(h->ev_ready, h->stream));
-    WFM_CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
-    WFM_CK(h, cudaMemcpyAsync(out, h->psf.p, (size_t)h->npix() * h->nzl * h->esz(), cudaMemcpyDeviceToHost, h->copy_stream));
+    const int cp = (h->pstate > 0) ? 0 : host_chunk_planes(h);
+    if (cp > 0) {
+        // dirty PSF: computePsf in plane windows, every window's read-back queued right behind it on the second stream
+        const size_t plane = (size_t)h->npix() * h->esz();
+        int rc = ensure_chunk_events(h, h->ev_chunk, (h->nzl + cp - 1) / cp); if (rc) return rc;
+        rc = compute_psf_windows(h, cp, [&](int p0, int np) {
+            cudaEvent_t ev = h->ev_chunk[p0 / cp];
+            WFM_CK(h, cudaEventRecord(ev, h->stream));
+            WFM_CK(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
+            WFM_CK(h, cudaMemcpyAsync((char*)out + plane * p0, (const char*)h->psf.p + plane * p0, plane * np,
+                                      cudaMemcpyDeviceToHost, h->copy_stream));
+            return (int)WFM_OK;
+        });
+        if (rc) return rc;
+    } else {
+        int rc = compute_psf_impl(h); if (rc) return rc;                       // WFM:1800-1802
+        WFM_CK(h, cudaEventRecord(h->ev_ready, h->stream));
+        WFM_CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
+        WFM_CK(h, cudaMemcpyAsync(out, h->psf.p, (size_t)h->npix() * h->nzl * h->esz(), cudaMemcpyDeviceToHost, h->copy_stream));
+    }
     WFM_CK(h, cudaEventRecord(h->ev_copied, h->copy_stream));
     h->copy_pending = true;
     return WFM_OK;
@@ -1287,27 +1369,58 @@ int wfm_apply_jacobian_dev(wfm_model* h, unsigned kinds, const void* q_dev, doub
     WFM_MULTI_NO(h, "wfm_apply_jacobian_dev (use wfm_multi_apply_jacobian_dev)");
     WFM_ENTER(h);
     if (!q_dev || !grad_dev) return h->fail(WFM_ERR_INVALID_ARG, "q_dev / grad_dev is NULL");
-    if (!(kinds & 7u)) return h->fail(WFM_ERR_INVALID_ARG, "no Jacobian selected");
-    if ((kinds & WFM_J_PHASE) && h->nphase <= 0) return h->fail(WFM_ERR_STATE, "phase space is empty (nPhase = 0)");
-    if ((kinds & WFM_J_MODULUS) && h->nmod <= 0) return h->fail(WFM_ERR_STATE, "modulus coefficients not set");
-    if ((kinds & (WFM_J_PHASE | WFM_J_MODULUS)) && h->nzern <= 0) return h->fail(WFM_ERR_STATE, "Zernike basis not set");
-    int rc = compute_psf_impl(h); if (rc) return rc;                           // quirk Q5: recompute if dirty
+    int rc = jacobian_preconditions(h, kinds); if (rc) return rc;
+    rc = compute_psf_impl(h); if (rc) return rc;                               // quirk Q5: recompute if dirty
     return (h->precision == WFM_F64) ? dispatch_jac<double>(h, kinds, q_dev, grad_dev)
                                      : dispatch_jac<float>(h, kinds, q_dev, grad_dev);
+}
+
+
+// One device, q in host memory: H2D of q, Jacobian, D2H of the K-vector ([nbatch][glen] doubles into g_out).
+// Large slabs move in plane chunks on a stream of their own (host_chunk_planes): the copy starts at once -- beside a
+// PSF that is still being computed or read back -- and the adjoint pipeline of chunk c runs under the copy of chunk c+1.
+static int apply_host_single(wfm_model* h, unsigned kinds, const void* q_host, double* g_out) {
+    WFM_ENTER(h);
+    int rc = jacobian_preconditions(h, kinds); if (rc) return rc;
+    const size_t plane = (size_t)h->npix() * h->esz(), bytes = plane * h->nzl;
+    WFM_CK(h, h->qdev.ensure(bytes));
+    WFM_CK(h, h->grad.ensure(8 * (size_t)h->glen() * h->nbatch));
+    const int cp = host_chunk_planes(h);
+    if (cp <= 0) {
+        WFM_CK(h, cudaMemcpyAsync(h->qdev.p, q_host, bytes, cudaMemcpyHostToDevice, h->stream));
+        rc = wfm_apply_jacobian_dev(h, kinds, h->qdev.p, (double*)h->grad.p); if (rc) return rc;
+    } else {
+        if (!h->in_stream) WFM_CK(h, cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking));
+        const int nch = (h->nzl + cp - 1) / cp;
+        rc = ensure_chunk_events(h, h->ev_in, nch); if (rc) return rc;
+        // (qdev is idle here: every call that reads it drains the handle's stream before it returns)
+        for (int c = 0; c < nch; ++c) {
+            const int p0 = c * cp, np = std::min(cp, h->nzl - p0);
+            WFM_CK(h, cudaMemcpyAsync((char*)h->qdev.p + plane * p0, (const char*)q_host + plane * p0, plane * np,
+                                      cudaMemcpyHostToDevice, h->in_stream));
+            WFM_CK(h, cudaEventRecord(h->ev_in[c], h->in_stream));
+        }
+        rc = compute_psf_impl(h);                                              // quirk Q5: recompute if dirty
+        for (int c = 0; c < nch && !rc; ++c) {
+            const int p0 = c * cp, np = std::min(cp, h->nzl - p0);
+            WFM_CK(h, cudaStreamWaitEvent(h->stream, h->ev_in[c], 0));
+            h->win0 = p0; h->winN = np;
+            rc = (h->precision == WFM_F64) ? dispatch_jac<double>(h, kinds, h->qdev.p, (double*)h->grad.p)
+                                           : dispatch_jac<float>(h, kinds, h->qdev.p, (double*)h->grad.p);
+            h->win0 = 0; h->winN = 0;
+        }
+        if (rc) { cudaStreamSynchronize(h->in_stream); return rc; }
+    }
+    WFM_CK(h, cudaMemcpyAsync(g_out, h->grad.p, 8 * (size_t)h->glen() * h->nbatch, cudaMemcpyDeviceToHost, h->stream));
+    WFM_CK(h, cudaStreamSynchronize(h->stream));
+    return check_pipeline(h);
 }
 
 static int apply_host(wfm_model* h, unsigned kinds, const void* q_host, std::vector<double>& g) {
     if (!q_host) return h->fail(WFM_ERR_INVALID_ARG, "q is NULL");
     if (h->multi()) return wfm_multi::apply_host(h, kinds, q_host, g);
-    WFM_ENTER(h);
-    const size_t bytes = (size_t)h->npix() * h->nzl * h->esz();
-    WFM_CK(h, h->qdev.ensure(bytes));
-    WFM_CK(h, cudaMemcpyAsync(h->qdev.p, q_host, bytes, cudaMemcpyHostToDevice, h->stream));
-    int rc = wfm_apply_jacobian_dev(h, kinds, h->qdev.p, (double*)h->grad.p); if (rc) return rc;
     g.resize((size_t)h->glen() * h->nbatch);
-    WFM_CK(h, cudaMemcpyAsync(g.data(), h->grad.p, 8 * g.size(), cudaMemcpyDeviceToHost, h->stream));
-    WFM_CK(h, cudaStreamSynchronize(h->stream));
-    return check_pipeline(h);
+    return apply_host_single(h, kinds, q_host, g.data());
 }
 
 #define WFM_NO_BATCH(h) do { if ((h)->nbatch > 1) return (h)->fail(WFM_ERR_UNSUPPORTED, "batch handle: use wfm_batch_apply_jacobian"); } while (0)

@@ -98,14 +98,9 @@ int apply_host(wfm_model* h, unsigned kinds, const void* q_host, std::vector<dou
     int rc = parallel(h, [&](int i) {
         wfm_model* c = h->parts[i];
         DeviceScope s(c->device);
-        const size_t off = plane * (size_t)(c->z0 - h->z0), bytes = plane * (size_t)c->nzl;
-        WFM_CK(c, c->qdev.ensure(bytes));
-        WFM_CK(c, cudaMemcpyAsync(c->qdev.p, (const char*)q_host + off, bytes, cudaMemcpyHostToDevice, c->stream));
-        int r = wfm_apply_jacobian_dev(c, kinds, c->qdev.p, (double*)c->grad.p); if (r) return r;
+        const size_t off = plane * (size_t)(c->z0 - h->z0);
         part[i].resize(L);
-        WFM_CK(c, cudaMemcpyAsync(part[i].data(), c->grad.p, 8 * (size_t)L, cudaMemcpyDeviceToHost, c->stream));
-        WFM_CK(c, cudaStreamSynchronize(c->stream));
-        return check_pipeline(c);
+        return apply_host_single(c, kinds, (const char*)q_host + off, part[i].data());
     });
     if (rc) return rc;
     g.assign(L, 0.0);

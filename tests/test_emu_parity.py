@@ -357,7 +357,9 @@ def test_randomised_configurations_match_oracle(lib, seed):
 def test_gpu_case_helpers_at_small_sizes(lib):
     """The bodies of the full-stack / escape-hatch GPU tests, run on the emulated build at sizes it finishes in
     seconds (a ragged slab across the z wrap, more planes than the intermediate ring holds)."""
-    from tests.test_gpu_parity import escape_hatch_case, full_stack_case
+    from tests.test_gpu_parity import chunked_host_case, escape_hatch_case, full_stack_case
+    chunked_host_case(lib, 32, 40, 7, 29, False, {"WFM_HOST_CHUNKS": "4", "WFM_HOST_CHUNK_MIN_BYTES": "1"})
+    chunked_host_case(lib, 32, 12, 0, 12, True, {"WFM_HOST_CHUNKS": "3", "WFM_HOST_CHUNK_MIN_BYTES": "1"})
     full_stack_case(lib, 32, 96, 40, 50, False)
     full_stack_case(lib, 32, 16, 3, 9, True)
     escape_hatch_case(lib, ((32, 5, 0.2), (32, 3, 0.4)))

@@ -360,6 +360,68 @@ def test_async_psf_readback_overlaps_and_orders(lib):
     m.close()
 
 
+def chunked_host_case(lib, N, Nz, z0, nzl, single, env):
+    """Host-buffer entry points with the slab moved in plane chunks (plane windows of the pipelines, copies on their own
+    streams): getPsfAsync of a dirty PSF, then every host-q Jacobian, against the oracle; then the same through a clean
+    PSF (single-piece read-back) -- the results must not depend on how the slab was cut."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        ref = o.WideFieldModelOracle((N, N, 2), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], single=single)
+        m = WideFieldModel((N, N, Nz), 10, 4, P["NA"], P["lam"], P["ni"], P["dxy"], P["dz"], False, single, lib=lib,
+                           basis=lambda nz: ref.Z[:nz], z0=z0, nz_local=nzl)
+        alpha = o.synthetic_alpha(10)
+        for mm in (ref, m):
+            mm.setPhase(alpha)
+            mm.setModulus(BETA4)
+        q = o.synthetic_q(N, N, Nz, z0=z0, nz_local=nzl, single=single)
+        cpx, psf, gd, gp, gm = _oracle_stack(ref, Nz, z0, nzl, q, single)
+        t = tol(single)
+        tj = 20 * t if single else t
+        dt = np.float32 if single else np.float64
+        nbytes = N * N * nzl * np.dtype(dt).itemsize
+        hp = C.c_void_p()
+        assert lib.wfm_host_alloc(C.byref(hp), nbytes) == 0
+        out = np.frombuffer((C.c_char * nbytes).from_address(hp.value), dtype=dt).reshape(nzl, N, N)
+        out[:] = -1
+        m.getPsfAsync(hp.value)                       # dirty PSF: windows of computePsf, each read back behind it
+        g = m.apply_J_phase(q).data                   # q in chunks on its own stream, adjoint windows behind them
+        m.waitTransfers()
+        assert max(o.rel_l2(out[l], psf[l]) for l in range(nzl)) <= t
+        assert o.rel_l2(m.get_cpxPsf(), cpx) <= t
+        assert o.rel_l2(g, gp) <= tj
+        d, p, mo = m.apply_J_all(q)
+        assert o.rel_l2(d, gd) <= tj and o.rel_l2(p, gp) <= tj and o.rel_l2(mo, gm) <= tj
+        assert o.rel_l2(m.apply_J_defocus(q).data, gd) <= tj
+        assert o.rel_l2(m.apply_J_modulus(q).data, gm) <= tj
+        out[:] = -1
+        m.getPsfAsync(hp.value); m.waitTransfers()    # clean PSF: one copy
+        assert max(o.rel_l2(out[l], psf[l]) for l in range(nzl)) <= t
+        m.setPhase(alpha * 0.5)                       # dirty again; Jacobian first (quirk Q5 recomputes the whole slab)
+        ref.setPhase(alpha * 0.5)
+        cpx2, psf2, gd2, gp2, gm2 = _oracle_stack(ref, Nz, z0, nzl, q, single)
+        assert o.rel_l2(m.apply_J_phase(q).data, gp2) <= tj
+        assert o.rel_l2(m.getPsf(), psf2) <= t
+        lib.wfm_host_free(hp)
+        m.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("N,Nz,z0,nzl,single,env", [
+    (512, 256, 0, 256, False, {}),                                                        # default policy: 8 chunks of 32 planes
+    (256, 128, 40, 70, False, {"WFM_HOST_CHUNKS": "4", "WFM_HOST_CHUNK_MIN_BYTES": "1"}),  # ragged last chunk (18, 18, 18, 16)
+    (256, 64, 0, 64, True, {"WFM_HOST_CHUNKS": "3", "WFM_HOST_CHUNK_MIN_BYTES": "1"}),
+])
+def test_host_paths_in_plane_chunks(lib, N, Nz, z0, nzl, single, env):
+    chunked_host_case(lib, N, Nz, z0, nzl, single, env)
+
+
 @pytest.mark.parametrize("N,Nz", [(64, 32), (256, 64)])
 def test_rolled_psf_and_mtf(lib, N, Nz):
     """Row f4: ArrayUtils.roll(getPsf()) (BlindDeconvJob.java:100) and the intended getMtf() (WFM:1807-1828)."""
