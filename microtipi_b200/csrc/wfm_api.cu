@@ -451,8 +451,14 @@ int launch_jac_reduce(wfm_model* h, unsigned kinds, const Geom& g, const double*
         r.glen = h->glen();
         const bool batch = h->nbatch > 1;
         r.bpar = batch ? (const double*)h->bpar_dev.p : nullptr;
-        r.cpm = (h->nzm + WFM_RED_CHUNK_PLANES - 1) / WFM_RED_CHUNK_PLANES;
         const int nblocks = h->ncells > 0 ? (h->ncells + WFM_RED_THREADS - 1) / WFM_RED_THREADS : 1;
+        // the longest chunks that still give every SM two CTAs (512^2 x 256: 64-plane chunks, one wave of 360 CTAs;
+        // 256^2 x 128: 16-plane chunks, 184 CTAs instead of 46)
+        r.batches = WFM_RED_BATCHES;
+        while (r.batches > 1 &&
+               (long)nblocks * ((h->nzm + WFM_RED_PLANES * r.batches - 1) / (WFM_RED_PLANES * r.batches)) * h->nbatch < 2L * h->num_sms)
+            r.batches >>= 1;
+        r.cpm = (h->nzm + WFM_RED_PLANES * r.batches - 1) / (WFM_RED_PLANES * r.batches);
         const int nchunks = r.cpm * h->nbatch;
         WFM_CK(h, h->block_part.ensure(sizeof(double) * (size_t)nblocks * nchunks * r.glen));
         r.block_part = (double*)h->block_part.p;
@@ -500,7 +506,7 @@ template <typename T, int N> int launch_jac(wfm_model* h, unsigned kinds, const 
     }
     int rc = set_smem(h, kfn, Cfg::SMEM_JAC); if (rc) return rc;
     rc = pack_strip(h); if (rc) return rc;
-    const int nA = N / Cfg::ROWS_PER_ITEM, nB = h->pitch / Cfg::C;
+    const int nA = N / Cfg::ROWS_PER_ITEM_JAC, nB = h->pitch / Cfg::C;
     const size_t plane_bytes = sizeof(cx<T>) * (size_t)N * h->pitch;
     // plane window of this launch (chunked host path): the z-sums run once, after the last window (win0 + winN == nzl)
     const int P0 = h->winN ? h->win0 : 0, PN = h->winN ? h->winN : h->nzl;
@@ -843,7 +849,7 @@ static int create_impl(wfm_model** out, int nx, int ny, int nz_global, int z0, i
     }
     // (the model index is a grid.y dimension of the setters and, times the plane chunks per model, of the reduction)
     if (nbatch < 1 || (long long)nbatch * nz_local > (1ll << 24) ||
-        (long long)nbatch * ((nz_local + WFM_RED_CHUNK_PLANES - 1) / WFM_RED_CHUNK_PLANES) > 65535) {
+        (long long)nbatch * ((nz_local + WFM_RED_PLANES - 1) / WFM_RED_PLANES) > 65535) {
         g_create_error = "bad batch size"; return WFM_ERR_INVALID_ARG;
     }
     if (precision != WFM_F64 && precision != WFM_F32) { g_create_error = "bad precision"; return WFM_ERR_INVALID_ARG; }

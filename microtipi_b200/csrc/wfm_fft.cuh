@@ -172,7 +172,14 @@ template <> struct Plan<512> : PlanBase<512, 16, 16, 8, 4> {};
 #else
 template <> struct Plan<512> : PlanBase<512, 8, 8, 8, 8> {};
 #endif
+// 1024 = 8*8*16: two radix-8 butterflies per thread in the twiddled stages, the radix-16 butterfly last (no twiddles
+// behind it: fewest live registers).  Measured at 1024^2 x 64 fp64 against 16*8*8 (-DWFM_PLAN1024_A): 0.923 vs 0.948 ms per
+// step at two resident CTAs, 1.05 vs 1.27 ms at three (profiles/r02g_other_shapes.md).
+#ifdef WFM_PLAN1024_A
 template <> struct Plan<1024> : PlanBase<1024, 16, 16, 8, 8> {};
+#else
+template <> struct Plan<1024> : PlanBase<1024, 16, 8, 8, 16> {};
+#endif
 template <> struct Plan<2048> : PlanBase<2048, 16, 16, 16, 8> {};
 
 // Row padding shifts (PA, PB): pad(i) = i + (i >> PA) + (i >> PB), 0 disables a term.
@@ -187,7 +194,11 @@ template <> struct RowPad<512, 16> { static constexpr int PA = 3, PB = 6; };
 #else
 template <> struct RowPad<512, 16> { static constexpr int PA = 0, PB = 6; };
 #endif
+#ifdef WFM_PLAN1024_A
 template <> struct RowPad<1024, 16> { static constexpr int PA = 0, PB = 6; };
+#else
+template <> struct RowPad<1024, 16> { static constexpr int PA = 0, PB = 7; };
+#endif
 template <> struct RowPad<2048, 16> { static constexpr int PA = 0, PB = 7; };
 template <> struct RowPad<16, 8> { static constexpr int PA = 0, PB = 0; };
 template <> struct RowPad<32, 8> { static constexpr int PA = 3, PB = 4; };
@@ -195,7 +206,11 @@ template <> struct RowPad<64, 8> { static constexpr int PA = 3, PB = 5; };
 template <> struct RowPad<128, 8> { static constexpr int PA = 2, PB = 0; };
 template <> struct RowPad<256, 8> { static constexpr int PA = 0, PB = 4; };
 template <> struct RowPad<512, 8> { static constexpr int PA = 0, PB = 6; };
+#ifdef WFM_PLAN1024_A
 template <> struct RowPad<1024, 8> { static constexpr int PA = 0, PB = 6; };
+#else
+template <> struct RowPad<1024, 8> { static constexpr int PA = 0, PB = 7; };
+#endif
 template <> struct RowPad<2048, 8> { static constexpr int PA = 4, PB = 8; };
 
 template <typename T, int N> struct RowLayout {
@@ -294,7 +309,12 @@ struct NoHook { WFM_DEVI void operator()() const {} };
 //         2 = two interleaved chains stepping by w^2 (depth R/2, 3 live)
 // Hook2: callable run once by every thread right after the SECOND exchange barrier of a three-stage plan, i.e. before
 // the last (twiddle-free, lowest register pressure) stage: the place to put loads for the NEXT transform in flight.
-template <typename T, class P, class L, class S, class Hook = NoHook, bool SPARSE1 = false, int TWTREE = 0, class Hook2 = NoHook>
+// TWTAB: bit 0 = the stage-1 twiddles w^k come from the shared table, tw[(k-1)*S1 + b] = W_N^(b*k), k in [1, R1) (row k = 1
+//        is the base table); bit 1 = the stage-2 twiddles likewise, tw2[(k-1)*R3 + d3] = W_N^(R1*d3*k), k in [1, R2)
+//        (the R3 lanes of a butterfly group read adjacent entries: one wavefront per load).  No power chains: fewer FP64 instructions, shorter
+//        dependency chains, more LDS.
+template <typename T, class P, class L, class S, class Hook = NoHook, bool SPARSE1 = false, int TWTREE = 0, class Hook2 = NoHook,
+          int TWTAB = 0>
 WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>* tw, const cx<T>* tw2,
                           const int sync_id, const Hook& hook = Hook(), const Hook2& hook2 = Hook2()) {
     static_assert(!SPARSE1 || P::R1 == 8 || P::R1 == 16, "sparse first stage: radix 8 or 16");
@@ -321,7 +341,10 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
         cx<T>* const s1 = sm + L::at(b);               // AFF: leg k of this butterfly lives at s1[k * LS1]
         auto cell1 = [&](int k) -> cx<T>& { return AFF ? s1[k * LS1] : sm[L::at(k * S1 + b)]; };
         cell1(0) = a[0];
-        if constexpr (TWTREE == 1) {
+        if constexpr (TWTAB & 1) {
+#pragma unroll
+            for (int k = 1; k < R1; ++k) cell1(k) = cmul(a[k], tw[(k - 1) * S1 + b]);
+        } else if constexpr (TWTREE == 1) {
             cx<T> pw[R1];
             twiddle_powers<T, R1>(pw, tw[b]);
 #pragma unroll
@@ -375,7 +398,10 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
 #else
             cell2(0) = a[0];
             // compact table tw2[d] = W_N^(R1*d): adjacent lanes, adjacent cells
-            if constexpr (TWTREE == 1) {
+            if constexpr (TWTAB & 2) {
+#pragma unroll
+                for (int k = 1; k < R2; ++k) cell2(k) = cmul(a[k], tw2[(k - 1) * R3 + d3]);
+            } else if constexpr (TWTREE == 1) {
                 cx<T> pw[R2];
                 twiddle_powers<T, R2>(pw, tw2[d3]);
 #pragma unroll

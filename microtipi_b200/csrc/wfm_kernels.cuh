@@ -408,6 +408,12 @@ struct PipeCtl {
 #ifndef WFM_PSF_TW_TREE
 #define WFM_PSF_TW_TREE 0
 #endif
+#ifndef WFM_PSF_TWTAB
+#define WFM_PSF_TWTAB 0
+#endif
+#ifndef WFM_JAC_TWTAB
+#define WFM_JAC_TWTAB 0
+#endif
 // Row items of the Jacobian bulk-prefetch their next row of conj(a) and q into L2 (TMA prefetch).
 #ifndef WFM_L2_PREFETCH
 #define WFM_L2_PREFETCH 1
@@ -422,14 +428,26 @@ template <typename T, int N> struct PipeCfg {
     // queue claim at the item boundary are paid once per C*KR rows
     static constexpr int KR = ((N / C) % WFM_PIPE_KR == 0 && N >= 256) ? WFM_PIPE_KR : 1;
     static constexpr int ROWS_PER_ITEM = C * KR;
+    // Jacobian row items at 1024 and up: 2 rows per group (0.462 -> 0.425 ms per launch at 1024^2 x 64, the PSF row items
+    // prefer 4: 0.439 vs 0.449 ms)
+#ifdef WFM_PIPE_KR_JAC
+    static constexpr int KR_JAC = WFM_PIPE_KR_JAC;
+#else
+    static constexpr int KR_JAC = (N >= 1024 && KR > 2) ? 2 : KR;
+#endif
+    static constexpr int ROWS_PER_ITEM_JAC = C * KR_JAC;
     static constexpr int SH = ilog2_c(P::S1);
     using ColL = ColLayout<C, SH>;
     static constexpr int ROWLEN = RowLayout<T, N>::LEN;
     static constexpr int COLLEN = ColL::pad_c(N - 1) + 1;
     static constexpr int CELLS = C * (ROWLEN > COLLEN ? ROWLEN : COLLEN);
-    static constexpr int TW2 = 16;                      // stage-2 base twiddles (R3 <= 16 entries)
+    // WFM_{PSF,JAC}_TWTAB: twiddle powers read from shared tables instead of formed by multiplication (fft_inplace TWTAB)
+    static constexpr int TWTAB_ANY = (WFM_PSF_TWTAB) | (WFM_JAC_TWTAB);
+    // stage-2 twiddles: base entries (R3 <= 16), or every power k in [1, R2) when tabulated
+    static constexpr int TW2 = (TWTAB_ANY & 2) ? (((P::R2 - 1) * P::R3 + 1) & ~1) : 16;   // even: what follows stays 16-byte aligned
     // the engine reads tw[b] for b < N/R1 only (stage-1 base twiddles): the shared copy holds just those S1 entries
-    static constexpr int TW1 = P::S1;
+    // (tabulated: R1 - 1 rows of S1 entries, row k-1 = W_N^(b k))
+    static constexpr int TW1 = (TWTAB_ANY & 1) ? (((P::R1 - 1) * P::S1 + 1) & ~1) : P::S1;
     static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(CELLS + TW1 + TW2) + sizeof(int) * (size_t)N +
                                    sizeof(double2) * WFM_CIS_ENTRIES;         // + the e^{i 2 pi k/64} table of wfm_cis
     // Jacobian row items: conj(a) rows arrive by bulk-async copy (TMA) in a per-group landing buffer, one row ahead
@@ -444,10 +462,14 @@ template <typename T, int N> struct PipeCfg {
     // resident CTAs per SM the register allocation is tuned for: 1024 threads (64 registers each)
     static constexpr int BY_THREADS = 1024 / THREADS < 1 ? 1 : (1024 / THREADS > 8 ? 8 : 1024 / THREADS);
     static constexpr int BY_SMEM = (int)((220 * 1024) / SMEM) < 1 ? 1 : (int)((220 * 1024) / SMEM);
+    // 16 fp64 complex values per thread are 64 registers of data alone: at three resident 256-thread CTAs (85 registers)
+    // the 1024-point kernels spill hundreds of bytes per thread (measured 1.05-1.27 vs 0.92 ms per step at 1024^2 x 64)
+    static constexpr int BY_REGS = (sizeof(T) == 8 && P::E >= 16) ? (512 / THREADS < 1 ? 1 : 512 / THREADS) : 8;
 #ifdef WFM_PIPE_MINB
     static constexpr int MINB = WFM_PIPE_MINB;
 #else
-    static constexpr int MINB = BY_THREADS < BY_SMEM ? BY_THREADS : BY_SMEM;
+    static constexpr int MINB0 = BY_THREADS < BY_SMEM ? BY_THREADS : BY_SMEM;
+    static constexpr int MINB = MINB0 < BY_REGS ? MINB0 : BY_REGS;
 #endif
     // The Jacobian pipeline spills at 64 registers (hoisted strip offsets + pointwise part); it is
     // faster with ~85 registers and three quarters of the CTAs (measured 0.410 vs 0.432 ms at 512^2).
@@ -700,8 +722,8 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int bm, int ri
             v[e] = val;
         }
     }
-    fft_inplace<T, P, L, CtaSync, PipePrefetchHook<>, NARROW, WFM_PSF_TW_TREE>(v, cells + c, t, tw_s, tw_s + PipeCfg<T, N>::TW1, 0,
-                                                                               PipePrefetchHook<>{qu, ctl, a.g.nzl, NoClaimAction{}});
+    fft_inplace<T, P, L, CtaSync, PipePrefetchHook<>, NARROW, WFM_PSF_TW_TREE, NoHook, WFM_PSF_TWTAB>(
+        v, cells + c, t, tw_s, tw_s + PipeCfg<T, N>::TW1, 0, PipePrefetchHook<>{qu, ctl, a.g.nzl, NoClaimAction{}});
     pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
     cx<T>* dst = a.T1 + (size_t)ringoff + (size_t)sub * N * C + c;
 #pragma unroll
@@ -769,7 +791,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ringoff, c
             v[e] = (leg_live<P::R1, NARROW>(e % P::R1) && xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
 #endif
 #endif
-        fft_inplace<T, P, L, RowSync<TT>, NoHook, NARROW, WFM_PSF_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
+        fft_inplace<T, P, L, RowSync<TT>, NoHook, NARROW, WFM_PSF_TW_TREE, NoHook, WFM_PSF_TWTAB>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
 #ifdef WFM_PROBE_PSF_L2ST          /* timing probe only (wrong results): stores that never reach DRAM */
         const size_t base = (size_t)N * (blockIdx.x * C + slot);
 #else
@@ -791,6 +813,24 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ringoff, c
     }
 }
 
+// shared twiddle tables of a pipeline CTA, from the global W_N table (tw[m] = W_N^m)
+template <typename T, int N> WFM_DEVI void pipe_fill_twiddles(cx<T>* tw_s, cx<T>* tw2_s, const cx<T>* __restrict__ tw) {
+    using Cfg = PipeCfg<T, N>;
+    using P = Plan<N>;
+    for (int i = threadIdx.x; i < ((Cfg::TWTAB_ANY & 1) ? (P::R1 - 1) * P::S1 : P::S1); i += Cfg::THREADS) {
+        const int k = i / P::S1 + 1, b = i % P::S1;          // row k-1: W_N^(b k); row 0 is the base table
+        tw_s[i] = tw[(b * k) % N];
+    }
+    if constexpr (Cfg::TWTAB_ANY & 2) {
+        for (int i = threadIdx.x; i < (P::R2 - 1) * P::R3; i += Cfg::THREADS) {
+            const int k = i / P::R3 + 1, d3 = i % P::R3;
+            tw2_s[i] = tw[(P::R1 * d3 * k) % N];
+        }
+    } else {
+        if (threadIdx.x < P::R3) tw2_s[threadIdx.x] = tw[P::R1 * threadIdx.x];
+    }
+}
+
 template <typename T, int N, bool NARROW>
 __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k_psf_pipeline(PsfArgs<T> a, PipeCtl ctl) {
     using Cfg = PipeCfg<T, N>;
@@ -799,9 +839,9 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
     cx<T>* tw2_s = tw_s + Cfg::TW1;
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     double2* cis_s = reinterpret_cast<double2*>(invx_s + N);
-    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { if (i < Cfg::TW1) tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
+    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) invx_s[i] = a.inv_x[i];
+    pipe_fill_twiddles<T, N>(tw_s, tw2_s, a.tw);
     if (threadIdx.x < WFM_CIS_ENTRIES) cis_s[threadIdx.x] = a.cis[threadIdx.x];
-    if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
     wfm_grid_dep_trigger();  // the next kernel's CTAs may take the place of ours as we exit
     wfm_grid_dep_wait();     // the tables above are constants; everything below depends on the previous kernel
     __shared__ int s_queue[2 * PipeQueue::SLOT];
@@ -868,7 +908,7 @@ template <typename T, int N> struct JacClaimPrefetch {
 #if WFM_CLAIM_PREFETCH && WFM_L2_PREFETCH
         using Cfg = PipeCfg<T, N>;
         if (it.type != 0) return;
-        const size_t base = (size_t)it.plane * N * N + (size_t)N * (it.sub * Cfg::ROWS_PER_ITEM);
+        const size_t base = (size_t)it.plane * N * N + (size_t)N * (it.sub * Cfg::ROWS_PER_ITEM_JAC);
 #pragma unroll
         for (int r = 0; r < Cfg::C; ++r) {
             wfm_prefetch_l2(&cpx[base + (size_t)N * r], (unsigned)(N * sizeof(cx<T>)));
@@ -924,7 +964,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
     if constexpr (Cfg::JAC_TMA) {
         // first row of the item: nothing of this group is in flight any more (its previous item is complete), so the
         // landing buffer is free; the copy is an L2 hit when the claim-time prefetch was in time
-        const size_t base0 = (size_t)pl * N * N + (size_t)N * (sub * Cfg::ROWS_PER_ITEM + slot);
+        const size_t base0 = (size_t)pl * N * N + (size_t)N * (sub * Cfg::ROWS_PER_ITEM_JAC + slot);
         RowBulkLoadHook first{landing + (size_t)slot * N, &a.cpx[base0], (unsigned)(N * sizeof(cx<T>)), &mbar[slot], t == 0,
                               landq + (size_t)slot * N, &a.q[base0], Cfg::JAC_TMA_Q ? (unsigned)(N * sizeof(T)) : 0u};
         first();
@@ -943,7 +983,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
     cx<T> nc[E];
     T nq[E];
     {
-        const size_t base0 = (size_t)pl * N * N + (size_t)N * (sub * Cfg::ROWS_PER_ITEM + slot);
+        const size_t base0 = (size_t)pl * N * N + (size_t)N * (sub * Cfg::ROWS_PER_ITEM_JAC + slot);
 #pragma unroll
         for (int u = 0; u < E / P::R1; ++u)
 #pragma unroll
@@ -958,10 +998,10 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
 #pragma unroll
     for (int e = 0; e < E; ++e) qn[e] = (T)0;
 #pragma unroll 1
-    for (int kk = 0; kk < Cfg::KR; ++kk) {
-        if (kk == Cfg::KR - 1 && qu.prefetch(ctl, a.g.nzl))           // claim the next item behind the last row
+    for (int kk = 0; kk < Cfg::KR_JAC; ++kk) {
+        if (kk == Cfg::KR_JAC - 1 && qu.prefetch(ctl, a.g.nzl))           // claim the next item behind the last row
             JacClaimPrefetch<T, N>{a.cpx, a.q}(qu.peek_next());
-        const int y = sub * Cfg::ROWS_PER_ITEM + kk * C + slot;      // N % ROWS_PER_ITEM == 0
+        const int y = sub * Cfg::ROWS_PER_ITEM_JAC + kk * C + slot;      // N % ROWS_PER_ITEM == 0
 #if defined(WFM_PROBE_JAC_L1)      /* timing probes only (wrong results): what if the row loads never left the SM / the L2? */
         const size_t base = 0;
 #elif defined(WFM_PROBE_JAC_L2)
@@ -970,7 +1010,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
         const size_t base = (size_t)pl * N * N + (size_t)N * y;
 #endif
 #if WFM_L2_PREFETCH && !defined(WFM_PROBE_JAC_L1) && !defined(WFM_PROBE_JAC_L2)
-        if (t == 0 && kk + 1 < Cfg::KR) {              // this group's next row: DRAM -> L2 while this row is transformed
+        if (t == 0 && kk + 1 < Cfg::KR_JAC) {              // this group's next row: DRAM -> L2 while this row is transformed
             if constexpr (!Cfg::JAC_TMA) wfm_prefetch_l2(&a.cpx[base + (size_t)N * C], (unsigned)(N * sizeof(cx<T>)));
             if constexpr (!Cfg::JAC_TMA_Q) wfm_prefetch_l2(&a.q[base + (size_t)N * C], (unsigned)(N * sizeof(T)));
         }
@@ -979,7 +1019,7 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
 #if WFM_ROW_PREFETCH
 #pragma unroll
         for (int e = 0; e < E; ++e) v[e] = mkc<T>(nc[e].x * nq[e], nc[e].y * nq[e]);
-        if (kk + 1 < Cfg::KR) {                        // next row in flight during this row's transform
+        if (kk + 1 < Cfg::KR_JAC) {                        // next row in flight during this row's transform
             const size_t nb = base + (size_t)N * C;
 #pragma unroll
             for (int u = 0; u < E / P::R1; ++u)
@@ -1035,23 +1075,23 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
         }
 #endif
         if constexpr (Cfg::JAC_TMA) {
-            const bool more = kk + 1 < Cfg::KR;
+            const bool more = kk + 1 < Cfg::KR_JAC;
             RowBulkLoadHook hk{landing + (size_t)slot * N, &a.cpx[base + (more ? (size_t)N * C : 0)],
                                (unsigned)(N * sizeof(cx<T>)), &mbar[slot], more && t == 0,
                                landq + (size_t)slot * N, &a.q[base + (more ? (size_t)N * C : 0)],
                                Cfg::JAC_TMA_Q ? (unsigned)(N * sizeof(T)) : 0u};
             using QHook = RowQAheadHook<T, E, P::R1, TT, P::S1>;
             QHook qh{qn, &a.q[base + (more ? (size_t)N * C : 0)], t, WFM_JAC_Q_AHEAD && more && !Cfg::JAC_TMA_Q};
-            fft_inplace<T, P, L, RowSync<TT>, RowBulkLoadHook, false, WFM_JAC_TW_TREE, QHook>(v, cells + slot * L::LEN, t, tw_s,
-                                                                                            tw_s + PipeCfg<T, N>::TW1, slot, hk, qh);
+            fft_inplace<T, P, L, RowSync<TT>, RowBulkLoadHook, false, WFM_JAC_TW_TREE, QHook, WFM_JAC_TWTAB>(v, cells + slot * L::LEN, t, tw_s,
+                                                                                                           tw_s + PipeCfg<T, N>::TW1, slot, hk, qh);
         } else {
-            fft_inplace<T, P, L, RowSync<TT>, NoHook, false, WFM_JAC_TW_TREE>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
+            fft_inplace<T, P, L, RowSync<TT>, NoHook, false, WFM_JAC_TW_TREE, NoHook, WFM_JAC_TWTAB>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
         }
         cx<T>* dst = a.T2 + (size_t)ringoff + (size_t)y * C;
 #pragma unroll
         for (int e = 0; e < E; ++e)
             if (leg_live<P::RL, NARROW>(e % P::RL) && xis[e] >= 0) __stcg(&dst[xis[e]], v[e]);
-        if (kk + 1 < Cfg::KR) RowSync<TT>::sync(slot);
+        if (kk + 1 < Cfg::KR_JAC) RowSync<TT>::sync(slot);
     }
 }
 
@@ -1089,8 +1129,8 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int bm, int ri
             if (leg_live<P::RL, NARROW>(r))
                 fl |= (unsigned)__ldg(&a.st.flags[sbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
     using ClaimHook = PipePrefetchHook<JacClaimPrefetch<T, N>>;
-    fft_inplace<T, P, L, CtaSync, ClaimHook, false, WFM_JAC_TW_TREE>(v, cells + c, t, tw_s, tw_s + PipeCfg<T, N>::TW1, 0,
-                                                                     ClaimHook{qu, ctl, a.g.nzl, JacClaimPrefetch<T, N>{a.cpx, a.q}});
+    fft_inplace<T, P, L, CtaSync, ClaimHook, false, WFM_JAC_TW_TREE, NoHook, WFM_JAC_TWTAB>(
+        v, cells + c, t, tw_s, tw_s + PipeCfg<T, N>::TW1, 0, ClaimHook{qu, ctl, a.g.nzl, JacClaimPrefetch<T, N>{a.cpx, a.q}});
     const int iz = a.g.z0 + (pl - bm * a.g.nzm);
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
     const bool mod_plane = (a.Gm != nullptr) && (!a.last_plane_only || iz == a.g.nz_global - 1);
@@ -1124,7 +1164,8 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
     cx<T>* tw2_s = tw_s + Cfg::TW1;
     int* invx_s = reinterpret_cast<int*>(tw2_s + Cfg::TW2);
     double2* cis_s = reinterpret_cast<double2*>(invx_s + N);
-    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) { if (i < Cfg::TW1) tw_s[i] = a.tw[i]; invx_s[i] = a.inv_x[i]; }
+    for (int i = threadIdx.x; i < N; i += Cfg::THREADS) invx_s[i] = a.inv_x[i];
+    pipe_fill_twiddles<T, N>(tw_s, tw2_s, a.tw);
     if (threadIdx.x < WFM_CIS_ENTRIES) cis_s[threadIdx.x] = a.cis[threadIdx.x];
     // landing buffers of the row items (bulk-async copies of conj(a) rows) and their barriers
     cx<T>* landing = reinterpret_cast<cx<T>*>(cis_s + WFM_CIS_ENTRIES);
@@ -1134,7 +1175,6 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
         if (threadIdx.x < Cfg::C) wfm_mbar_init(&mbar[threadIdx.x], 1);
         wfm_mbar_init_fence();
     }
-    if (threadIdx.x < Plan<N>::R3) tw2_s[threadIdx.x] = a.tw[Plan<N>::R1 * threadIdx.x];
     wfm_grid_dep_trigger();  // the next kernel's CTAs may take the place of ours as we exit
     wfm_grid_dep_wait();     // the tables above are constants; everything below depends on the previous kernel
     __shared__ int s_queue[2 * PipeQueue::SLOT];
@@ -1195,6 +1235,7 @@ struct ReduceArgs {
     double dxy, lambda_ni, deltaX, deltaY;
     const double* bpar;      // batch handles: [nbatch][4] = {ni/lambda, deltaX, deltaY, 1/|beta|} per model, else NULL
     int cpm;                 // plane chunks per model: grid.y = nbatch * cpm
+    int batches;             // batches of WFM_RED_PLANES planes per chunk (1 .. WFM_RED_BATCHES), chosen per launch
     double* block_part;      // [nbatch][cpm][nblocks][glen]
     int glen;                // 3 + nphase + nmod
 };
@@ -1205,8 +1246,9 @@ struct ReduceArgs {
 #define WFM_RED_PLANES 16   // loads a thread keeps in flight at once; 4 and 8 measured slower
 #endif
 #ifndef WFM_RED_BATCHES
-#define WFM_RED_BATCHES 4   // batches of WFM_RED_PLANES a thread sums one after the other: a CTA owns a chunk of
-#endif                      // 64 planes, so that 512^2 x 256 is ONE wave of 360 CTAs (was 2.4 waves of 1440)
+#define WFM_RED_BATCHES 4   // most batches of WFM_RED_PLANES a thread sums one after the other: a CTA owns a chunk of up to
+#endif                      // 64 planes, so that 512^2 x 256 is ONE wave of 360 CTAs (was 2.4 waves of 1440); small stacks
+                            // take fewer batches per chunk so that the grid still fills the GPU (launch_jac_reduce)
 #define WFM_RED_CHUNK_PLANES (WFM_RED_PLANES * WFM_RED_BATCHES)
 
 // One thread per support cell and per chunk of WFM_RED_PLANES planes.  Sums the planes of the chunk
@@ -1224,12 +1266,13 @@ __global__ void __launch_bounds__(WFM_RED_THREADS) k_jac_reduce(ReduceArgs a) {
     wfm_grid_dep_trigger();
     wfm_grid_dep_wait();                               // Gj / Gm come from the pipeline kernel before us
     const int bm = blockIdx.y / a.cpm;                 // model of a batch handle (0 otherwise); chunks never straddle models
-    const int zc0 = (blockIdx.y - bm * a.cpm) * WFM_RED_CHUNK_PLANES;   // first plane of the chunk inside its model
-    const int pend = (zc0 + WFM_RED_CHUNK_PLANES < a.g.nzm) ? bm * a.g.nzm + zc0 + WFM_RED_CHUNK_PLANES : (bm + 1) * a.g.nzm;
+    const int chunk_planes = WFM_RED_PLANES * a.batches;
+    const int zc0 = (blockIdx.y - bm * a.cpm) * chunk_planes;          // first plane of the chunk inside its model
+    const int pend = (zc0 + chunk_planes < a.g.nzm) ? bm * a.g.nzm + zc0 + chunk_planes : (bm + 1) * a.g.nzm;
     const bool m = sup && (a.flags[(size_t)bm * img + cell] & 1u);
     double gP = 0.0, gD = 0.0, gM = 0.0;
 #pragma unroll 1
-    for (int bt = 0; bt < WFM_RED_BATCHES; ++bt) {
+    for (int bt = 0; bt < a.batches; ++bt) {
         const int zl0 = zc0 + bt * WFM_RED_PLANES;
         const int p0 = bm * a.g.nzm + zl0;
         if (p0 >= pend) break;

@@ -10,7 +10,7 @@ stage-3 read).
 import itertools, sys
 
 PLANS = {32: (8, 8, 4, 1), 64: (8, 8, 8, 1), 128: (8, 8, 4, 4), 256: (8, 8, 8, 4),
-         512: (8, 8, 8, 8), 1024: (16, 16, 8, 8), 2048: (16, 16, 16, 8)}
+         512: (8, 8, 8, 8), 1024: (16, 8, 8, 16), 2048: (16, 16, 16, 8)}
 
 
 def pad(i, pa, pb):
