@@ -14,7 +14,10 @@
 #include <cstring>
 #include <functional>
 #include <new>
+#include <atomic>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace wfm;
@@ -62,6 +65,9 @@ struct wfm_model {
     // (winN == 0: the whole slab); in_stream carries the H2D chunks of q, ev_chunk[c] marks chunk c
     int win0 = 0, winN = 0;
     cudaStream_t in_stream = nullptr;
+    // pageable host arrays (Java-heap double[] behind GetPrimitiveArrayCritical, numpy): multi-threaded staging (HostStage)
+    struct HostStage* stage = nullptr;
+    int siblings = 1;                             // children of a multi-device handle share the host's cores
     std::vector<cudaEvent_t> ev_chunk, ev_in;
     // optics (WFM:161-166)
     bool have_optics = false;
@@ -174,7 +180,144 @@ struct Exchange {
     bool connected = false;
 };
 
+// ---- pageable host arrays: staged, multi-threaded copies ---------------------------------------------------------
+// cudaMemcpy from / to ordinary (pageable) memory goes through the driver's bounce buffer on ONE thread: ~6-7 GB/s here
+// (78 ms for the 2 x 537 MB of a 512^2 x 256 step against 12 ms from pinned buffers).  TiPi's arrays are Java-heap
+// double[]: whatever the binding does, the library sees pageable memory.  So for large pageable arrays the
+// library stages itself: T host threads copy their share of every PIECE between the caller's array and pinned slots
+// (two per thread: one being filled or drained by the thread, one on the PCIe link), and the device copies of the
+// pieces are queued as they become ready.
+struct HostStage {
+    int threads = 0;
+    size_t share = 0;                          // bytes per thread and slot
+    std::vector<void*> slot;                   // [threads][2], pinned
+    std::vector<cudaEvent_t> ev;               // [threads][2]: the slot's last device copy has completed
+    size_t piece() const { return share * (size_t)threads; }
+    void release() {
+        for (void* p : slot) if (p) cudaFreeHost(p);
+        for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+        slot.clear(); ev.clear(); threads = 0;
+    }
+};
+
 namespace {
+
+bool host_is_pageable(const void* p) {
+    if (getenv("WFM_FORCE_STAGED")) return true;           // (tests: take the staged path for any pointer)
+    if (getenv("WFM_NO_STAGED")) return false;
+#ifdef WFM_EMU
+    (void)p;
+    return false;
+#else
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+#endif
+}
+
+// the staging area of a handle (created on first use, kept): NULL when staging is off or cannot be set up
+HostStage* host_stage(wfm_model* h) {
+    if (h->stage) return h->stage->threads > 0 ? h->stage : nullptr;
+    h->stage = new HostStage();
+    int t = (int)std::thread::hardware_concurrency() / (2 * (h->siblings > 0 ? h->siblings : 1));
+    if (t > 8) t = 8;
+    if (const char* e = getenv("WFM_HOST_THREADS")) t = atoi(e);
+    if (t < 1) t = 1;
+    size_t share = (size_t)4 << 20;
+    if (const char* e = getenv("WFM_HOST_SHARE_BYTES")) share = (size_t)atoll(e);          // (tests: many small pieces)
+    share = (share + 255) / 256 * 256;
+    HostStage* st = h->stage;
+    st->slot.assign((size_t)2 * t, nullptr); st->ev.assign((size_t)2 * t, nullptr);
+    for (int i = 0; i < 2 * t; ++i)
+        if (cudaHostAlloc(&st->slot[i], share, cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&st->ev[i], cudaEventDisableTiming) != cudaSuccess) { st->release(); cudaGetLastError(); return nullptr; }
+    st->threads = t; st->share = share;
+    return st;
+}
+
+// Host -> device through the staging slots, on `stream`.  Returns after every piece has been QUEUED; on_piece(k) is
+// called on the calling thread, in order, once piece k (bytes [k*piece, (k+1)*piece)) is completely queued.
+template <class F> int staged_h2d(wfm_model* h, HostStage* st, void* dev, const void* host, size_t bytes, cudaStream_t stream,
+                                  F on_piece) {
+    const int T = st->threads;
+    const size_t piece = st->piece();
+    const int npieces = (int)((bytes + piece - 1) / piece);
+    std::unique_ptr<std::atomic<int>[]> arrived(new std::atomic<int>[npieces]);
+    for (int k = 0; k < npieces; ++k) arrived[k].store(0);
+    std::atomic<int> failed{0};
+    const int device = h->device;
+    auto work = [&](int w) {
+        if (cudaSetDevice(device) != cudaSuccess) failed.store(1);
+        for (int k = 0; k < npieces; ++k) {
+            const int s = 2 * w + (k & 1);
+            const size_t off = (size_t)k * piece + (size_t)w * st->share;
+            if (off < bytes && !failed.load()) {
+                const size_t len = std::min(st->share, bytes - off);
+                if (k >= 2 && cudaEventSynchronize(st->ev[s]) != cudaSuccess) failed.store(1);   // the slot's previous copy has left
+                memcpy(st->slot[s], (const char*)host + off, len);
+                if (cudaMemcpyAsync((char*)dev + off, st->slot[s], len, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+                    cudaEventRecord(st->ev[s], stream) != cudaSuccess) failed.store(1);
+            }
+            arrived[k].fetch_add(1);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
+    int rc = WFM_OK;
+    if (T == 1) {
+        work(0);
+        for (int k = 0; k < npieces && !rc; ++k) rc = on_piece(k);
+    } else {
+        pool.emplace_back(work, 0);
+        for (int k = 0; k < npieces; ++k) {
+            while (arrived[k].load() < T) std::this_thread::yield();
+            if (!rc) rc = on_piece(k);
+        }
+    }
+    for (auto& t : pool) t.join();
+    if (failed.load()) { cudaGetLastError(); return h->fail(WFM_ERR_CUDA, "staged host -> device copy failed"); }
+    return rc;
+}
+
+// Device -> host through the staging slots, on `stream`; blocks until `host` holds all the bytes.  ready(b) must return
+// (after queueing what `stream` has to wait for) once the device bytes [0, b) may be read; it is called by the worker
+// threads with increasing b.
+template <class F> int staged_d2h(wfm_model* h, HostStage* st, void* host, const void* dev, size_t bytes, cudaStream_t stream,
+                                  F ready) {
+    const int T = st->threads;
+    const size_t piece = st->piece();
+    const int npieces = (int)((bytes + piece - 1) / piece);
+    std::atomic<int> failed{0};
+    const int device = h->device;
+    auto work = [&](int w) {
+        if (cudaSetDevice(device) != cudaSuccess) failed.store(1);
+        auto queue = [&](int k) {
+            const size_t off = (size_t)k * piece + (size_t)w * st->share;
+            if (off >= bytes || failed.load()) return;
+            const size_t len = std::min(st->share, bytes - off);
+            const int s = 2 * w + (k & 1);
+            if (ready(off + len) != WFM_OK) { failed.store(1); return; }
+            if (cudaMemcpyAsync(st->slot[s], (const char*)dev + off, len, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                cudaEventRecord(st->ev[s], stream) != cudaSuccess) failed.store(1);
+        };
+        queue(0);
+        for (int k = 0; k < npieces; ++k) {
+            if (k + 1 < npieces) queue(k + 1);                   // the other slot: on the link while this one is drained
+            const size_t off = (size_t)k * piece + (size_t)w * st->share;
+            if (off >= bytes || failed.load()) continue;
+            const size_t len = std::min(st->share, bytes - off);
+            const int s = 2 * w + (k & 1);
+            if (cudaEventSynchronize(st->ev[s]) != cudaSuccess) { failed.store(1); continue; }
+            memcpy((char*)host + off, st->slot[s], len);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
+    work(0);
+    for (auto& t : pool) t.join();
+    if (failed.load()) { cudaGetLastError(); return h->fail(WFM_ERR_CUDA, "staged device -> host copy failed"); }
+    return WFM_OK;
+}
 
 cudaEvent_t take_event(wfm_model* h) {
     if (!h->free_events.empty()) { cudaEvent_t e = h->free_events.back(); h->free_events.pop_back(); return e; }
@@ -926,6 +1069,7 @@ int wfm_destroy(wfm_model* h) {
     if (h->in_stream) { cudaStreamSynchronize(h->in_stream); cudaStreamDestroy(h->in_stream); }
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
+    if (h->stage) { h->stage->release(); delete h->stage; h->stage = nullptr; }
     if (h->ev_ready) cudaEventDestroy(h->ev_ready);
     if (h->ev_copied) cudaEventDestroy(h->ev_copied);
     if (h->ev_order) cudaEventDestroy(h->ev_order);
@@ -1225,9 +1369,34 @@ int wfm_set_modulus_mode(wfm_model* h, int mode) {
     return WFM_OK;
 }
 
+static int ensure_copy_stream(wfm_model* h) {
+    if (h->copy_stream) return WFM_OK;
+    WFM_CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    WFM_CK(h, cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+    WFM_CK(h, cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+    return WFM_OK;
+}
+
+#define WFM_STAGED_MIN_BYTES ((size_t)8 << 20)
+static bool use_staging(const void* host, size_t bytes) {
+    size_t min_bytes = WFM_STAGED_MIN_BYTES;
+    if (const char* e = getenv("WFM_STAGED_MIN_BYTES")) min_bytes = (size_t)atoll(e);
+    return bytes >= min_bytes && host_is_pageable(host);
+}
+
 static int copy_out(wfm_model* h, void* out, const void* dev, size_t bytes) {
     if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
     WFM_ENTER(h);
+    HostStage* st = use_staging(out, bytes) ? host_stage(h) : nullptr;
+    if (st) {                                     // large pageable destination: staged, multi-threaded
+        int rc = ensure_copy_stream(h); if (rc) return rc;
+        WFM_CK(h, cudaEventRecord(h->ev_ready, h->stream));
+        WFM_CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
+        rc = staged_d2h(h, st, out, dev, bytes, h->copy_stream, [](size_t) { return (int)WFM_OK; });
+        if (rc) return rc;
+        WFM_CK(h, cudaStreamSynchronize(h->stream));
+        return check_pipeline(h);
+    }
     WFM_CK(h, cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
     WFM_CK(h, cudaStreamSynchronize(h->stream));
     return check_pipeline(h);
@@ -1261,8 +1430,33 @@ int wfm_get_psf(wfm_model* h, void* out) {
     if (!h) return WFM_ERR_INVALID_ARG;
     if (h->multi()) return wfm_multi::get_stack(h, out, false, false);
     WFM_ENTER(h);
+    if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
+    const size_t plane = (size_t)h->npix() * h->esz(), bytes = plane * h->nzl;
+    const int cp = (h->pstate > 0) ? 0 : host_chunk_planes(h);
+    HostStage* st = (cp > 0 && use_staging(out, bytes)) ? host_stage(h) : nullptr;
+    if (st) {
+        // dirty PSF into a large pageable array: computePsf in plane windows (all queued at once), the staged read-back
+        // of a piece waits for the window that holds its last byte
+        int rc = ensure_copy_stream(h); if (rc) return rc;
+        const int nwin = (h->nzl + cp - 1) / cp;
+        rc = ensure_chunk_events(h, h->ev_chunk, nwin); if (rc) return rc;
+        rc = compute_psf_windows(h, cp, [&](int p0, int) {
+            WFM_CK(h, cudaEventRecord(h->ev_chunk[p0 / cp], h->stream));
+            return (int)WFM_OK;
+        });
+        if (rc) return rc;
+        const size_t wbytes = plane * cp;
+        cudaStream_t cs = h->copy_stream;
+        const std::vector<cudaEvent_t>& evs = h->ev_chunk;
+        rc = staged_d2h(h, st, out, h->psf.p, bytes, cs, [&evs, cs, wbytes](size_t b) {
+            return cudaStreamWaitEvent(cs, evs[(b - 1) / wbytes], 0) == cudaSuccess ? (int)WFM_OK : (int)WFM_ERR_CUDA;
+        });
+        if (rc) return rc;
+        WFM_CK(h, cudaStreamSynchronize(h->stream));
+        return check_pipeline(h);
+    }
     int rc = compute_psf_impl(h); if (rc) return rc;                           // WFM:1800-1802
-    return copy_out(h, out, h->psf.p, (size_t)h->npix() * h->nzl * h->esz());
+    return copy_out(h, out, h->psf.p, bytes);
 }
 
 // getPsf() whose device->host copy runs on the handle's second stream: returns once the copy is queued.
@@ -1273,11 +1467,7 @@ int wfm_get_psf_async(wfm_model* h, void* out) {
     if (h->multi()) return wfm_multi::get_stack(h, out, false, true);
     WFM_ENTER(h);
     if (!out) return h->fail(WFM_ERR_INVALID_ARG, "output pointer is NULL");
-    if (!h->copy_stream) {
-        WFM_CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        WFM_CK(h, cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
-        WFM_CK(h, cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
-    }
+    { int rc0 = ensure_copy_stream(h); if (rc0) return rc0; }
     const int cp = (h->pstate > 0) ? 0 : host_chunk_planes(h);
     if (cp > 0) {
         // dirty PSF: computePsf in plane windows, every window's read-back queued right behind it on the second stream
@@ -1392,7 +1582,34 @@ static int apply_host_single(wfm_model* h, unsigned kinds, const void* q_host, d
     WFM_CK(h, h->qdev.ensure(bytes));
     WFM_CK(h, h->grad.ensure(8 * (size_t)h->glen() * h->nbatch));
     const int cp = host_chunk_planes(h);
-    if (cp <= 0) {
+    HostStage* st = use_staging(q_host, bytes) ? host_stage(h) : nullptr;
+    if (st) {
+        // large pageable q: staged through pinned slots by the host threads; the adjoint window of a plane chunk is
+        // launched as soon as the pieces that hold it have been queued
+        if (!h->in_stream) WFM_CK(h, cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking));
+        const int wp = cp > 0 ? cp : h->nzl;                                   // planes per window (one window: the slab)
+        const int nwin = (h->nzl + wp - 1) / wp;
+        rc = ensure_chunk_events(h, h->ev_in, nwin); if (rc) return rc;
+        rc = compute_psf_impl(h); if (rc) return rc;                           // quirk Q5 (queued; the staging overlaps it)
+        int next = 0;
+        const size_t piece = st->piece();
+        rc = staged_h2d(h, st, h->qdev.p, q_host, bytes, h->in_stream, [&](int k) {
+            const size_t have = std::min(bytes, (size_t)(k + 1) * piece);
+            while (next < nwin && plane * (size_t)std::min(h->nzl, (next + 1) * wp) <= have) {
+                const int p0 = next * wp, np = std::min(wp, h->nzl - p0);
+                WFM_CK(h, cudaEventRecord(h->ev_in[next], h->in_stream));
+                WFM_CK(h, cudaStreamWaitEvent(h->stream, h->ev_in[next], 0));
+                if (nwin > 1) { h->win0 = p0; h->winN = np; }
+                const int r = (h->precision == WFM_F64) ? dispatch_jac<double>(h, kinds, h->qdev.p, (double*)h->grad.p)
+                                                        : dispatch_jac<float>(h, kinds, h->qdev.p, (double*)h->grad.p);
+                h->win0 = 0; h->winN = 0;
+                if (r) return r;
+                ++next;
+            }
+            return (int)WFM_OK;
+        });
+        if (rc) { cudaStreamSynchronize(h->in_stream); cudaStreamSynchronize(h->stream); return rc; }
+    } else if (cp <= 0) {
         WFM_CK(h, cudaMemcpyAsync(h->qdev.p, q_host, bytes, cudaMemcpyHostToDevice, h->stream));
         rc = wfm_apply_jacobian_dev(h, kinds, h->qdev.p, (double*)h->grad.p); if (rc) return rc;
     } else {

@@ -157,6 +157,7 @@ int wfm_create_multi(wfm_model** out, int nx, int ny, int nz, double dxy, double
         wfm_model* c = nullptr;
         const int rc = wfm_create_slab(&c, nx, ny, nz, z0, nzl, dxy, dz, precision, devices[i]);
         if (rc != WFM_OK) { wfm_multi::destroy(h); return rc; }          // g_create_error set by the child
+        c->siblings = n_dev;                                             // (the children share the host's cores when they stage)
         h->parts.push_back(c);
         h->part_z0.push_back(z0);
         z0 += nzl;

@@ -360,6 +360,10 @@ def test_gpu_case_helpers_at_small_sizes(lib):
     from tests.test_gpu_parity import chunked_host_case, escape_hatch_case, full_stack_case
     chunked_host_case(lib, 32, 40, 7, 29, False, {"WFM_HOST_CHUNKS": "4", "WFM_HOST_CHUNK_MIN_BYTES": "1"})
     chunked_host_case(lib, 32, 12, 0, 12, True, {"WFM_HOST_CHUNKS": "3", "WFM_HOST_CHUNK_MIN_BYTES": "1"})
+    staged = {"WFM_FORCE_STAGED": "1", "WFM_STAGED_MIN_BYTES": "1"}          # the pageable-array path: staged by host threads
+    chunked_host_case(lib, 32, 40, 7, 29, False, dict(staged, WFM_HOST_THREADS="3", WFM_HOST_SHARE_BYTES="5000",
+                                                      WFM_HOST_CHUNKS="4", WFM_HOST_CHUNK_MIN_BYTES="1"))
+    chunked_host_case(lib, 32, 12, 0, 12, True, dict(staged, WFM_HOST_THREADS="1", WFM_HOST_SHARE_BYTES="3000"))
     full_stack_case(lib, 32, 96, 40, 50, False)
     full_stack_case(lib, 32, 16, 3, 9, True)
     escape_hatch_case(lib, ((32, 5, 0.2), (32, 3, 0.4)))

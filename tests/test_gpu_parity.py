@@ -395,6 +395,9 @@ def chunked_host_case(lib, N, Nz, z0, nzl, single, env):
         assert o.rel_l2(d, gd) <= tj and o.rel_l2(p, gp) <= tj and o.rel_l2(mo, gm) <= tj
         assert o.rel_l2(m.apply_J_defocus(q).data, gd) <= tj
         assert o.rel_l2(m.apply_J_modulus(q).data, gm) <= tj
+        m.setPhase(alpha)                             # dirty again: the synchronous getPsf() (plane windows; staged through
+        got = m.getPsf()                              # pinned slots by the host threads when the array is pageable)
+        assert max(o.rel_l2(got[l], psf[l]) for l in range(nzl)) <= t
         out[:] = -1
         m.getPsfAsync(hp.value); m.waitTransfers()    # clean PSF: one copy
         assert max(o.rel_l2(out[l], psf[l]) for l in range(nzl)) <= t
@@ -417,6 +420,11 @@ def chunked_host_case(lib, N, Nz, z0, nzl, single, env):
     (512, 256, 0, 256, False, {}),                                                        # default policy: 8 chunks of 32 planes
     (256, 128, 40, 70, False, {"WFM_HOST_CHUNKS": "4", "WFM_HOST_CHUNK_MIN_BYTES": "1"}),  # ragged last chunk (18, 18, 18, 16)
     (256, 64, 0, 64, True, {"WFM_HOST_CHUNKS": "3", "WFM_HOST_CHUNK_MIN_BYTES": "1"}),
+    (512, 256, 0, 256, False, {"WFM_FORCE_STAGED": "1"}),                                 # pageable-array path, default policy
+    (256, 128, 40, 70, False, {"WFM_FORCE_STAGED": "1", "WFM_STAGED_MIN_BYTES": "1", "WFM_HOST_THREADS": "3",
+                               "WFM_HOST_SHARE_BYTES": "300000", "WFM_HOST_CHUNKS": "4", "WFM_HOST_CHUNK_MIN_BYTES": "1"}),
+    (128, 16, 0, 16, True, {"WFM_FORCE_STAGED": "1", "WFM_STAGED_MIN_BYTES": "1", "WFM_HOST_THREADS": "1",
+                            "WFM_HOST_SHARE_BYTES": "70000"}),                           # one window, one thread
 ])
 def test_host_paths_in_plane_chunks(lib, N, Nz, z0, nzl, single, env):
     chunked_host_case(lib, N, Nz, z0, nzl, single, env)
