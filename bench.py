@@ -689,7 +689,8 @@ def run_e2e(args, torch, dist, lib, w, world, dev, fence, max_over_ranks, planes
         res.append({"value": planes_global * n_it / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": qbytes + 80,
                     "d2h_bytes_per_step": pbytes + 80, "steps": n_it, "ms_per_step": ms / n_it})
     res[0]["buffers"] = "pinned (wfm_host_alloc), PSF read-back on a second stream beside the H2D of q"
-    res[1]["buffers"] = "pageable numpy arrays (stand-in for Java-heap double[]), synchronous wfm_get_psf"
+    res[1]["buffers"] = ("pageable numpy arrays (stand-in for Java-heap double[]), synchronous wfm_get_psf; the library stages "
+                         "them through pinned slots with its own host threads (WFM_NO_STAGED=1: plain cudaMemcpy)")
     lib.wfm_host_free(hq)
     lib.wfm_host_free(hp)
     return res[0], res[1]

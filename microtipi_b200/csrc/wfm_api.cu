@@ -223,7 +223,7 @@ HostStage* host_stage(wfm_model* h) {
     if (t > 8) t = 8;
     if (const char* e = getenv("WFM_HOST_THREADS")) t = atoi(e);
     if (t < 1) t = 1;
-    size_t share = (size_t)4 << 20;
+    size_t share = (size_t)1 << 20;               // (measured, 2 x 537 MB per step: 256 KB 48.9 ms, 512 KB 41.3, 1 MB 27.0, 2 MB 27.9, 4 MB 28.9, 16 MB 33.7)
     if (const char* e = getenv("WFM_HOST_SHARE_BYTES")) share = (size_t)atoll(e);          // (tests: many small pieces)
     share = (share + 255) / 256 * 256;
     HostStage* st = h->stage;
@@ -795,7 +795,7 @@ template <typename T> int dispatch_jac(wfm_model* h, unsigned kinds, const void*
 // (psf, device -> host) is on the PCIe link, so that only one chunk's kernel time is left outside the copies.
 int host_chunk_planes(const wfm_model* h) {
     if (h->generic || h->nbatch > 1 || h->multi()) return 0;
-    int nch = 8;
+    int nch = 4;                                  // (2 .. 8 chunks measure alike, 11.1-11.8 ms per 2 x 537 MB step; 1: 12.4, 16: 13.1)
     if (const char* e = getenv("WFM_HOST_CHUNKS")) nch = atoi(e);
     if (nch <= 1) return 0;
     const size_t plane = (size_t)h->npix() * h->esz();

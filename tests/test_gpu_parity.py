@@ -417,7 +417,7 @@ def chunked_host_case(lib, N, Nz, z0, nzl, single, env):
 
 
 @pytest.mark.parametrize("N,Nz,z0,nzl,single,env", [
-    (512, 256, 0, 256, False, {}),                                                        # default policy: 8 chunks of 32 planes
+    (512, 256, 0, 256, False, {}),                                                        # default policy: 4 chunks of 64 planes
     (256, 128, 40, 70, False, {"WFM_HOST_CHUNKS": "4", "WFM_HOST_CHUNK_MIN_BYTES": "1"}),  # ragged last chunk (18, 18, 18, 16)
     (256, 64, 0, 64, True, {"WFM_HOST_CHUNKS": "3", "WFM_HOST_CHUNK_MIN_BYTES": "1"}),
     (512, 256, 0, 256, False, {"WFM_FORCE_STAGED": "1"}),                                 # pageable-array path, default policy
