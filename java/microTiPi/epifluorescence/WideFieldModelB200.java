@@ -55,6 +55,17 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
         return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), d);
     }
     private static FunctionDescriptor ints(java.lang.foreign.MemoryLayout... args) { return FunctionDescriptor.of(JAVA_INT, args); }
+    /**
+     * Downcall that may be handed HEAP segments (MemorySegment.ofArray): Linker.Option.critical(true) pins the Java array
+     * for the duration of the call and passes its address, so psf / q / cpxPsf move between the TiPi arrays (double[] /
+     * float[] on the Java heap, SURVEY 8 b4) and the device without a Java-side copy.  The library sees ordinary pageable
+     * memory and stages it itself (host threads + pinned slots, wfm_api.cu "pageable host arrays"): measured 27 ms per
+     * 2 x 537 MB step against 78 ms for a plain cudaMemcpy of pageable memory and 11-12 ms from pinned buffers.
+     * The callee makes no upcalls and returns within milliseconds, as a critical call must.
+     */
+    private static MethodHandle fnHeap(String name, FunctionDescriptor d) {
+        return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), d, Linker.Option.critical(true));
+    }
 
     private static final MethodHandle CREATE = fn("wfm_create", ints(ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_INT, JAVA_INT));
     private static final MethodHandle CREATE_MULTI = fn("wfm_create_multi", ints(ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_INT, ADDRESS, JAVA_INT));
@@ -72,10 +83,10 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
     private static final MethodHandle GET_MASK = fn("wfm_get_mask", ints(ADDRESS, ADDRESS));
     private static final MethodHandle COMPUTE_PSF = fn("wfm_compute_psf", ints(ADDRESS));
     private static final MethodHandle INVALIDATE = fn("wfm_invalidate", ints(ADDRESS));
-    private static final MethodHandle GET_PSF = fn("wfm_get_psf", ints(ADDRESS, ADDRESS));
-    private static final MethodHandle GET_CPX = fn("wfm_get_cpx_psf", ints(ADDRESS, ADDRESS));
-    private static final MethodHandle GET_MTF = fn("wfm_get_mtf", ints(ADDRESS, ADDRESS));
-    private static final MethodHandle APPLY_J = fn("wfm_apply_jacobian", ints(ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    private static final MethodHandle GET_PSF = fnHeap("wfm_get_psf", ints(ADDRESS, ADDRESS));
+    private static final MethodHandle GET_CPX = fnHeap("wfm_get_cpx_psf", ints(ADDRESS, ADDRESS));
+    private static final MethodHandle GET_MTF = fnHeap("wfm_get_mtf", ints(ADDRESS, ADDRESS));
+    private static final MethodHandle APPLY_J = fnHeap("wfm_apply_jacobian", ints(ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
     private static final MethodHandle HOST_ALLOC = fn("wfm_host_alloc", ints(ADDRESS, java.lang.foreign.ValueLayout.JAVA_LONG));
     private static final MethodHandle HOST_FREE = fn("wfm_host_free", ints(ADDRESS));
 
@@ -96,8 +107,7 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
     private final Arena arena = Arena.ofShared();
     private MemorySegment handle = MemorySegment.NULL;
     private final long vox, elemBytes;
-    private final MemorySegment staging;      // pinned host buffer, psf / q sized (TiPi arrays are on the Java heap: one copy)
-    private MemorySegment cpxBuf = null;      // lazily pinned, cpxPsf / MTF sized
+    // (no staging buffers on the Java side: psf / q / cpxPsf are handed over as heap segments, see fnHeap)
 
     /** WFM:137-152 (no Zernike modes: nPhase = 0, nModulus = 1). */
     public WideFieldModelB200(Shape psfShape, double NA, double lambda, double ni, double dxy, double dz, boolean radial, boolean single) {
@@ -123,7 +133,6 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
         handle = out.get(ADDRESS, 0);
         vox = (long) Nx * Ny * Nz;
         elemBytes = single ? 4 : 8;
-        staging = pinned(vox * elemBytes);
         check(handle, call(SET_OPTICS, handle, NA, lambda, ni));                    // computeMaskPupil()  WFM:174, 1374-1406
         this.nModulus = Math.max(1, nModulus);                                      // WFM:176-179
         this.nPhase = nPhase;
@@ -171,14 +180,14 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
         DoubleShapedVectorSpace space = parameterSpace[flag];
         if (space == null) throw new IllegalArgumentException("DoubleShapedVector grad does not belong to any space");
         int n = space.getNumber();
-        if (isSingle()) MemorySegment.copy(((FloatShapedVector) q).getData(), 0, staging, JAVA_FLOAT, 0, (int) vox);
-        else MemorySegment.copy(((DoubleShapedVector) q).getData(), 0, staging, JAVA_DOUBLE, 0, (int) vox);
-        try (Arena a = Arena.ofConfined()) {
-            MemorySegment out = a.allocate(JAVA_DOUBLE, n);
-            check(handle, call(APPLY_J, handle, flag, staging, out, n));            // recomputes the PSF if dirty (quirk Q5)
-            PState = 1;
-            return space.wrap(out.toArray(JAVA_DOUBLE));
-        }
+        // q straight from the TiPi vector's backing array (no copy on the Java side)
+        MemorySegment qs = isSingle() ? MemorySegment.ofArray(((FloatShapedVector) q).getData())
+                                      : MemorySegment.ofArray(((DoubleShapedVector) q).getData());
+        if (qs.byteSize() != vox * elemBytes) throw new IllegalArgumentException("q does not have the shape of the PSF");
+        double[] out = new double[n];
+        check(handle, call(APPLY_J, handle, flag, qs, MemorySegment.ofArray(out), n));   // recomputes the PSF if dirty (quirk Q5)
+        PState = 1;
+        return space.wrap(out);
     }
 
     /** WFM:412-422. */
@@ -329,27 +338,37 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
     @Override
     public Array3D getPsf() {
         if (PState < 1) computePsf();
-        check(handle, call(GET_PSF, handle, staging));
-        psf = isSingle() ? Float3D.wrap(staging.asSlice(0, vox * 4).toArray(JAVA_FLOAT), psfShape)
-                         : Double3D.wrap(staging.asSlice(0, vox * 8).toArray(JAVA_DOUBLE), psfShape);
+        if (isSingle()) {
+            float[] a = new float[(int) vox];
+            check(handle, call(GET_PSF, handle, MemorySegment.ofArray(a)));          // device -> the array TiPi will own
+            psf = Float3D.wrap(a, psfShape);
+        } else {
+            double[] a = new double[(int) vox];
+            check(handle, call(GET_PSF, handle, MemorySegment.ofArray(a)));
+            psf = Double3D.wrap(a, psfShape);
+        }
         return psf;
     }
     /** WFM:1856-1861: conj(FFT2(A_z)), shape (2, Nx, Ny, Nz). */
     public Array4D get_cpxPsf() {
         if (PState < 1) computePsf();
-        MemorySegment b = cpx();
-        check(handle, call(GET_CPX, handle, b));
         Shape s = new Shape(2, Nx, Ny, Nz);
-        return isSingle() ? Float4D.wrap(b.asSlice(0, 2 * vox * 4).toArray(JAVA_FLOAT), s)
-                          : Double4D.wrap(b.asSlice(0, 2 * vox * 8).toArray(JAVA_DOUBLE), s);
+        if (isSingle()) {
+            float[] a = new float[(int) (2 * vox)];
+            check(handle, call(GET_CPX, handle, MemorySegment.ofArray(a)));
+            return Float4D.wrap(a, s);
+        }
+        double[] a = new double[(int) (2 * vox)];
+        check(handle, call(GET_CPX, handle, MemorySegment.ofArray(a)));
+        return Double4D.wrap(a, s);
     }
     /** WFM:1807-1828 as intended (the reference copy loop `i = i++` never terminates, quirk Q8): FFT3 of the PSF. */
     @Override
     public Array4D getMtf() {
-        MemorySegment b = cpx();
-        check(handle, call(GET_MTF, handle, b));
+        double[] a = new double[(int) (2 * vox)];
+        check(handle, call(GET_MTF, handle, MemorySegment.ofArray(a)));
         PState = 1;
-        return Double4D.wrap(b.asSlice(0, 2 * vox * 8).toArray(JAVA_DOUBLE), new Shape(2, Nx, Ny, Nz));
+        return Double4D.wrap(a, new Shape(2, Nx, Ny, Nz));
     }
     /** WFM:1866-1895 prints statistics of the pupil; kept as a one-line summary. */
     public void getInfo() {
@@ -368,8 +387,6 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
     @Override
     public void close() {
         if (!handle.equals(MemorySegment.NULL)) { call(DESTROY, handle); handle = MemorySegment.NULL; }
-        call(HOST_FREE, staging);
-        if (cpxBuf != null) call(HOST_FREE, cpxBuf);
         arena.close();
     }
 
@@ -386,10 +403,6 @@ public class WideFieldModelB200 extends MicroscopeModel implements AutoCloseable
         try (Arena a = Arena.ofConfined()) {
             check(handle, call(setter, handle, a.allocateFrom(JAVA_DOUBLE, v), v.length));
         }
-    }
-    private MemorySegment cpx() {
-        if (cpxBuf == null) cpxBuf = pinned(2 * vox * 8);
-        return cpxBuf;
     }
     private MemorySegment pinned(long bytes) {
         MemorySegment out = arena.allocate(ADDRESS);
