@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--sustain", type=float, default=2.5, help="seconds of the sustained-roofline loop (0 = skip)")
     ap.add_argument("--no-others", dest="others", action="store_false", help="skip the extra lines of configs 2, 4, 5")
     ap.add_argument("--quick", action="store_true", help="headline numbers only (variant A/B runs)")
+    ap.add_argument("--quick-sustain", action="store_true", help="with --quick: keep the sustained loop")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: how the K-vector is summed over the ranks (peer = inside k_jac_final over CUDA-IPC "
                          "peer memory; nccl = one all-reduce per step; auto = peer if every rank can map its peers)")
@@ -467,7 +468,7 @@ def run_b200(args):
 
     # ---- sustained: the same step back to back for >= args.sustain seconds (the 1 kW power cap pulls the clock down) --
     sustained = None
-    if args.sustain > 0 and not args.quick:
+    if args.sustain > 0 and (not args.quick or args.quick_sustain):
         s2 = ClockSampler(local)
         t_target = args.sustain * 1e3
         est = ms / args.steps

@@ -414,6 +414,19 @@ struct PipeCtl {
 #ifndef WFM_JAC_TWTAB
 #define WFM_JAC_TWTAB 0
 #endif
+// the same knobs for the fp32 pipelines (half the shared-memory wavefronts per element: the table reads may pay there)
+#ifndef WFM_PSF_TWTAB32
+#define WFM_PSF_TWTAB32 0
+#endif
+#ifndef WFM_JAC_TWTAB32
+#define WFM_JAC_TWTAB32 0
+#endif
+// Consumed ring data is dropped from L2 without write-back (wfm_discard_l2): the ring (44 planes, 63 MB at 512^2 fp64)
+// outlives its L2 residency between two tenants of a slot, so without this every ring byte is eventually written to
+// DRAM (ncu: 0.31 GB of DRAM writes per Jacobian launch that stores 0.05 GB of integrands).
+#ifndef WFM_RING_DISCARD
+#define WFM_RING_DISCARD 1
+#endif
 // Row items of the Jacobian bulk-prefetch their next row of conj(a) and q into L2 (TMA prefetch).
 #ifndef WFM_L2_PREFETCH
 #define WFM_L2_PREFETCH 1
@@ -442,7 +455,9 @@ template <typename T, int N> struct PipeCfg {
     static constexpr int COLLEN = ColL::pad_c(N - 1) + 1;
     static constexpr int CELLS = C * (ROWLEN > COLLEN ? ROWLEN : COLLEN);
     // WFM_{PSF,JAC}_TWTAB: twiddle powers read from shared tables instead of formed by multiplication (fft_inplace TWTAB)
-    static constexpr int TWTAB_ANY = (WFM_PSF_TWTAB) | (WFM_JAC_TWTAB);
+    static constexpr int TWTAB_PSF = sizeof(T) == 8 ? (WFM_PSF_TWTAB) : (WFM_PSF_TWTAB32);
+    static constexpr int TWTAB_JAC = sizeof(T) == 8 ? (WFM_JAC_TWTAB) : (WFM_JAC_TWTAB32);
+    static constexpr int TWTAB_ANY = TWTAB_PSF | TWTAB_JAC;
     // stage-2 twiddles: base entries (R3 <= 16), or every power k in [1, R2) when tabulated
     static constexpr int TW2 = (TWTAB_ANY & 2) ? (((P::R2 - 1) * P::R3 + 1) & ~1) : 16;   // even: what follows stays 16-byte aligned
     // the engine reads tw[b] for b < N/R1 only (stage-1 base twiddles): the shared copy holds just those S1 entries
@@ -545,6 +560,16 @@ WFM_DEVI void pipe_wait(const unsigned* cnt, unsigned target, unsigned* err) {
 WFM_DEVI void pipe_signal(unsigned* cnt) {
     __syncthreads();
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(cnt, 1u); }
+}
+// The same, with the item's consumed ring lines dropped from L2 (wfm_discard_l2) by the first warp between the barrier
+// and the publication: drop(lane) issues lane's share; the warp barrier + thread 0's fence order them before the atomic.
+template <class Drop> WFM_DEVI void pipe_signal_drop(unsigned* cnt, const Drop& drop) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        drop((int)threadIdx.x);
+        __syncwarp();
+        if (threadIdx.x == 0) { __threadfence(); atomicAdd(cnt, 1u); }
+    }
 }
 
 // Self-cleaning control block: the last CTA to leave the work loop zeroes the queue and the per-plane
@@ -722,7 +747,7 @@ WFM_DEVI void psf_cols_item(const PsfArgs<T>& a, int pl, int sub, int bm, int ri
             v[e] = val;
         }
     }
-    fft_inplace<T, P, L, CtaSync, PipePrefetchHook<>, NARROW, WFM_PSF_TW_TREE, NoHook, WFM_PSF_TWTAB>(
+    fft_inplace<T, P, L, CtaSync, PipePrefetchHook<>, NARROW, WFM_PSF_TW_TREE, NoHook, PipeCfg<T, N>::TWTAB_PSF>(
         v, cells + c, t, tw_s, tw_s + PipeCfg<T, N>::TW1, 0, PipePrefetchHook<>{qu, ctl, a.g.nzl, NoClaimAction{}});
     pipe_wait(dep);                                   // ring slot free? (its previous tenant's row items are done)
     cx<T>* dst = a.T1 + (size_t)ringoff + (size_t)sub * N * C + c;
@@ -791,7 +816,7 @@ WFM_DEVI void psf_rows_item(const PsfArgs<T>& a, int pl, int sub, int ringoff, c
             v[e] = (leg_live<P::R1, NARROW>(e % P::R1) && xis[e] >= 0) ? __ldcg(&src[xis[e]]) : mkc<T>((T)0, (T)0);
 #endif
 #endif
-        fft_inplace<T, P, L, RowSync<TT>, NoHook, NARROW, WFM_PSF_TW_TREE, NoHook, WFM_PSF_TWTAB>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
+        fft_inplace<T, P, L, RowSync<TT>, NoHook, NARROW, WFM_PSF_TW_TREE, NoHook, PipeCfg<T, N>::TWTAB_PSF>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
 #ifdef WFM_PROBE_PSF_L2ST          /* timing probe only (wrong results): stores that never reach DRAM */
         const size_t base = (size_t)N * (blockIdx.x * C + slot);
 #else
@@ -867,9 +892,36 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::MINB) k
             if (ctl.roles & 2) {
                 if (!ready) pipe_wait(&ctl.cntA[it.plane], ctl.nA, ctl.err);
                 psf_rows_item<T, N, NARROW>(a, it.plane, it.sub, it.ringoff, cells, tw_s, invx_s, qu, ctl);
+#if WFM_RING_DISCARD == 1
+                // rows [sub*RPI, (sub+1)*RPI) of every column tile have been read by all groups: drop their lines from L2
+                if constexpr ((sizeof(cx<T>) * Cfg::C * Cfg::ROWS_PER_ITEM) % 128 == 0) {
+                    __syncthreads();
+                    constexpr int LPT = (int)(sizeof(cx<T>) * Cfg::C * Cfg::ROWS_PER_ITEM / 128);     // lines per tile
+                    const int ntiles = a.pitch / Cfg::C;
+                    const char* base = reinterpret_cast<const char*>(a.T1 + (size_t)it.ringoff + (size_t)it.sub * Cfg::ROWS_PER_ITEM * Cfg::C);
+                    for (int i = threadIdx.x; i < ntiles * LPT; i += Cfg::THREADS)
+                        wfm_discard_l2(base + (size_t)(i / LPT) * (sizeof(cx<T>) * (size_t)N * Cfg::C) + (size_t)(i % LPT) * 128);
+                }
+#endif
             }
             qu.prefetch(ctl, P);
+#if WFM_RING_DISCARD == 2
+            if constexpr ((sizeof(cx<T>) * Cfg::C * Cfg::ROWS_PER_ITEM) % 128 == 0) {
+                // rows [sub*RPI, (sub+1)*RPI) of every column tile have been read: drop their lines from L2
+                constexpr int LPT = (int)(sizeof(cx<T>) * Cfg::C * Cfg::ROWS_PER_ITEM / 128);     // lines per tile
+                const int nl = (a.pitch / Cfg::C) * LPT;
+                const char* base = reinterpret_cast<const char*>(a.T1 + (size_t)it.ringoff + (size_t)it.sub * Cfg::ROWS_PER_ITEM * Cfg::C);
+                pipe_signal_drop(&ctl.cntB[it.plane], [&](int lane) {
+                    if (!(ctl.roles & 2)) return;
+                    for (int i = lane; i < nl; i += 32)
+                        wfm_discard_l2(base + (size_t)(i / LPT) * (sizeof(cx<T>) * (size_t)N * Cfg::C) + (size_t)(i % LPT) * 128);
+                });
+            } else {
+                pipe_signal(&ctl.cntB[it.plane]);
+            }
+#else
             pipe_signal(&ctl.cntB[it.plane]);
+#endif
         }
         qu.advance();
     }
@@ -1082,10 +1134,10 @@ WFM_DEVI void jac_rows_item(const JacArgs<T>& a, int pl, int sub, int ringoff, c
                                Cfg::JAC_TMA_Q ? (unsigned)(N * sizeof(T)) : 0u};
             using QHook = RowQAheadHook<T, E, P::R1, TT, P::S1>;
             QHook qh{qn, &a.q[base + (more ? (size_t)N * C : 0)], t, WFM_JAC_Q_AHEAD && more && !Cfg::JAC_TMA_Q};
-            fft_inplace<T, P, L, RowSync<TT>, RowBulkLoadHook, false, WFM_JAC_TW_TREE, QHook, WFM_JAC_TWTAB>(v, cells + slot * L::LEN, t, tw_s,
+            fft_inplace<T, P, L, RowSync<TT>, RowBulkLoadHook, false, WFM_JAC_TW_TREE, QHook, PipeCfg<T, N>::TWTAB_JAC>(v, cells + slot * L::LEN, t, tw_s,
                                                                                                            tw_s + PipeCfg<T, N>::TW1, slot, hk, qh);
         } else {
-            fft_inplace<T, P, L, RowSync<TT>, NoHook, false, WFM_JAC_TW_TREE, NoHook, WFM_JAC_TWTAB>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
+            fft_inplace<T, P, L, RowSync<TT>, NoHook, false, WFM_JAC_TW_TREE, NoHook, PipeCfg<T, N>::TWTAB_JAC>(v, cells + slot * L::LEN, t, tw_s, tw_s + PipeCfg<T, N>::TW1, slot);
         }
         cx<T>* dst = a.T2 + (size_t)ringoff + (size_t)y * C;
 #pragma unroll
@@ -1129,8 +1181,15 @@ WFM_DEVI void jac_cols_item(const JacArgs<T>& a, int pl, int sub, int bm, int ri
             if (leg_live<P::RL, NARROW>(r))
                 fl |= (unsigned)__ldg(&a.st.flags[sbase + (size_t)((t + TT * u) + P::SL * r) * C]) << (2 * (u * P::RL + r));
     using ClaimHook = PipePrefetchHook<JacClaimPrefetch<T, N>>;
-    fft_inplace<T, P, L, CtaSync, ClaimHook, false, WFM_JAC_TW_TREE, NoHook, WFM_JAC_TWTAB>(
+    fft_inplace<T, P, L, CtaSync, ClaimHook, false, WFM_JAC_TW_TREE, NoHook, PipeCfg<T, N>::TWTAB_JAC>(
         v, cells + c, t, tw_s, tw_s + PipeCfg<T, N>::TW1, 0, ClaimHook{qu, ctl, a.g.nzl, JacClaimPrefetch<T, N>{a.cpx, a.q}});
+#if WFM_RING_DISCARD == 1
+    {   // the tile has been read by every thread (the transform's barriers are behind us): drop its lines from L2
+        const char* tile = reinterpret_cast<const char*>(a.T2 + (size_t)ringoff + (size_t)sub * N * C);
+        constexpr int LINES = (int)(sizeof(cx<T>) * (size_t)N * C / 128);
+        for (int i = threadIdx.x; i < LINES; i += PipeCfg<T, N>::THREADS) wfm_discard_l2(tile + (size_t)i * 128);
+    }
+#endif
     const int iz = a.g.z0 + (pl - bm * a.g.nzm);
     const double s = defoc_scale_dev(iz, a.g.nz_global, a.g.dz);
     const bool mod_plane = (a.Gm != nullptr) && (!a.last_plane_only || iz == a.g.nz_global - 1);
@@ -1202,7 +1261,18 @@ __global__ void __launch_bounds__(PipeCfg<T, N>::THREADS, PipeCfg<T, N>::templat
                 jac_cols_item<T, N, NARROW>(a, it.plane, it.sub, it.model, it.ringoff, cells, tw_s, cis_s, qu, ctl);
             }
             if (qu.prefetch(ctl, P)) JacClaimPrefetch<T, N>{a.cpx, a.q}(qu.peek_next());
+#if WFM_RING_DISCARD == 2
+            {   // the column tile has been read by every thread: drop its lines from L2
+                const char* tile = reinterpret_cast<const char*>(a.T2 + (size_t)it.ringoff + (size_t)it.sub * N * Cfg::C);
+                constexpr int LINES = (int)(sizeof(cx<T>) * (size_t)N * Cfg::C / 128);
+                pipe_signal_drop(&ctl.cntB[it.plane], [&](int lane) {
+                    if (!(ctl.roles & 2)) return;
+                    for (int i = lane; i < LINES; i += 32) wfm_discard_l2(tile + (size_t)i * 128);
+                });
+            }
+#else
             pipe_signal(&ctl.cntB[it.plane]);
+#endif
         }
         qu.advance();
     }

@@ -36,6 +36,14 @@ __device__ __forceinline__ void wfm_prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// Drop one 128-byte line from L2 WITHOUT writing it back (its contents become undefined): for ring data that has been
+// consumed and will be overwritten before it is read again -- otherwise every dead ring line is written to DRAM when it
+// is finally evicted.  p must be 128-byte aligned.  (PTX: the discard is performed as a write of an unspecified value, so
+// the barrier + fence + atomic that publishes the ring slot orders it before the next tenant's stores.)
+__device__ __forceinline__ void wfm_discard_l2(const void* p) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+
 // ---- mbarrier + 1-D bulk-async copy (TMA engine; SASS: UBLKCP + SYNCS) ---------------------------------------
 // One elected thread posts the expected byte count on the shared-memory barrier and issues the copy; the data moves
 // global -> shared without passing through registers or the LSU; every consumer waits on the barrier's phase.

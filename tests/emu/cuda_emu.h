@@ -316,6 +316,7 @@ static inline unsigned long long wfm_now_ns() {
 }
 
 static inline void wfm_prefetch_l2(const void*, unsigned) {}
+static inline void wfm_discard_l2(const void*) {}
 // mbarrier + bulk-async copy: the copy is done on the spot by the issuing fiber; the barrier word counts completed phases
 static inline void wfm_mbar_init(uint64_t* bar, unsigned) { __atomic_store_n(bar, (uint64_t)0, __ATOMIC_SEQ_CST); }
 static inline void wfm_mbar_init_fence() {}
