@@ -369,6 +369,14 @@ def test_gpu_case_helpers_at_small_sizes(lib):
     escape_hatch_case(lib, ((32, 5, 0.2), (32, 3, 0.4)))
 
 
+def test_tight_ring_on_the_emulator(lib, monkeypatch):
+    """WFM_PIPE_LAG=1: a ring of four planes, every producer waits for the slot's previous tenant (queue order and
+    counter protocol at the least slack; the GPU twin also exercises the L2 discards)."""
+    from tests.test_gpu_parity import full_stack_case
+    monkeypatch.setenv("WFM_PIPE_LAG", "1")
+    full_stack_case(lib, 32, 24, 2, 20, False)
+
+
 @pytest.mark.parametrize("N,Nz,single", [(48, 3, False), (100, 2, False), (30, 4, True), (36, 2, False)])
 def test_any_n_path_matches_oracle(lib, N, Nz, single):
     """Nx = Ny that is not a power of two in [32, 2048] (the reference's JTransforms takes any N, WFM:319): the

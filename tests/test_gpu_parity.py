@@ -515,6 +515,17 @@ def full_stack_case(lib, N, Nz, z0, nzl, single):
     m.close()
 
 
+@pytest.mark.parametrize("lag", ["1", "2", "3"])
+def test_tight_ring_slot_reuse(lib, monkeypatch, lag):
+    """A ring of 4 / 6 / 8 planes (WFM_PIPE_LAG): the producers of a plane wait on the counter of the slot's previous
+    tenant for most items, so a slot is rewritten microseconds after its consumer dropped its lines from L2
+    (wfm_discard_l2) and published it -- the ordering the discard relies on, under the least slack the queue allows."""
+    monkeypatch.setenv("WFM_PIPE_LAG", lag)
+    for _ in range(2):
+        full_stack_case(lib, 512, 96, 16, 64, False)
+    full_stack_case(lib, 256, 64, 0, 64, True)
+
+
 @pytest.mark.parametrize("single", [False, True])
 def test_config5_batch_of_eight_256x256x64(lib, single):
     """BASELINE config 5 at its own plane count: 8 of the 64 models (512 planes through one pipeline launch pair)."""
