@@ -235,6 +235,11 @@ HostStage* host_stage(wfm_model* h) {
     return st;
 }
 
+// (no exception may cross the C ABI: a thread that cannot be started is reported, its share is done by the caller)
+template <class W> bool spawn_worker(std::vector<std::thread>& pool, W& work, int w) {
+    try { pool.emplace_back([&work, w] { work(w); }); return true; } catch (...) { return false; }
+}
+
 // Host -> device through the staging slots, on `stream`.  Returns after every piece has been QUEUED; on_piece(k) is
 // called on the calling thread, in order, once piece k (bytes [k*piece, (k+1)*piece)) is completely queued.
 template <class F> int staged_h2d(wfm_model* h, HostStage* st, void* dev, const void* host, size_t bytes, cudaStream_t stream,
@@ -262,17 +267,14 @@ template <class F> int staged_h2d(wfm_model* h, HostStage* st, void* dev, const 
         }
     };
     std::vector<std::thread> pool;
-    for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
+    std::vector<int> inline_w;                       // shares whose thread could not be started: done by the caller itself
+    for (int w = 0; w < T; ++w)
+        if (T == 1 || !spawn_worker(pool, work, w)) inline_w.push_back(w);
+    for (int w : inline_w) work(w);
     int rc = WFM_OK;
-    if (T == 1) {
-        work(0);
-        for (int k = 0; k < npieces && !rc; ++k) rc = on_piece(k);
-    } else {
-        pool.emplace_back(work, 0);
-        for (int k = 0; k < npieces; ++k) {
-            while (arrived[k].load() < T) std::this_thread::yield();
-            if (!rc) rc = on_piece(k);
-        }
+    for (int k = 0; k < npieces; ++k) {
+        while (arrived[k].load() < T) std::this_thread::yield();
+        if (!rc) rc = on_piece(k);
     }
     for (auto& t : pool) t.join();
     if (failed.load()) { cudaGetLastError(); return h->fail(WFM_ERR_CUDA, "staged host -> device copy failed"); }
@@ -312,8 +314,10 @@ template <class F> int staged_d2h(wfm_model* h, HostStage* st, void* host, const
         }
     };
     std::vector<std::thread> pool;
-    for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
-    work(0);
+    std::vector<int> inline_w{0};
+    for (int w = 1; w < T; ++w)
+        if (!spawn_worker(pool, work, w)) inline_w.push_back(w);
+    for (int w : inline_w) work(w);
     for (auto& t : pool) t.join();
     if (failed.load()) { cudaGetLastError(); return h->fail(WFM_ERR_CUDA, "staged device -> host copy failed"); }
     return WFM_OK;
