@@ -848,7 +848,10 @@ int compute_psf_impl(wfm_model* h) {
     return compute_psf_windows(h, 0, [](int, int) { return WFM_OK; });
 }
 
+// a setter changed a pupil array: the PSF is stale (freeMem(), WFM:1970-1974) and so is the packed strip
 int invalidate(wfm_model* h) { h->pstate = 0; h->strip_dirty = true; return WFM_OK; }
+// freeMem() alone: the PSF is stale, the pupil arrays (and their strip copy) are what they were
+int invalidate_psf(wfm_model* h) { h->pstate = 0; return WFM_OK; }
 
 // After a synchronisation point: did a pipeline dependency wait time out?  (It cannot by
 // construction; the flag turns a would-be hang into an error code.)
@@ -1275,10 +1278,14 @@ int wfm_set_phase(wfm_model* h, const double* alpha, int n) {
     h->nphase = n;
     KernelSpan span(h, WFM_K_SETTERS);
     auto kfn = &k_set_phase;
+    // the strip is packed and phi is all that changes: refresh its strip copy in the same pass (no k_pack_strip launch)
+    const bool fused = !h->activity_dirty && !h->strip_dirty && h->s_phi.p && h->inv_x.p && h->support.p &&
+                       getenv("WFM_NO_FUSED_SETPHASE") == nullptr;
     WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix())), dim3(256), 0, h->stream, (double*)h->phi.p,
-               (const double*)h->Z.p, (const uint8_t*)h->mask.p, h->alpha, n, off, h->npix());
+               (const double*)h->Z.p, (const uint8_t*)h->mask.p, h->alpha, n, off, h->npix(),
+               fused ? (double*)h->s_phi.p : (double*)nullptr, (const int*)h->inv_x.p, (const uint8_t*)h->support.p, h->N, h->ctile);
     WFM_CK_LAUNCH(h, "k_set_phase");
-    return invalidate(h);                                                      // WFM:1648
+    return fused ? invalidate_psf(h) : invalidate(h);                          // WFM:1648
 }
 
 int wfm_set_modulus(wfm_model* h, const double* beta, int n) {
@@ -1420,8 +1427,8 @@ int wfm_compute_psf(wfm_model* h) {
 }
 int wfm_invalidate(wfm_model* h) {
     if (!h) return WFM_ERR_INVALID_ARG;
-    for (wfm_model* c : h->parts) invalidate(c);
-    return invalidate(h);
+    for (wfm_model* c : h->parts) invalidate_psf(c);
+    return invalidate_psf(h);
 }
 int wfm_psf_state(const wfm_model* h) {
     if (!h) return 0;

@@ -109,6 +109,9 @@ template <typename T, int N> struct ColCfg {
     static constexpr size_t SMEM = sizeof(cx<T>) * (size_t)N * C;
 };
 
+// strip cell of pixel (ky, compact column xi): tile-major, see "Pupil strip" below
+WFM_DEVI size_t strip_cell(int ky, int xi, int N, int C) { return ((size_t)(xi / C) * N + ky) * C + (xi % C); }
+
 // ================================================================================================
 // pupil construction (elementwise; arithmetic mirrors the JVM: no FMA contraction)
 // ================================================================================================
@@ -148,8 +151,12 @@ __global__ void k_compute_defocus(double* __restrict__ psi, uint8_t* __restrict_
 }
 
 // setPhase() WFM:1625-1649: phi = sum_n Z[in + (n+off)*Npix]*alpha_n on maskPupil, else 0
+// s_phi != NULL: the strip copy of phi (k_pack_strip's layout) is refreshed in the same pass -- when phi is the only
+// pupil array that changed since the strip was packed, the step needs no k_pack_strip launch.
 __global__ void k_set_phase(double* __restrict__ phi, const double* __restrict__ Z,
-                            const uint8_t* __restrict__ mask, Coefs alpha, int n, int off, int npix) {
+                            const uint8_t* __restrict__ mask, Coefs alpha, int n, int off, int npix,
+                            double* __restrict__ s_phi, const int* __restrict__ inv_x,
+                            const uint8_t* __restrict__ support, int N, int C) {
     const int in = blockIdx.x * blockDim.x + threadIdx.x;
     wfm_grid_dep_trigger();
     if (in >= npix) return;
@@ -158,6 +165,10 @@ __global__ void k_set_phase(double* __restrict__ phi, const double* __restrict__
         for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(Z[in + (size_t)(k + off) * npix], alpha.v[k]));
     }
     phi[in] = acc;
+    if (s_phi) {
+        const int xi = inv_x[in % N];
+        if (xi >= 0) s_phi[strip_cell(in / N, xi, N, C)] = support[in] ? acc : 0.0;
+    }
 }
 
 // setModulus() WFM:1588-1610: rho = sum_n Z[in + n*Npix]*beta_n*betaNorm on maskPupil, else 0
@@ -327,7 +338,6 @@ __global__ void k_roll3(T* __restrict__ out, const T* __restrict__ in, int nx, i
 // tile: cell(ky, xi) = ((xi / C) * N + ky) * C + xi % C.  A column item then reads / writes one
 // contiguous 16*C*(lanes/C)-byte run per warp access instead of touching one cache line per row
 // (ncu, profiles/r01d_*: the 171-column pass cost as many L1 wavefronts as the 512-row pass).
-WFM_DEVI size_t strip_cell(int ky, int xi, int N, int C) { return ((size_t)(xi / C) * N + ky) * C + (xi % C); }
 struct Strip {
     const double* rho; const double* phi; const double* psi;   // [pitch/C][N][C]
     const uint8_t* flags;                                        // bit 0: maskPupil, bit 1: support
