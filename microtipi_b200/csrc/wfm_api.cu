@@ -90,6 +90,7 @@ struct wfm_model {
     bool basis_packed = false;
     DevBuf s_rho, s_phi, s_psi, s_flags;          // pupil strip [N][pitch]
     bool strip_dirty = true;
+    bool phi_clean_off_support = false;           // phi == 0 off the mask (left so by a full k_set_phase; the escape hatch clears it)
     int ncells = 0;
     // FFT twiddles
     DevBuf tw;
@@ -1277,15 +1278,23 @@ int wfm_set_phase(wfm_model* h, const double* alpha, int n) {
     for (int k = 0; k < n; ++k) h->alpha.v[k] = alpha[k];
     h->nphase = n;
     KernelSpan span(h, WFM_K_SETTERS);
-    auto kfn = &k_set_phase;
-    // the strip is packed and phi is all that changes: refresh its strip copy in the same pass (no k_pack_strip launch)
-    const bool fused = !h->activity_dirty && !h->strip_dirty && h->s_phi.p && h->inv_x.p && h->support.p &&
+    // the strip is packed and phi is all that changes: support cells only, phi and its strip copy in one pass
+    const bool fused = !h->activity_dirty && !h->strip_dirty && h->s_phi.p && h->ncells > 0 && h->phi_clean_off_support &&
                        getenv("WFM_NO_FUSED_SETPHASE") == nullptr;
+    if (fused) {
+        auto kfn = &k_set_phase_cells;
+        WFM_LAUNCH(kfn, dim3(elementwise_grid(h->ncells)), dim3(256), 0, h->stream, (double*)h->phi.p, (double*)h->s_phi.p,
+                   (const double*)h->Z.p, (const uint8_t*)h->mask.p, h->alpha, n, off, h->npix(),
+                   (const int*)h->cell_list.p, (const int*)h->in_list.p, h->ncells);
+        WFM_CK_LAUNCH(h, "k_set_phase_cells");
+        return invalidate_psf(h);                                              // WFM:1648
+    }
+    auto kfn = &k_set_phase;
     WFM_LAUNCH(kfn, dim3(elementwise_grid(h->npix())), dim3(256), 0, h->stream, (double*)h->phi.p,
-               (const double*)h->Z.p, (const uint8_t*)h->mask.p, h->alpha, n, off, h->npix(),
-               fused ? (double*)h->s_phi.p : (double*)nullptr, (const int*)h->inv_x.p, (const uint8_t*)h->support.p, h->N, h->ctile);
+               (const double*)h->Z.p, (const uint8_t*)h->mask.p, h->alpha, n, off, h->npix());
     WFM_CK_LAUNCH(h, "k_set_phase");
-    return fused ? invalidate_psf(h) : invalidate(h);                          // WFM:1648
+    h->phi_clean_off_support = true;          // a full pass: phi is zero wherever the mask is off
+    return invalidate(h);                                                      // WFM:1648
 }
 
 int wfm_set_modulus(wfm_model* h, const double* beta, int n) {
@@ -1360,7 +1369,10 @@ int wfm_set_pupil_arrays(wfm_model* h, const double* rho, const double* phi, con
         for (size_t i = 0; i < npix; ++i) if (rho[i] != 0.0) h->h_esc[i] = 1;
         h->have_rho = true;
     }
-    if (phi) WFM_CK(h, cudaMemcpy(h->phi.p, phi, 8 * npix, cudaMemcpyHostToDevice));
+    if (phi) {
+        WFM_CK(h, cudaMemcpy(h->phi.p, phi, 8 * npix, cudaMemcpyHostToDevice));
+        h->phi_clean_off_support = false;     // arbitrary values anywhere: the next setPhase() takes the full pass
+    }
     if (psi) WFM_CK(h, cudaMemcpy(h->psi.p, psi, 8 * npix, cudaMemcpyHostToDevice));
     if (mask) {
         std::vector<uint8_t> m(npix);

@@ -151,12 +151,8 @@ __global__ void k_compute_defocus(double* __restrict__ psi, uint8_t* __restrict_
 }
 
 // setPhase() WFM:1625-1649: phi = sum_n Z[in + (n+off)*Npix]*alpha_n on maskPupil, else 0
-// s_phi != NULL: the strip copy of phi (k_pack_strip's layout) is refreshed in the same pass -- when phi is the only
-// pupil array that changed since the strip was packed, the step needs no k_pack_strip launch.
 __global__ void k_set_phase(double* __restrict__ phi, const double* __restrict__ Z,
-                            const uint8_t* __restrict__ mask, Coefs alpha, int n, int off, int npix,
-                            double* __restrict__ s_phi, const int* __restrict__ inv_x,
-                            const uint8_t* __restrict__ support, int N, int C) {
+                            const uint8_t* __restrict__ mask, Coefs alpha, int n, int off, int npix) {
     const int in = blockIdx.x * blockDim.x + threadIdx.x;
     wfm_grid_dep_trigger();
     if (in >= npix) return;
@@ -165,10 +161,23 @@ __global__ void k_set_phase(double* __restrict__ phi, const double* __restrict__
         for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(Z[in + (size_t)(k + off) * npix], alpha.v[k]));
     }
     phi[in] = acc;
-    if (s_phi) {
-        const int xi = inv_x[in % N];
-        if (xi >= 0) s_phi[strip_cell(in / N, xi, N, C)] = support[in] ? acc : 0.0;
+}
+// setPhase() when phi is the only pupil array that changed since the strip was packed (the steady state of the
+// optimiser loop): one thread per SUPPORT cell (8.7 % of the pixels) writes phi and its strip copy -- same sums, term by
+// term; off the support phi is zero already (every earlier setPhase left it so) -- and the step needs no k_pack_strip.
+__global__ void k_set_phase_cells(double* __restrict__ phi, double* __restrict__ s_phi, const double* __restrict__ Z,
+                                  const uint8_t* __restrict__ mask, Coefs alpha, int n, int off, int npix,
+                                  const int* __restrict__ cell_list, const int* __restrict__ in_list, int ncells) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    wfm_grid_dep_trigger();
+    if (li >= ncells) return;
+    const int in = in_list[li];
+    double acc = 0.0;
+    if (mask[in]) {
+        for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __dmul_rn(Z[in + (size_t)(k + off) * npix], alpha.v[k]));
     }
+    phi[in] = acc;
+    s_phi[cell_list[li]] = acc;
 }
 
 // setModulus() WFM:1588-1610: rho = sum_n Z[in + n*Npix]*beta_n*betaNorm on maskPupil, else 0

@@ -111,3 +111,36 @@ def test_stream_ordering_entry_points(lib):
     m.orderStreamAfter(0)
     assert lib.wfm_wait_stream(None, None) != 0 and lib.wfm_fence_stream(None, None) != 0
     m.close()
+
+
+def test_steady_state_set_phase_keeps_phi_and_strip_in_step(lib):
+    """setPhase() on a packed strip takes the support-cell kernel (phi and its strip copy in one pass, no
+    k_pack_strip): getPhi(), the PSF and the Jacobians must follow every new vector; a phase array loaded through the
+    escape hatch (values off the support too) must be wiped by the next setPhase() exactly as the full pass does."""
+    N, Nz = 32, 4
+    ref, m = make_pair(N, Nz, lib)
+    q = o.synthetic_q(N, N, Nz)
+    m.getPsf()                                                   # packs the strip
+    rng = np.random.default_rng(5)
+    for it in range(3):
+        a = rng.normal(0, 0.3, 10)
+        n0 = lib.wfm_launch_count()
+        m.setPhase(m.parameterSpace[m.PHASE].wrap(a.copy())); ref.setPhase(a)   # the optimiser's call: a vector of the space
+        assert lib.wfm_launch_count() == n0 + 1                  # one setter launch ...
+        m.computePsf()
+        assert lib.wfm_launch_count() == n0 + 2                  # ... and the PSF pipeline: no k_pack_strip
+        np.testing.assert_array_equal(m.getPhi(), ref.phi.ravel())
+        assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+        assert o.rel_l2(m.apply_J_phase(q).data, ref.apply_J_phase(q)) <= 1e-12
+    junk = rng.normal(size=N * N)                                # non-zero everywhere, also off the support
+    assert lib.wfm_set_pupil_arrays(m.handle, None, junk.ctypes.data_as(C.c_void_p), None, None) == 0
+    m.getPsf()                                                   # packs the strip again
+    a = rng.normal(0, 0.3, 10)
+    m.setPhase(a); ref.setPhase(a)
+    np.testing.assert_array_equal(m.getPhi(), ref.phi.ravel())   # zero off the mask again
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+    m.setModulus(BETA4); ref.setModulus(BETA4)                   # another setter: the strip is stale, full path
+    m.setPhase(a * 0.5); ref.setPhase(a * 0.5)
+    np.testing.assert_array_equal(m.getPhi(), ref.phi.ravel())
+    assert o.rel_l2(m.getPsf(), ref.getPsf()) <= 1e-12
+    m.close()
