@@ -213,10 +213,41 @@ template <> struct RowPad<1024, 8> { static constexpr int PA = 0, PB = 7; };
 #endif
 template <> struct RowPad<2048, 8> { static constexpr int PA = 4, PB = 8; };
 
+// fp32 rows (8-byte cells, 16 lanes per 128-byte pass): no shift padding serves both the stage-2 exchange (two stage-1
+// blocks per pass) and the last-stage loads without replays (best 1.33x: 25 % of the shared wavefronts of the fp32
+// pipelines were replays, profiles/r02i).  A per-block offset  off(k1) = A (k1 & 1) + B ((k1 >> 1) & 1) + C (k1 >> 2)  cells
+// together with 16-byte last-stage loads (two adjacent cells per LDS.128) is conflict free for every access of the
+// engine (tools/bank_conflicts.py, score_off).  A = 0 selects the shift padding.
+template <int N, int ESZ> struct RowOff { static constexpr int A = 0, B = 0, C = 0; };
+#ifndef WFM_NO_F32_ROWOFF
+// (only off(k1) mod 16 matters for the banks; multiples of 16 are added so that off() is non-decreasing -- blocks must not overlap)
+template <> struct RowOff<128, 8> { static constexpr int A = 4, B = 8, C = 2 + 16; };            // 0 4 8 12 18 22 26 30
+template <> struct RowOff<256, 8> { static constexpr int A = 4, B = 8, C = 2 + 16; };
+template <> struct RowOff<512, 8> { static constexpr int A = 8, B = 2 + 16, C = 4 + 32; };       // 0 8 18 26 36 44 54 62
+template <> struct RowOff<1024, 8> { static constexpr int A = 2, B = 4, C = 8; };                // 0 2 4 ... 14
+#endif
+
 template <typename T, int N> struct RowLayout {
     using P = RowPad<N, (int)sizeof(cx<T>)>;
-    __host__ __device__ static constexpr int pad_c(int i) { return i + (P::PA ? (i >> P::PA) : 0) + (P::PB ? (i >> P::PB) : 0); }
-    static constexpr int LEN = pad_c(N - 1) + 1;      // cells per transform
+    using O = RowOff<N, (int)sizeof(cx<T>)>;
+    static constexpr bool BLOCK_OFF = (O::A != 0);
+    static constexpr int S1 = Plan<N>::S1;
+    __host__ __device__ static constexpr int pad_c(int i) {
+        if (BLOCK_OFF) {
+            const int k = i / S1;
+            return i + O::A * (k & 1) + O::B * ((k >> 1) & 1) + O::C * (k >> 2);
+        }
+        return i + (P::PA ? (i >> P::PA) : 0) + (P::PB ? (i >> P::PB) : 0);
+    }
+    static constexpr bool blocks_disjoint() {
+        for (int k = 1; k < N / S1; ++k) if (pad_c(k * S1) < pad_c(k * S1 - 1) + 1) return false;
+        return true;
+    }
+    static_assert(blocks_disjoint(), "row layout: the stage-1 blocks overlap");
+    // cells per transform (even with block offsets: every private row then starts 16-byte aligned)
+    static constexpr int LEN = BLOCK_OFF ? ((pad_c(N - 1) + 2) & ~1) : pad_c(N - 1) + 1;
+    // the last stage may read its adjacent cells two at a time (16-byte loads): cell indices of a butterfly's first leg are even
+    static constexpr bool VEC_LAST = BLOCK_OFF;
     static WFM_DEVI int at(int i) { return pad_c(i); }
     __host__ __device__ static constexpr int at_c(int i) { return pad_c(i); }
     // Index arithmetic the engine may rely on for blocks of B consecutive indices starting at multiples of B
@@ -224,7 +255,7 @@ template <typename T, int N> struct RowLayout {
     // inside its block.  Both hold when every padding term steps exactly once per block, i.e. 2^shift == B
     // (constant inside a block, and (k*B + b) >> shift == k + (b >> shift)).
     template <int B> __host__ __device__ static constexpr bool affine() {
-        return (P::PA == 0 || (1 << P::PA) == B) && (P::PB == 0 || (1 << P::PB) == B);
+        return BLOCK_OFF ? (B == S1) : ((P::PA == 0 || (1 << P::PA) == B) && (P::PB == 0 || (1 << P::PB) == B));
     }
     static constexpr int UNIT = 1;                    // distance between consecutive indices of a block
 };
@@ -238,6 +269,7 @@ template <int C, int SH> struct ColLayout {
     __host__ __device__ static constexpr int at_c(int i) { return pad_c(i) * C; }
     template <int B> __host__ __device__ static constexpr bool affine() { return (1 << SH) == B; }
     static constexpr int UNIT = C;
+    static constexpr bool VEC_LAST = false;
 };
 __host__ __device__ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }
 
@@ -327,7 +359,7 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
 #else
     constexpr bool AFF = L::template affine<S1>();
 #endif
-    constexpr int LS1 = L::at_c(S1), UNIT = L::UNIT;
+    constexpr int UNIT = L::UNIT;
     // stage 1: radix R1 over legs of stride S1, twiddle W_N^(b*k1), scatter to cell k1*S1 + b
 #pragma unroll
     for (int u = 0; u < E / R1; ++u) {
@@ -339,7 +371,7 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
         else Dft<T, R1>::run(a);
         const int b = t + TT * u;
         cx<T>* const s1 = sm + L::at(b);               // AFF: leg k of this butterfly lives at s1[k * LS1]
-        auto cell1 = [&](int k) -> cx<T>& { return AFF ? s1[k * LS1] : sm[L::at(k * S1 + b)]; };
+        auto cell1 = [&](int k) -> cx<T>& { return AFF ? s1[L::at_c(k * S1)] : sm[L::at(k * S1 + b)]; };   // (= k * LS1 for the shift paddings)
         cell1(0) = a[0];
         if constexpr (TWTAB & 1) {
 #pragma unroll
@@ -443,8 +475,18 @@ WFM_DEVI void fft_inplace(cx<T> (&v)[P::E], cx<T>* sm, const int t, const cx<T>*
             (void)base;
 #else
             const cx<T>* const s3 = sm + L::at(base);      // AFF: R3 adjacent cells of block k1
+            if constexpr (AFF && L::VEC_LAST && sizeof(cx<T>) == 8 && R3 % 2 == 0) {
+                const float4* const s3v = reinterpret_cast<const float4*>(s3);      // two cells per 16-byte load
 #pragma unroll
-            for (int r = 0; r < R3; ++r) a[r] = AFF ? s3[r * UNIT] : sm[L::at(base + r)];
+                for (int r = 0; r < R3; r += 2) {
+                    const float4 x = s3v[r / 2];
+                    a[r] = mkc<T>((T)x.x, (T)x.y);
+                    a[r + 1] = mkc<T>((T)x.z, (T)x.w);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R3; ++r) a[r] = AFF ? s3[r * UNIT] : sm[L::at(base + r)];
+            }
 #endif
             Dft<T, R3>::run(a);
 #pragma unroll

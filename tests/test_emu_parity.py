@@ -20,7 +20,8 @@ def lib():
 
 
 @pytest.mark.parametrize("N,Nz,single", [(32, 6, False), (64, 4, False), (128, 3, False), (64, 4, True),
-                                         (256, 2, False), (512, 2, False), (512, 2, True), (1024, 1, False)])   # production-size plans (narrow, affine)
+                                         (256, 2, False), (512, 2, False), (512, 2, True), (1024, 1, False),   # production-size plans (narrow, affine)
+                                         (128, 3, True), (256, 2, True), (1024, 1, True)])                       # fp32 rows with per-block offsets
 def test_psf_and_jacobians_match_oracle(lib, N, Nz, single):
     ref, m = make_pair(N, Nz, lib, single=single)
     t = tol(single)
