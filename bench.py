@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-others", dest="others", action="store_false", help="skip the extra lines of configs 2, 4, 5")
     ap.add_argument("--quick", action="store_true", help="headline numbers only (variant A/B runs)")
     ap.add_argument("--quick-sustain", action="store_true", help="with --quick: keep the sustained loop")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded 128^2 parity check (single-size experiment builds)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: how the K-vector is summed over the ranks (peer = inside k_jac_final over CUDA-IPC "
                          "peer memory; nccl = one all-reduce per step; auto = peer if every rank can map its peers)")
@@ -411,7 +412,7 @@ def run_b200(args):
         return max_over_ranks(e0.elapsed_time(e1))
 
     # ---- parity before timing: a small sharded run against the oracle (checker only), on every rank ----------
-    parity = None if args.quick else check_parity(torch, dist, local, world, rank, stream, args.exchange)
+    parity = None if (args.quick or args.no_parity) else check_parity(torch, dist, local, world, rank, stream, args.exchange)
 
     cfg_id = args.config
     single = args.single

@@ -196,10 +196,18 @@ __global__ void __launch_bounds__(RowCfg<N / 2>::THREADS) k_conv_rows_r2c(ConvAr
     cx<T>* sm = cells + slot * L::LEN;
     fft_inplace<T, P, L, RowSync<TT>>(v, sm, t, tw_s, tw_s + M, slot);
     RowSync<TT>::sync(slot);                           // the last stage has read the cells: reuse them for the mirror
+    // Z[k] goes to cell (M - k) mod M of the UNPADDED row, so that the partner reads cell k: both accesses are runs of
+    // consecutive cells across lanes (descending / ascending) -- conflict free.  (Storing at the padded cell of k and
+    // reading the padded cell of M - k made every 8-lane group straddle a padding step: two wavefronts per read, 17 % of
+    // the shared wavefronts of this kernel, ncu profiles/r01n.)
 #pragma unroll
     for (int u = 0; u < E / P::RL; ++u)
 #pragma unroll
+#ifdef WFM_CONV_MIRROR_PADDED   /* A/B knob: the round-1 exchange */
         for (int r = 0; r < P::RL; ++r) sm[L::at((t + TT * u) + P::SL * r)] = v[u * P::RL + r];
+#else
+        for (int r = 0; r < P::RL; ++r) sm[(M - ((t + TT * u) + P::SL * r)) & (M - 1)] = v[u * P::RL + r];
+#endif
     RowSync<TT>::sync(slot);
     if (!valid) return;
     cx<T>* out = (STORE == CS_SPECTRUM ? a.Xout : a.V) + row * (size_t)conv_pitch(N);
@@ -208,7 +216,11 @@ __global__ void __launch_bounds__(RowCfg<N / 2>::THREADS) k_conv_rows_r2c(ConvAr
 #pragma unroll
         for (int r = 0; r < P::RL; ++r) {
             const int k = (t + TT * u) + P::SL * r;
+#ifdef WFM_CONV_MIRROR_PADDED
             const cx<T> Z = v[u * P::RL + r], Zm = sm[L::at((M - k) & (M - 1))], w = twn_s[k];
+#else
+            const cx<T> Z = v[u * P::RL + r], Zm = sm[k], w = twn_s[k];
+#endif
             const T sx = Z.x + Zm.x, sy = Z.y - Zm.y;              // Z + conj(Zm)
             const T dx = Z.x - Zm.x, dy = Z.y + Zm.y;              // Z - conj(Zm)
             const T px = w.x * dy + w.y * dx, py = w.y * dy - w.x * dx;   // -i w (Z - conj Zm)

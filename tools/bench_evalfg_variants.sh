@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   WFM_BUILD_FLAGS="-DWFM_ONLY_N=512 $flags" python -c "import __graft_entry__ as g; g.build_library(force=True)" > gpurun_out/build_$name.log 2>&1 || { echo "$name: build failed"; tail -5 gpurun_out/build_$name.log; continue; }
-  timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_$name.log 2>&1
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 1 --no-parity --no-others --sustain 0 > gpurun_out/bench_$name.log 2>&1
   python - "$name" <<'PY'
 import json,sys
 name=sys.argv[1]
