@@ -234,9 +234,15 @@ def jvm_probe():
 
 def git_head():
     try:
-        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True,
-                              timeout=5).stdout.strip() or None
+        head = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True,
+                              timeout=5).stdout.strip()
+        if head:
+            return head
     except Exception:                                                    # noqa: BLE001
+        pass
+    try:                                  # no .git on the GPU box: the commit the library was built from (__graft_entry__.build_library)
+        return open(os.path.join(ROOT, "microtipi_b200", "csrc", "BUILD_COMMIT")).read().strip() or None
+    except OSError:
         return None
 
 
