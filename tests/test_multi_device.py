@@ -68,6 +68,23 @@ def test_multi_handle_matches_oracle(lib, N, Nz, devices, single):
     m.close()
 
 
+def test_multi_handle_with_chunked_and_staged_host_paths(lib, monkeypatch):
+    """The children of a multi-device handle move their slabs in plane chunks and, for pageable arrays, through their own
+    staging threads (one host thread per device, each with its workers): same results through the same calls."""
+    monkeypatch.setenv("WFM_HOST_CHUNKS", "2")
+    monkeypatch.setenv("WFM_HOST_CHUNK_MIN_BYTES", "1")
+    ref, m, q = multi_case(lib, 32, 19, [0, 1, 2], False)
+    m.close()
+    monkeypatch.setenv("WFM_FORCE_STAGED", "1")
+    monkeypatch.setenv("WFM_STAGED_MIN_BYTES", "1")
+    monkeypatch.setenv("WFM_HOST_THREADS", "2")
+    monkeypatch.setenv("WFM_HOST_SHARE_BYTES", "4000")
+    ref, m, q = multi_case(lib, 32, 19, [1, 0], False)
+    m.close()
+    ref, m, q = multi_case(lib, 32, 9, [0, 1, 2], True)
+    m.close()
+
+
 def test_multi_handle_device_resident_path(lib):
     """wfm_multi_apply_jacobian_dev: per-device q slabs, partial vectors land in slots on the first device."""
     N, Nz = 32, 7
